@@ -178,7 +178,7 @@ def test_argmax_first_index_tie_break_and_temperature(micro_oracle):
     assert r["id"] == 200
     r2 = m.process_logits(lg, tokens_cur=[5], temperature=0.5)
     assert abs(r2["logits"][200] - 6.0) < 1e-6
-    assert abs(np.exp(r["logprobs"][np.isfinite(r["logprobs"])]).sum() - 1.0) < 1e-4
+    assert abs(np.exp(r["logprobs"][np.isfinite(r["logprobs"])]).sum() - 1.0) < 1e-3  # f32 sequential sum, as upstream
 
 
 # ---- full() ------------------------------------------------------------------------------------
