@@ -210,6 +210,11 @@ typedef struct oh_timings {
 } oh_timings;
 OH_API oh_timings oh_get_timings(oh_state* state);
 
+/* which mat-mul kernel the state uses: "tcgen05" (16-bit modes), "simt-f32" (parity mode) or "simt" (OH_GEMM=simt);
+ * and the relative L2 error the tcgen05 kernel showed against the SIMT kernel in the start-up self-test (-1 if not run) */
+OH_API const char* oh_gemm_backend(oh_state* state);
+OH_API float oh_gemm_selftest_error(void);
+
 /* run the library on a caller-provided CUDA stream (cudaStream_t as void*); NULL = the state's own */
 OH_API int oh_state_set_stream(oh_state* state, void* cuda_stream);
 

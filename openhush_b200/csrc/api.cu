@@ -1,0 +1,414 @@
+// extern "C" surface of libohwhisper.so — see include/oh_whisper.h for the whisper.h symbol each entry replaces.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include "engine.h"
+
+namespace oh {
+const std::string& get_error();
+}
+using namespace oh;
+
+static float g_selftest_err = -1.0f;
+
+static int select_device(oh_context* ctx) { return cudaSetDevice(ctx->params.gpu_device) == cudaSuccess ? OH_OK : OH_ERR_CUDA; }
+
+extern "C" {
+
+OH_API const char* oh_last_error(void) { return get_error().c_str(); }
+
+OH_API oh_context_params oh_context_default_params(void) {
+    oh_context_params p;
+    p.use_gpu = 1;
+    p.flash_attn = 0;
+    p.gpu_device = 0;
+    p.compute_type = OH_COMPUTE_F16;
+    p.max_batch = 1;
+    return p;
+}
+
+OH_API oh_context* oh_init_from_file(const char* path_model, oh_context_params params) {
+    set_error("");
+    if (!path_model) {
+        set_error("null model path");
+        return nullptr;
+    }
+    if (!params.use_gpu) {
+        set_error("use_gpu=false: this library has no CPU path");
+        return nullptr;
+    }
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0) {
+        set_error("no CUDA device available (there is no CPU fallback)");
+        return nullptr;
+    }
+    if (params.gpu_device < 0 || params.gpu_device >= n_dev) {
+        set_error("gpu_device out of range");
+        return nullptr;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, params.gpu_device) != cudaSuccess || prop.major < 10) {
+        set_error("device is not sm_100-class: the kernels are built for sm_100a only");
+        return nullptr;
+    }
+    if (params.compute_type < OH_COMPUTE_F32 || params.compute_type > OH_COMPUTE_BF16) {
+        set_error("bad compute_type");
+        return nullptr;
+    }
+    if (cudaSetDevice(params.gpu_device) != cudaSuccess) {
+        set_error("cudaSetDevice failed");
+        return nullptr;
+    }
+    // the tensor-core GEMM must prove itself against the SIMT kernel once per process before it is trusted;
+    // OH_GEMM=simt is the explicit opt-out (slow path, same results contract)
+    if (params.compute_type != OH_COMPUTE_F32) {
+        const char* gm = getenv("OH_GEMM");
+        const bool force_simt = gm && strcmp(gm, "simt") == 0;
+        static int selftest_rc = 1;  // 1 = not run
+        static float selftest_err = -1.0f;
+        if (!force_simt && selftest_rc == 1) {
+            if (!gemm_tc_available()) {
+                set_error("tcgen05 GEMM path unavailable on this device/driver (set OH_GEMM=simt to run the SIMT kernels)");
+                return nullptr;
+            }
+            selftest_rc = gemm_tc_selftest(nullptr, &selftest_err);
+            g_selftest_err = selftest_err;
+        }
+        if (!force_simt && (selftest_rc != OH_OK || !(selftest_err >= 0.0f && selftest_err < 2e-3f))) {
+            set_error("tcgen05 GEMM self-test failed: rc=" + std::to_string(selftest_rc) + " rel_err=" + std::to_string(selftest_err) + " " +
+                      get_error());
+            return nullptr;
+        }
+    }
+    Model* m = load_model(path_model, params.gpu_device, params.compute_type);
+    if (!m) return nullptr;
+    oh_context* ctx = new oh_context();
+    ctx->model = m;
+    ctx->params = params;
+    if (ctx->params.max_batch < 1) ctx->params.max_batch = 1;
+    ctx->act_type = params.compute_type == OH_COMPUTE_F32 ? DT_F32 : (params.compute_type == OH_COMPUTE_F16 ? DT_F16 : DT_BF16);
+    // FFT twiddles (double-precision evaluation, rounded once) and the periodic Hann window of A.3
+    float2 tw[kNFFT];
+    float hann[kNFFT];
+    for (int i = 0; i < kNFFT; ++i) {
+        const double th = 2.0 * M_PI * i / kNFFT;
+        tw[i] = make_float2((float)cos(th), (float)-sin(th));
+        hann[i] = 0.5f * (1.0f - cosf((2.0f * (float)M_PI * i) / kNFFT));
+    }
+    if (cudaMalloc(&ctx->d_twiddle, sizeof tw) != cudaSuccess || cudaMalloc(&ctx->d_hann, sizeof hann) != cudaSuccess ||
+        cudaMemcpy(ctx->d_twiddle, tw, sizeof tw, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(ctx->d_hann, hann, sizeof hann, cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error("cudaMalloc failed for the mel tables");
+        oh_free(ctx);
+        return nullptr;
+    }
+    return ctx;
+}
+
+OH_API oh_state* oh_init_state(oh_context* ctx) {
+    if (!ctx || !ctx->model) return nullptr;
+    if (select_device(ctx)) return nullptr;
+    oh_state* st = new oh_state();
+    st->ctx = ctx;
+    if (state_alloc(st) != OH_OK) {
+        state_release(st);
+        delete st;
+        return nullptr;
+    }
+    ctx->n_states++;
+    return st;
+}
+
+static void destroy_context(oh_context* ctx) {
+    cudaSetDevice(ctx->params.gpu_device);
+    if (ctx->d_twiddle) cudaFree(ctx->d_twiddle);
+    if (ctx->d_hann) cudaFree(ctx->d_hann);
+    delete ctx->model;
+    delete ctx;
+}
+
+OH_API void oh_free_state(oh_state* st) {
+    if (!st) return;
+    oh_context* ctx = st->ctx;
+    cudaSetDevice(ctx->params.gpu_device);
+    cudaDeviceSynchronize();
+    state_release(st);
+    delete st;
+    // whisper-rs keeps the context alive while a state exists (Arc); mirror that: a context freed first is
+    // destroyed when its last state goes
+    if (--ctx->n_states == 0 && ctx->freed) destroy_context(ctx);
+}
+
+OH_API void oh_free(oh_context* ctx) {
+    if (!ctx) return;
+    if (ctx->n_states > 0) {
+        ctx->freed = true;
+        return;
+    }
+    destroy_context(ctx);
+}
+
+OH_API oh_full_params oh_full_default_params(int strategy) {
+    oh_full_params p;
+    memset(&p, 0, sizeof p);
+    p.strategy = strategy;
+    p.n_threads = 4;
+    p.n_max_text_ctx = 16384;
+    p.no_context = 1;
+    p.suppress_blank = 1;
+    p.temperature = 0.0f;
+    p.max_initial_ts = 1.0f;
+    p.length_penalty = -1.0f;
+    p.temperature_inc = 0.2f;
+    p.entropy_thold = 2.4f;
+    p.logprob_thold = -1.0f;
+    p.no_speech_thold = 0.6f;
+    p.greedy_best_of = strategy == OH_SAMPLING_GREEDY ? 1 : -1;
+    p.beam_size = strategy == OH_SAMPLING_BEAM_SEARCH ? 5 : -1;
+    p.beam_patience = -1.0f;
+    p.language = "en";
+    return p;
+}
+
+static int full_impl(oh_context* ctx, oh_state* st, const oh_full_params& p, const float* const* samples, const int* n, int batch, bool on_device) {
+    if (!ctx || !st || st->ctx != ctx || !samples || !n) return OH_ERR_INVALID;
+    if (select_device(ctx)) return OH_ERR_CUDA;
+    set_error("");
+    for (int i = 0; i < batch; ++i)
+        if (n[i] < 0 || (!samples[i] && n[i] > 0)) return OH_ERR_INVALID;
+    int rc = run_full(st, p, samples, n, batch, on_device);
+    if (rc == OH_OK && batch == 1 && !st->items.empty()) rc = st->items[0].rc;
+    return rc;
+}
+
+OH_API int oh_full(oh_context* ctx, oh_state* st, oh_full_params params, const float* samples, int n_samples) {
+    const float* ptrs[1] = {samples};
+    int ns[1] = {n_samples};
+    return full_impl(ctx, st, params, ptrs, ns, 1, false);
+}
+OH_API int oh_full_batch(oh_context* ctx, oh_state* st, oh_full_params params, const float* const* samples, const int* n_samples, int batch) {
+    return full_impl(ctx, st, params, samples, n_samples, batch, false);
+}
+OH_API int oh_full_batch_device(oh_context* ctx, oh_state* st, oh_full_params params, const float* const* d_samples, const int* n_samples,
+                                int batch) {
+    return full_impl(ctx, st, params, d_samples, n_samples, batch, true);
+}
+
+// ---- results
+static const Item* item_of(oh_state* st, int item) {
+    if (!st || item < 0 || item >= (int)st->items.size()) return nullptr;
+    return &st->items[item];
+}
+static const Segment* seg_of(oh_state* st, int item, int i) {
+    const Item* it = item_of(st, item);
+    if (!it || i < 0 || i >= (int)it->segments.size()) return nullptr;
+    return &it->segments[i];
+}
+OH_API int oh_full_n_segments_item(oh_state* st, int item) {
+    const Item* it = item_of(st, item);
+    return it ? (int)it->segments.size() : 0;
+}
+OH_API const char* oh_full_get_segment_text_item(oh_state* st, int item, int i) {
+    const Segment* s = seg_of(st, item, i);
+    return s ? s->text.c_str() : nullptr;
+}
+OH_API int64_t oh_full_get_segment_t0_item(oh_state* st, int item, int i) {
+    const Segment* s = seg_of(st, item, i);
+    return s ? s->t0 : 0;
+}
+OH_API int64_t oh_full_get_segment_t1_item(oh_state* st, int item, int i) {
+    const Segment* s = seg_of(st, item, i);
+    return s ? s->t1 : 0;
+}
+OH_API int oh_full_n_tokens_item(oh_state* st, int item, int i) {
+    const Segment* s = seg_of(st, item, i);
+    return s ? (int)s->tokens.size() : 0;
+}
+static const TokenData* tok_of(oh_state* st, int item, int i, int j) {
+    const Segment* s = seg_of(st, item, i);
+    if (!s || j < 0 || j >= (int)s->tokens.size()) return nullptr;
+    return &s->tokens[j];
+}
+OH_API int oh_full_get_token_id_item(oh_state* st, int item, int i, int j) {
+    const TokenData* t = tok_of(st, item, i, j);
+    return t ? t->id : -1;
+}
+OH_API float oh_full_get_token_plog_item(oh_state* st, int item, int i, int j) {
+    const TokenData* t = tok_of(st, item, i, j);
+    return t ? t->plog : 0.0f;
+}
+OH_API int oh_full_get_token_tid_item(oh_state* st, int item, int i, int j) {
+    const TokenData* t = tok_of(st, item, i, j);
+    return t ? t->tid : -1;
+}
+OH_API int oh_full_n_segments(oh_state* st) { return oh_full_n_segments_item(st, 0); }
+OH_API const char* oh_full_get_segment_text(oh_state* st, int i) { return oh_full_get_segment_text_item(st, 0, i); }
+OH_API int64_t oh_full_get_segment_t0(oh_state* st, int i) { return oh_full_get_segment_t0_item(st, 0, i); }
+OH_API int64_t oh_full_get_segment_t1(oh_state* st, int i) { return oh_full_get_segment_t1_item(st, 0, i); }
+OH_API int oh_full_n_tokens(oh_state* st, int i) { return oh_full_n_tokens_item(st, 0, i); }
+OH_API int oh_full_get_token_id(oh_state* st, int i, int j) { return oh_full_get_token_id_item(st, 0, i, j); }
+OH_API float oh_full_get_token_p(oh_state* st, int i, int j) {
+    const TokenData* t = tok_of(st, 0, i, j);
+    return t ? t->p : 0.0f;
+}
+OH_API int oh_full_lang_id(oh_state* st) {
+    const Item* it = item_of(st, 0);
+    return it ? it->lang_id : -1;
+}
+
+OH_API int64_t oh_full_pack_records(oh_state* st, int64_t* out, int64_t cap) {
+    if (!st) return 0;
+    int64_t w = 0;
+    auto put = [&](int64_t v) {
+        if (out && w < cap) out[w] = v;
+        ++w;
+    };
+    for (size_t i = 0; i < st->items.size(); ++i) {
+        const Item& it = st->items[i];
+        put((int64_t)i);
+        put((int64_t)it.segments.size());
+        for (const Segment& s : it.segments) {
+            put(s.t0);
+            put(s.t1);
+            put((int64_t)s.tokens.size());
+            for (const TokenData& t : s.tokens) put(t.id);
+        }
+    }
+    return w;
+}
+
+// ---- model introspection
+OH_API int oh_n_vocab(oh_context* c) { return c->model->hp.n_vocab; }
+OH_API int oh_n_audio_ctx(oh_context* c) { return c->model->hp.n_audio_ctx; }
+OH_API int oh_n_audio_state(oh_context* c) { return c->model->hp.n_audio_state; }
+OH_API int oh_n_audio_layer(oh_context* c) { return c->model->hp.n_audio_layer; }
+OH_API int oh_n_text_ctx(oh_context* c) { return c->model->hp.n_text_ctx; }
+OH_API int oh_n_text_state(oh_context* c) { return c->model->hp.n_text_state; }
+OH_API int oh_n_text_layer(oh_context* c) { return c->model->hp.n_text_layer; }
+OH_API int oh_n_mels(oh_context* c) { return c->model->hp.n_mels; }
+OH_API int oh_is_multilingual(oh_context* c) { return c->model->vocab.is_multilingual() ? 1 : 0; }
+OH_API int oh_token_eot(oh_context* c) { return c->model->vocab.token_eot; }
+OH_API int oh_token_sot(oh_context* c) { return c->model->vocab.token_sot; }
+OH_API int oh_token_beg(oh_context* c) { return c->model->vocab.token_beg; }
+OH_API int oh_token_not(oh_context* c) { return c->model->vocab.token_not; }
+OH_API const char* oh_token_to_str(oh_context* c, int token) {
+    const Vocab& v = c->model->vocab;
+    return (token >= 0 && token < v.n_vocab) ? v.id_to_token[token].c_str() : nullptr;
+}
+OH_API int oh_lang_id(const char* lang) { return lang_id_from_code(lang); }
+
+// ---- stage entry points
+OH_API int oh_pcm_to_mel_batch(oh_context* ctx, oh_state* st, const float* const* samples, const int* n_samples, int batch, float* const* out_mel,
+                               int* out_n_len) {
+    if (!ctx || !st || st->ctx != ctx || batch < 1) return OH_ERR_INVALID;
+    if (select_device(ctx)) return OH_ERR_CUDA;
+    int rc = run_mel(st, samples, n_samples, batch, false);
+    if (rc) return rc;
+    const int n_mel = ctx->model->hp.n_mels;
+    DevBuf tmp;
+    for (int i = 0; i < batch; ++i) {
+        const Item& it = st->items[i];
+        if (out_n_len) out_n_len[i] = it.n_len;
+        if (it.rc) return it.rc;
+        if (!out_mel || !out_mel[i]) continue;
+        const size_t bytes = (size_t)n_mel * it.n_len * 4;
+        if ((rc = ensure(tmp, bytes))) return rc;
+        const int* max_key = clip_max_key(st, batch, i);
+        rc = launch_mel_normalize((const float*)st->mel_raw.p + (size_t)i * n_mel * st->mel_ld, st->mel_ld, n_mel, it.n_active, it.n_len, max_key,
+                                  (float*)tmp.p, st->stream);
+        if (rc) return rc;
+        OH_CUDA_CHECK(cudaMemcpyAsync(out_mel[i], tmp.p, bytes, cudaMemcpyDeviceToHost, st->stream));
+        OH_CUDA_CHECK(cudaStreamSynchronize(st->stream));
+    }
+    OH_CUDA_CHECK(cudaStreamSynchronize(st->stream));
+    if (tmp.p) cudaFree(tmp.p);
+    return OH_OK;
+}
+
+OH_API int oh_pcm_to_mel_device(oh_context* ctx, oh_state* st, const float* d_samples, int n_samples, int batch, float* d_out_mel) {
+    if (!ctx || !st || st->ctx != ctx || batch < 1 || !d_samples) return OH_ERR_INVALID;
+    if (select_device(ctx)) return OH_ERR_CUDA;
+    std::vector<const float*> ptrs(batch);
+    std::vector<int> ns(batch, n_samples);
+    for (int i = 0; i < batch; ++i) ptrs[i] = d_samples + (size_t)i * n_samples;
+    int rc = run_mel(st, ptrs.data(), ns.data(), batch, true);
+    if (rc) return rc;
+    if (d_out_mel) {
+        const int n_mel = ctx->model->hp.n_mels;
+        for (int i = 0; i < batch; ++i) {
+            const Item& it = st->items[i];
+            if (it.rc) return it.rc;
+            const int* max_key = clip_max_key(st, batch, i);
+            rc = launch_mel_normalize((const float*)st->mel_raw.p + (size_t)i * n_mel * st->mel_ld, st->mel_ld, n_mel, it.n_active, it.n_len, max_key,
+                                      d_out_mel + (size_t)i * n_mel * it.n_len, st->stream);
+            if (rc) return rc;
+        }
+    }
+    return OH_OK;
+}
+
+static int encode_impl(oh_context* ctx, oh_state* st, const float* d_mel, int batch, float* out_enc_host) {
+    const HParams& hp = ctx->model->hp;
+    const int T = hp.n_audio_ctx, d = hp.n_audio_state;
+    int rc;
+    if (batch > st->max_batch) return OH_ERR_INVALID;
+    if (out_enc_host && (rc = ensure(st->enc_f32, (size_t)st->enc_chunk * T * d * 4))) return rc;
+    for (int c0 = 0; c0 < batch; c0 += st->enc_chunk) {
+        const int nw = std::min(st->enc_chunk, batch - c0);
+        if ((rc = launch_window_from_mel(d_mel + (size_t)c0 * hp.n_mels * kChunkFrames, hp.n_mels, nw, st->xin.p, ctx->act_type, st->stream))) return rc;
+        if ((rc = run_encoder(st, nw, c0, out_enc_host ? (float*)st->enc_f32.p : nullptr))) return rc;
+        if (out_enc_host) {
+            OH_CUDA_CHECK(cudaMemcpyAsync(out_enc_host + (size_t)c0 * T * d, st->enc_f32.p, (size_t)nw * T * d * 4, cudaMemcpyDeviceToHost, st->stream));
+            OH_CUDA_CHECK(cudaStreamSynchronize(st->stream));
+        }
+    }
+    return OH_OK;
+}
+
+OH_API int oh_encode_batch(oh_context* ctx, oh_state* st, const float* mel_windows, int batch, float* out_enc) {
+    if (!ctx || !st || st->ctx != ctx || batch < 1 || !mel_windows) return OH_ERR_INVALID;
+    if (select_device(ctx)) return OH_ERR_CUDA;
+    const HParams& hp = ctx->model->hp;
+    DevBuf tmp;
+    const size_t bytes = (size_t)batch * hp.n_mels * kChunkFrames * 4;
+    int rc = ensure(tmp, bytes);
+    if (rc) return rc;
+    OH_CUDA_CHECK(cudaMemcpyAsync(tmp.p, mel_windows, bytes, cudaMemcpyHostToDevice, st->stream));
+    rc = encode_impl(ctx, st, (const float*)tmp.p, batch, out_enc);
+    cudaStreamSynchronize(st->stream);
+    cudaFree(tmp.p);
+    return rc;
+}
+
+OH_API int oh_encode_device(oh_context* ctx, oh_state* st, const float* d_mel_windows, int batch) {
+    if (!ctx || !st || st->ctx != ctx || batch < 1 || !d_mel_windows) return OH_ERR_INVALID;
+    if (select_device(ctx)) return OH_ERR_CUDA;
+    return encode_impl(ctx, st, d_mel_windows, batch, nullptr);
+}
+
+OH_API int oh_decode_batch(oh_context* ctx, oh_state* st, const int* tokens, int n_tokens, int n_past, int batch, float* out_logits) {
+    if (!ctx || !st || st->ctx != ctx || batch < 1 || batch > st->max_batch || !tokens || n_tokens < 1) return OH_ERR_INVALID;
+    if (n_past < 0 || n_past + n_tokens > ctx->model->hp.n_text_ctx) return OH_ERR_DECODE;
+    if (select_device(ctx)) return OH_ERR_CUDA;
+    return decode_tokens_stage(st, tokens, n_tokens, n_past, batch, out_logits);
+}
+
+OH_API const char* oh_gemm_backend(oh_state* st) {
+    if (!st) return "none";
+    if (st->ctx->act_type == DT_F32) return "simt-f32";
+    return (st->gemm_mode == 0 && gemm_tc_available()) ? "tcgen05" : "simt";
+}
+OH_API float oh_gemm_selftest_error(void) { return g_selftest_err; }
+
+OH_API oh_timings oh_get_timings(oh_state* st) { return st ? st->timings : oh_timings{}; }
+
+OH_API int oh_state_set_stream(oh_state* st, void* cuda_stream) {
+    if (!st) return OH_ERR_INVALID;
+    st->stream = cuda_stream ? (cudaStream_t)cuda_stream : st->own_stream;
+    for (auto& kv : st->step_graphs) cudaGraphExecDestroy(kv.second);  // graphs are stream-agnostic, but keep it simple
+    st->step_graphs.clear();
+    return OH_OK;
+}
+
+}  // extern "C"

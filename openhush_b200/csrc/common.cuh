@@ -1,0 +1,82 @@
+// Shared declarations of libohwhisper (product code; never includes anything from oracle/).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+namespace oh {
+
+void set_error(const std::string& msg);
+
+#define OH_CUDA_CHECK(expr)                                                                              \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess) {                                                                         \
+            ::oh::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " at " + __FILE__ + ":" + \
+                            std::to_string(__LINE__));                                                   \
+            return OH_ERR_CUDA;                                                                          \
+        }                                                                                                \
+    } while (0)
+
+constexpr int kSampleRate = 16000;
+constexpr int kNFFT = 400;
+constexpr int kHop = 160;
+constexpr int kNBins = 201;
+constexpr int kChunkFrames = 3000;  // mel frames per 30 s window
+constexpr int kHeadDim = 64;        // every Whisper size
+
+// launch counter for bench.py's gpu_launches (host side, incremented by every kernel launch wrapper)
+extern thread_local long long g_launch_count;
+#define OH_COUNT_LAUNCH() (++::oh::g_launch_count)
+
+// ---- 16-bit activation type helpers ---------------------------------------------------------------
+template <typename T>
+struct Cvt;
+template <>
+struct Cvt<float> {
+    static __device__ __forceinline__ float to_f32(float v) { return v; }
+    static __device__ __forceinline__ float from_f32(float v) { return v; }
+};
+template <>
+struct Cvt<__half> {
+    static __device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
+    static __device__ __forceinline__ __half from_f32(float v) { return __float2half_rn(v); }
+};
+template <>
+struct Cvt<__nv_bfloat16> {
+    static __device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+    static __device__ __forceinline__ __nv_bfloat16 from_f32(float v) { return __float2bfloat16_rn(v); }
+};
+
+// GELU, tanh form.  Parity mode: ggml's f16 lookup table, table built on the host with
+// tanhf exactly as ggml does.  Tensor-core modes: x * sigmoid(2u) in f32 on the 16-bit-rounded input.
+__device__ __forceinline__ float gelu_lut(float x, const uint16_t* __restrict__ lut) {
+    if (x <= -10.0f) return 0.0f;
+    if (x >= 10.0f) return x;
+    unsigned short h = __half_as_ushort(__float2half_rn(x));
+    return __half2float(__ushort_as_half(lut[h]));
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+    // 0.5 x (1 + tanh(u)) = x / (1 + exp(-2u)),  u = sqrt(2/pi) x (1 + 0.044715 x^2)
+    const float u = 0.79788456080286535588f * x * (1.0f + 0.044715f * x * x);
+    const float e = exp2f(-2.0f * 1.44269504088896340736f * u);
+    return __fdividef(x, 1.0f + e);
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace oh

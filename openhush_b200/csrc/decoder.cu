@@ -1,0 +1,463 @@
+// K7 / K8 / K9 — the bandwidth-bound kernels of one autoregressive decoder step (SURVEY.md A.4 decoder,
+// A.6 logit rules, A.7 greedy pick, A.5 per-token bookkeeping).  They replace whisper.cpp's
+// `whisper_decode_internal` + `whisper_process_logits` + `whisper_sample_token`, reached from
+// /root/reference/src/engine/whisper.rs:266.
+//
+// All per-sequence control state (position, current token, has_ts, seek_delta, result_len, failed/completed)
+// lives in device memory (DecodeSeqState) and is advanced by the K9 kernel itself, so a greedy decode is a
+// fixed sequence of launches per token with no host round trip — which is what lets the step be replayed as
+// one CUDA graph.  Rows whose `active` flag is 0 exit immediately (no KV traffic).
+#include "../../include/oh_whisper.h"
+#include "decode_rules.h"
+#include "kernels.h"
+
+namespace oh {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------- embed
+template <typename TW>
+__global__ void embed_kernel(const TW* __restrict__ emb, const float* __restrict__ pos_emb, DecodeSeqState s, int d, float* __restrict__ x) {
+    const int b = blockIdx.x;
+    if (!s.active[b]) return;
+    const int tok = s.cur_token[b], pos = s.pos[b];
+    const TW* e = emb + (size_t)tok * d;
+    const float* p = pos_emb + (size_t)pos * d;
+    for (int c = threadIdx.x; c < d; c += blockDim.x) x[(size_t)b * d + c] = Cvt<TW>::to_f32(e[c]) + p[c];
+}
+
+// ------------------------------------------------------------------------------------ K7+K8a: self attention
+// grid (heads, rows), 128 threads.  Appends k,v of the current token at cache[slot][pos], then attends over [0, pos].
+template <typename T>
+__global__ void __launch_bounds__(128) self_attention_decode_kernel(const T* __restrict__ qkv, T* __restrict__ kcache, T* __restrict__ vcache,
+                                                                    DecodeSeqState s, int d, int n_ctx, T* __restrict__ out) {
+    const int h = blockIdx.x, b = blockIdx.y;
+    if (!s.active[b]) return;
+    __shared__ float q[kHeadDim];
+    __shared__ float sc[448];
+    __shared__ float red[4];
+    __shared__ float part[2][kHeadDim];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int pos = s.pos[b], slot = s.slot[b];
+    const int n_kv = pos + 1;
+    const T* row = qkv + (size_t)b * 3 * d;
+    T* K = kcache + (size_t)slot * n_ctx * d + h * kHeadDim;
+    T* V = vcache + (size_t)slot * n_ctx * d + h * kHeadDim;
+    if (tid < kHeadDim) {
+        q[tid] = Cvt<T>::to_f32(row[h * kHeadDim + tid]);
+        K[(size_t)pos * d + tid] = row[d + h * kHeadDim + tid];
+        V[(size_t)pos * d + tid] = row[2 * d + h * kHeadDim + tid];
+    }
+    __syncthreads();
+    float mx = -INFINITY;
+    for (int j = tid; j < n_kv; j += 128) {
+        const T* kr = K + (size_t)j * d;
+        float acc = 0.0f;
+#pragma unroll 16
+        for (int c = 0; c < kHeadDim; ++c) acc = fmaf(q[c], Cvt<T>::to_f32(kr[c]), acc);
+        acc *= 0.125f;
+        sc[j] = acc;
+        mx = fmaxf(mx, acc);
+    }
+    mx = warp_max(mx);
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    __syncthreads();
+    float sum = 0.0f;
+    for (int j = tid; j < n_kv; j += 128) {
+        const float e = expf(sc[j] - mx);
+        sc[j] = e;
+        sum += e;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    const float inv = 1.0f / ((red[0] + red[1]) + (red[2] + red[3]));
+    const int c = tid & 63, half_id = tid >> 6;
+    float acc = 0.0f;
+    for (int j = half_id; j < n_kv; j += 2) {
+        const float p = Cvt<T>::to_f32(Cvt<T>::from_f32(sc[j] * inv));
+        acc = fmaf(p, Cvt<T>::to_f32(V[(size_t)j * d + c]), acc);
+    }
+    part[half_id][c] = acc;
+    __syncthreads();
+    if (tid < kHeadDim) out[(size_t)b * d + h * kHeadDim + tid] = Cvt<T>::from_f32(part[0][tid] + part[1][tid]);
+}
+
+// ----------------------------------------------------------------------------------- K8b: cross attention
+// grid (heads, rows), 128 threads.  The cross cache of a slot is [T][2d] (k | v per encoder position).  Eight
+// lanes share one key: each reads 8 consecutive elements (16 B in the 16-bit modes), so a warp instruction
+// covers 4 keys x 128 B, and 4 independent keys are in flight per thread.
+template <typename T>
+struct Vec8 {
+    float v[8];
+    __device__ __forceinline__ void load(const T* p);
+};
+template <>
+__device__ __forceinline__ void Vec8<float>::load(const float* p) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 4));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void Vec8<__half>::load(const __half* p) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(h[i]);
+        v[2 * i] = f.x;
+        v[2 * i + 1] = f.y;
+    }
+}
+template <>
+__device__ __forceinline__ void Vec8<__nv_bfloat16>::load(const __nv_bfloat16* p) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(h[i]);
+        v[2 * i] = f.x;
+        v[2 * i + 1] = f.y;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) cross_attention_decode_kernel(const T* __restrict__ q, const T* __restrict__ xkv, DecodeSeqState s, int d,
+                                                                     int Tn, T* __restrict__ out) {
+    const int h = blockIdx.x, b = blockIdx.y;
+    if (!s.active[b]) return;
+    __shared__ float sc[1504];
+    __shared__ float red[4];
+    __shared__ float part[4][kHeadDim];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int sub = lane & 7, grp = lane >> 3;
+    const int kslot = warp * 4 + grp;  // 0..15: this thread's key phase
+    const int slot = s.slot[b];
+    const size_t ld = 2 * (size_t)d;
+    const T* Kb = xkv + (size_t)slot * Tn * ld + h * kHeadDim + sub * 8;
+    const T* Vb = Kb + d;
+    float qv[8];
+    {
+        const T* qr = q + (size_t)b * d + h * kHeadDim + sub * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) qv[i] = Cvt<T>::to_f32(qr[i]) ;
+    }
+    // ---- scores
+    float mx = -INFINITY;
+    for (int j0 = kslot; j0 < Tn; j0 += 64) {
+        Vec8<T> kv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + 16 * u;
+            if (j < Tn) kv[u].load(Kb + (size_t)j * ld);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + 16 * u;
+            float acc = 0.0f;
+            if (j < Tn) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc = fmaf(qv[i], kv[u].v[i], acc);
+            }
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+            acc *= 0.125f;
+            if (j < Tn) {
+                if (sub == 0) sc[j] = acc;
+                mx = fmaxf(mx, acc);
+            }
+        }
+    }
+    mx = warp_max(mx);
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    __syncthreads();
+    float sum = 0.0f;
+    for (int j = tid; j < Tn; j += 128) {
+        const float e = expf(sc[j] - mx);
+        sc[j] = e;
+        sum += e;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    const float inv = 1.0f / ((red[0] + red[1]) + (red[2] + red[3]));
+    // ---- P.V
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = 0.0f;
+    for (int j0 = kslot; j0 < Tn; j0 += 64) {
+        Vec8<T> vv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + 16 * u;
+            if (j < Tn) vv[u].load(Vb + (size_t)j * ld);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + 16 * u;
+            if (j < Tn) {
+                const float p = Cvt<T>::to_f32(Cvt<T>::from_f32(sc[j] * inv));
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = fmaf(p, vv[u].v[i], o[i]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        o[i] += __shfl_xor_sync(0xffffffffu, o[i], 8);
+        o[i] += __shfl_xor_sync(0xffffffffu, o[i], 16);
+    }
+    if (grp == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) part[warp][sub * 8 + i] = o[i];
+    }
+    __syncthreads();
+    if (tid < kHeadDim) out[(size_t)b * d + h * kHeadDim + tid] = Cvt<T>::from_f32((part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid]));
+}
+
+// ------------------------------------------------------------------------------------------------ K9
+struct MaxIdx {
+    float v;
+    int i;
+};
+__device__ __forceinline__ MaxIdx better(MaxIdx a, MaxIdx b) {  // larger value; on ties the lower index (A.7 strict '<' update)
+    if (b.v > a.v || (b.v == a.v && b.i < a.i)) return b;
+    return a;
+}
+__device__ __forceinline__ MaxIdx warp_best(MaxIdx m) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        MaxIdx other;
+        other.v = __shfl_xor_sync(0xffffffffu, m.v, o);
+        other.i = __shfl_xor_sync(0xffffffffu, m.i, o);
+        m = better(m, other);
+    }
+    return m;
+}
+
+struct LogitCtx {
+    int is_initial, last_ts, penult_ts, has_ts, seek_delta;
+};
+__device__ __forceinline__ bool logit_masked(int i, const DecodeRules& r, const LogitCtx& c) {
+    if (i == r.tok_not) return true;
+    if (r.no_timestamps && i >= r.beg) return true;
+    if (r.suppress_blank && c.is_initial && (i == r.eot || i == r.blank)) return true;
+    if (i == r.sot || i == r.nosp || i == r.solm || i == r.translate || i == r.transcribe || i == r.prev) return true;
+    if (i > r.sot && i <= r.sot + r.n_lang) return true;
+    if (c.last_ts && (c.penult_ts ? i >= r.beg : i < r.eot)) return true;
+    if (c.is_initial && r.tid0_initial >= 0 && i > r.beg + r.tid0_initial) return true;
+    if (c.has_ts && i >= r.beg && i < r.beg + c.seek_delta / 2) return true;
+    return false;
+}
+
+constexpr int K9_THREADS = 1024;
+
+__global__ void __launch_bounds__(K9_THREADS) logits_step_kernel(const float* __restrict__ logits, int ld, DecodeSeqState s,
+                                                                const DecodeRules* __restrict__ rp, float* __restrict__ dump_logprobs,
+                                                                float* __restrict__ dump_probs) {
+    const int b = blockIdx.x;
+    if (!s.active[b]) return;
+    const DecodeRules r = *rp;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int pos = s.pos[b];
+    if (pos + 1 < s.prompt_len[b]) {  // still feeding the prompt: nothing to sample
+        if (tid == 0) {
+            s.pos[b] = pos + 1;
+            s.cur_token[b] = s.prompt[(size_t)b * kMaxPrompt + pos + 1];
+        }
+        return;
+    }
+    __shared__ MaxIdx sm_txt[32], sm_ts[32];
+    __shared__ float sm_a[32], sm_b[32];
+    const int n_gen = s.n_gen[b];
+    LogitCtx c;
+    c.is_initial = n_gen == 0;
+    const int* toks = s.tok_id + (size_t)b * kMaxGen;
+    c.last_ts = n_gen > 0 && toks[n_gen - 1] >= r.beg;
+    c.penult_ts = n_gen < 2 || toks[n_gen - 2] >= r.beg;
+    c.has_ts = s.has_ts[b];
+    c.seek_delta = s.seek_delta[b];
+    const float* row = logits + (size_t)b * ld;
+    const float temp = r.temperature;
+
+    // pass 1: masked maxima (text ids < beg, timestamp ids >= beg), first index on ties
+    MaxIdx mtxt{-INFINITY, 0x7fffffff}, mts{-INFINITY, 0x7fffffff};
+    for (int i = tid; i < r.n_vocab; i += K9_THREADS) {
+        if (logit_masked(i, r, c)) continue;
+        float v = row[i];
+        if (temp > 0.0f) v = v / temp;
+        MaxIdx m{v, i};
+        if (i < r.beg) mtxt = better(mtxt, m);
+        else mts = better(mts, m);
+    }
+    mtxt = warp_best(mtxt);
+    mts = warp_best(mts);
+    if (lane == 0) {
+        sm_txt[warp] = mtxt;
+        sm_ts[warp] = mts;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        mtxt = warp_best(sm_txt[lane]);
+        mts = warp_best(sm_ts[lane]);
+        if (lane == 0) {
+            sm_txt[0] = mtxt;
+            sm_ts[0] = mts;
+        }
+    }
+    __syncthreads();
+    mtxt = sm_txt[0];
+    mts = sm_ts[0];
+    const float mx = fmaxf(mtxt.v, mts.v);
+    __syncthreads();
+
+    // pass 2: sum exp(x - max) over text and over timestamps
+    float st = 0.0f, sts = 0.0f;
+    for (int i = tid; i < r.n_vocab; i += K9_THREADS) {
+        if (logit_masked(i, r, c)) continue;
+        float v = row[i];
+        if (temp > 0.0f) v = v / temp;
+        const float e = expf(v - mx);
+        if (i < r.beg) st += e;
+        else sts += e;
+    }
+    st = warp_sum(st);
+    sts = warp_sum(sts);
+    if (lane == 0) {
+        sm_a[warp] = st;
+        sm_b[warp] = sts;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        st = warp_sum(sm_a[lane]);
+        sts = warp_sum(sm_b[lane]);
+        if (lane == 0) {
+            sm_a[0] = st;
+            sm_b[0] = sts;
+        }
+    }
+    __syncthreads();
+    st = sm_a[0];
+    sts = sm_b[0];
+    const float lse = logf(st + sts) + mx;
+    const float ts_logprob = sts > 0.0f ? logf(sts) + mx - lse : -INFINITY;
+    const float max_text_logprob = mtxt.v > -INFINITY ? mtxt.v - lse : -INFINITY;
+    const bool force_ts = ts_logprob > max_text_logprob;
+
+    if (dump_probs) {  // t > 0: the host samples (std::mt19937 + std::discrete_distribution, A.7)
+        float* lp = dump_logprobs + (size_t)b * ld;
+        float* pr = dump_probs + (size_t)b * ld;
+        for (int i = tid; i < r.n_vocab; i += K9_THREADS) {
+            float l = -INFINITY;
+            if (!logit_masked(i, r, c) && !(force_ts && i < r.beg)) {
+                float v = row[i];
+                if (temp > 0.0f) v = v / temp;
+                l = v - lse;
+            }
+            lp[i] = l;
+            pr[i] = l == -INFINITY ? 0.0f : expf(l);
+        }
+        return;
+    }
+
+    if (tid == 0) {
+        // greedy pick (A.7): first index with maximal probability
+        int id = 0;
+        float p = 0.0f, plog = 0.0f;
+        MaxIdx pick{-INFINITY, 0x7fffffff};
+        if (force_ts) pick = mts;
+        else pick = better(mtxt, mts);
+        if (pick.v > -INFINITY) {
+            const float lpv = pick.v - lse;
+            const float pv = expf(lpv);
+            if (pv > 0.0f) {
+                id = pick.i;
+                p = pv;
+                plog = lpv;
+            }
+        }
+        int tid_tok = 0;
+        float pt = 0.0f, ptsum = 0.0f;
+        if (mts.v > -INFINITY) {
+            const float pmax = expf(mts.v - lse);
+            ptsum = expf(ts_logprob);
+            if (pmax > 0.0f) tid_tok = mts.i;
+            pt = pmax / (ptsum + 1e-10f);
+        }
+        if (id >= r.beg) {
+            tid_tok = id;
+            pt = p;
+        }
+        const int i = n_gen;
+        const size_t o = (size_t)b * kMaxGen + i;
+        s.tok_id[o] = id;
+        s.tok_tid[o] = tid_tok;
+        s.tok_p[o] = p;
+        s.tok_plog[o] = plog;
+        s.tok_pt[o] = pt;
+        s.tok_ptsum[o] = ptsum;
+        s.n_gen[b] = i + 1;
+        SeqFlags f{c.has_ts, c.seek_delta, s.result_len[b], 0, 0};
+        const bool live = apply_token_rules(f, id, i, s.seek[b], s.seek_end[b], r.beg, r.eot, r.max_tokens, r.no_timestamps, r.single_segment, r.n_max);
+        s.has_ts[b] = f.has_ts;
+        s.seek_delta[b] = f.seek_delta;
+        s.result_len[b] = f.result_len;
+        s.failed[b] = f.failed;
+        s.completed[b] = f.completed;
+        if (live) {
+            s.cur_token[b] = id;
+            s.pos[b] = pos + 1;
+        } else {
+            s.active[b] = 0;
+            atomicSub(s.n_active_total, 1);
+        }
+    }
+}
+
+}  // namespace
+
+int launch_embed(const void* tok_emb, int w_type, const float* pos_emb, const DecodeSeqState& s, int rows, int d, float* x, cudaStream_t st) {
+    if (w_type == DT_BF16) embed_kernel<__nv_bfloat16><<<rows, 256, 0, st>>>((const __nv_bfloat16*)tok_emb, pos_emb, s, d, x);
+    else embed_kernel<__half><<<rows, 256, 0, st>>>((const __half*)tok_emb, pos_emb, s, d, x);
+    OH_COUNT_LAUNCH();
+    OH_CUDA_CHECK(cudaGetLastError());
+    return OH_OK;
+}
+
+int launch_self_attention_decode(const void* qkv, void* kcache, void* vcache, int type, const DecodeSeqState& s, int rows, int d, int n_ctx,
+                                 void* out, cudaStream_t st) {
+    dim3 grid(d / kHeadDim, rows);
+    if (n_ctx > 448) return OH_ERR_INVALID;
+    if (type == DT_F32) self_attention_decode_kernel<float><<<grid, 128, 0, st>>>((const float*)qkv, (float*)kcache, (float*)vcache, s, d, n_ctx, (float*)out);
+    else if (type == DT_F16) self_attention_decode_kernel<__half><<<grid, 128, 0, st>>>((const __half*)qkv, (__half*)kcache, (__half*)vcache, s, d, n_ctx, (__half*)out);
+    else self_attention_decode_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)kcache, (__nv_bfloat16*)vcache, s, d, n_ctx, (__nv_bfloat16*)out);
+    OH_COUNT_LAUNCH();
+    OH_CUDA_CHECK(cudaGetLastError());
+    return OH_OK;
+}
+
+int launch_cross_attention_decode(const void* q, const void* xkv, int type, const DecodeSeqState& s, int rows, int d, int T, void* out,
+                                  cudaStream_t st) {
+    dim3 grid(d / kHeadDim, rows);
+    if (T > 1504) return OH_ERR_INVALID;
+    if (type == DT_F32) cross_attention_decode_kernel<float><<<grid, 128, 0, st>>>((const float*)q, (const float*)xkv, s, d, T, (float*)out);
+    else if (type == DT_F16) cross_attention_decode_kernel<__half><<<grid, 128, 0, st>>>((const __half*)q, (const __half*)xkv, s, d, T, (__half*)out);
+    else cross_attention_decode_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)xkv, s, d, T, (__nv_bfloat16*)out);
+    OH_COUNT_LAUNCH();
+    OH_CUDA_CHECK(cudaGetLastError());
+    return OH_OK;
+}
+
+int launch_logits_step(const float* logits, int ld, const DecodeSeqState& s, const DecodeRules* r, int rows, float* dump_logprobs, float* dump_probs,
+                       cudaStream_t st) {
+    logits_step_kernel<<<rows, K9_THREADS, 0, st>>>(logits, ld, s, r, dump_logprobs, dump_probs);
+    OH_COUNT_LAUNCH();
+    OH_CUDA_CHECK(cudaGetLastError());
+    return OH_OK;
+}
+
+}  // namespace oh

@@ -1,0 +1,887 @@
+// Buffers, stage runners (mel / encoder / decoder step) and the batched full() driver.
+//
+// run_full() is the device-side replacement of whisper.cpp's `whisper_full_with_state` (SURVEY.md A.5, A.7,
+// A.8), reached from /root/reference/src/engine/whisper.rs:266.  Each batch item is one independent call of
+// the reference; items advance window by window in lock-step rounds:
+//   gather mel window at item.seek -> encoder -> cross-KV -> greedy decode (device state machine, CUDA graph)
+//   -> host scoring / temperature fallback -> segments -> seek += seek_delta.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include "decode_rules.h"
+#include "engine.h"
+
+namespace oh {
+
+thread_local long long g_launch_count = 0;
+static thread_local std::string g_error;
+void set_error(const std::string& msg) { g_error = msg; }
+const std::string& get_error() { return g_error; }
+
+int ensure(DevBuf& b, size_t bytes) {
+    if (b.bytes >= bytes && b.p) return OH_OK;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.bytes = 0;
+    OH_CUDA_CHECK(cudaMalloc(&b.p, bytes));
+    OH_CUDA_CHECK(cudaMemset(b.p, 0, bytes));
+    b.bytes = bytes;
+    return OH_OK;
+}
+static void release(DevBuf& b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.bytes = 0;
+}
+
+static inline size_t rup(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- layout of the DecodeSeqState block (ints unless noted), rows = max_batch -------------------------
+namespace seqlay {
+enum { SLOT, ACTIVE, POS, CUR, PLEN, NGEN, HAS_TS, SDELTA, RLEN, FAILED, COMPLETED, SEEK, SEEKEND, N_SCALARS };
+}
+struct SeqLayout {
+    size_t rows, prompt_off, tok_off[6], counter_off, total_words;
+    explicit SeqLayout(size_t r) : rows(r) {
+        size_t o = seqlay::N_SCALARS * rows;
+        prompt_off = o;
+        o += rows * kMaxPrompt;
+        for (int i = 0; i < 6; ++i) {
+            tok_off[i] = o;
+            o += rows * kMaxGen;
+        }
+        counter_off = o;
+        total_words = o + 4;
+    }
+};
+
+static DecodeSeqState seq_view(int32_t* base, const SeqLayout& L) {
+    DecodeSeqState s;
+    using namespace seqlay;
+    s.slot = base + SLOT * L.rows;
+    s.active = base + ACTIVE * L.rows;
+    s.pos = base + POS * L.rows;
+    s.cur_token = base + CUR * L.rows;
+    s.prompt_len = base + PLEN * L.rows;
+    s.n_gen = base + NGEN * L.rows;
+    s.has_ts = base + HAS_TS * L.rows;
+    s.seek_delta = base + SDELTA * L.rows;
+    s.result_len = base + RLEN * L.rows;
+    s.failed = base + FAILED * L.rows;
+    s.completed = base + COMPLETED * L.rows;
+    s.seek = base + SEEK * L.rows;
+    s.seek_end = base + SEEKEND * L.rows;
+    s.prompt = base + L.prompt_off;
+    s.tok_id = base + L.tok_off[0];
+    s.tok_tid = base + L.tok_off[1];
+    s.tok_p = reinterpret_cast<float*>(base + L.tok_off[2]);
+    s.tok_plog = reinterpret_cast<float*>(base + L.tok_off[3]);
+    s.tok_pt = reinterpret_cast<float*>(base + L.tok_off[4]);
+    s.tok_ptsum = reinterpret_cast<float*>(base + L.tok_off[5]);
+    s.n_active_total = base + L.counter_off;
+    return s;
+}
+
+int state_alloc(oh_state* st) {
+    const Model& m = *st->ctx->model;
+    const HParams& hp = m.hp;
+    const int d = hp.n_audio_state, C = hp.n_mels, T = hp.n_audio_ctx, L = hp.n_text_layer, V = hp.n_vocab;
+    st->esz = st->ctx->act_type == DT_F32 ? 4 : 2;
+    const size_t e = st->esz;
+    st->max_batch = std::max(1, st->ctx->params.max_batch);
+    int chunk = std::min(st->max_batch, 64);
+    if (const char* s = getenv("OH_ENC_CHUNK")) chunk = std::max(1, std::min(st->max_batch, atoi(s)));
+    st->enc_chunk = chunk;
+    if (const char* s = getenv("OH_GEMM")) st->gemm_mode = strcmp(s, "simt") == 0 ? 1 : 0;
+    if (const char* s = getenv("OH_ATTN")) st->attn_mode = strcmp(s, "simple") == 0 ? 1 : 0;
+    if (const char* s = getenv("OH_GRAPHS")) st->use_graphs = atoi(s) != 0;
+
+    OH_CUDA_CHECK(cudaStreamCreateWithFlags(&st->own_stream, cudaStreamNonBlocking));
+    st->stream = st->own_stream;
+    for (auto& ev : st->ev) OH_CUDA_CHECK(cudaEventCreate(&ev));
+
+    const size_t W = chunk;
+    int rc;
+    if ((rc = ensure(st->xin, W * (kChunkFrames + 2) * C * e))) return rc;
+    if ((rc = ensure(st->x1, W * (kChunkFrames + 2) * d * e))) return rc;
+    if ((rc = ensure(st->x, W * T * d * 4))) return rc;
+    if ((rc = ensure(st->h, W * T * d * e))) return rc;
+    if ((rc = ensure(st->qkv, W * T * 3 * d * e))) return rc;
+    if ((rc = ensure(st->hid, W * T * 4 * d * e))) return rc;
+    const size_t S = st->max_batch;
+    if ((rc = ensure(st->xkv, (size_t)L * S * T * 2 * d * e))) return rc;
+    if ((rc = ensure(st->kself, (size_t)L * S * hp.n_text_ctx * d * e))) return rc;
+    if ((rc = ensure(st->vself, (size_t)L * S * hp.n_text_ctx * d * e))) return rc;
+    if ((rc = ensure(st->dx, S * d * 4))) return rc;
+    if ((rc = ensure(st->dh, S * d * e))) return rc;
+    if ((rc = ensure(st->dqkv, S * 3 * d * e))) return rc;
+    if ((rc = ensure(st->datt, S * d * e))) return rc;
+    if ((rc = ensure(st->dq, S * d * e))) return rc;
+    if ((rc = ensure(st->dhid, S * 4 * d * e))) return rc;
+    st->ld_logits = (int)rup(V, 8);
+    if ((rc = ensure(st->logits, S * st->ld_logits * 4))) return rc;
+    SeqLayout lay(S);
+    if ((rc = ensure(st->seq_dev, lay.total_words * 4))) return rc;
+    st->seq = seq_view((int32_t*)st->seq_dev.p, lay);
+    if ((rc = ensure(st->rules_dev, sizeof(DecodeRules)))) return rc;
+    st->pinned_bytes = lay.total_words * 4 + 4096;
+    OH_CUDA_CHECK(cudaMallocHost(&st->pinned, st->pinned_bytes));
+    memset(st->pinned, 0, st->pinned_bytes);
+    st->rngs.assign(S, std::mt19937(0));
+    st->items.clear();
+    return OH_OK;
+}
+
+void state_release(oh_state* st) {
+    for (auto& kv : st->step_graphs) cudaGraphExecDestroy(kv.second);
+    st->step_graphs.clear();
+    DevBuf* all[] = {&st->pcm_stage, &st->mel_raw, &st->clip_meta, &st->xin, &st->x1, &st->x, &st->h, &st->qkv, &st->hid, &st->enc_f32,
+                     &st->xkv, &st->kself, &st->vself, &st->dx, &st->dh, &st->dqkv, &st->datt, &st->dq, &st->dhid, &st->logits,
+                     &st->dump_lp, &st->dump_p, &st->seq_dev, &st->rules_dev};
+    for (DevBuf* b : all) release(*b);
+    if (st->pinned) cudaFreeHost(st->pinned);
+    st->pinned = nullptr;
+    for (auto& ev : st->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (st->own_stream) cudaStreamDestroy(st->own_stream);
+    st->own_stream = nullptr;
+}
+
+// ------------------------------------------------------------------------------------------------ mel
+// clip_meta layout (device): [pcm ptrs (8 B each)] [n_samples] [n_active] [n_len] [max_key] [clip_of_slot] [seek_of_slot]
+struct ClipMeta {
+    const float** pcm;
+    int *n_samples, *n_active, *n_len, *max_key, *clip_of_slot, *seek_of_slot;
+};
+static ClipMeta clip_meta_view(void* base, size_t cap) {
+    ClipMeta c;
+    char* p = (char*)base;
+    c.pcm = (const float**)p;
+    p += cap * 8;
+    c.n_samples = (int*)p;
+    p += cap * 4;
+    c.n_active = (int*)p;
+    p += cap * 4;
+    c.n_len = (int*)p;
+    p += cap * 4;
+    c.max_key = (int*)p;
+    p += cap * 4;
+    c.clip_of_slot = (int*)p;
+    p += cap * 4;
+    c.seek_of_slot = (int*)p;
+    return c;
+}
+static size_t clip_meta_bytes(size_t cap) { return cap * (8 + 6 * 4); }
+
+int run_mel(oh_state* st, const float* const* pcm, const int* n, int batch, bool pcm_on_device) {
+    const Model& m = *st->ctx->model;
+    const int n_mel = m.hp.n_mels;
+    st->items.assign(batch, Item());
+    size_t stage_floats = 0;
+    int max_active = 0;
+    std::vector<size_t> off(batch);
+    for (int i = 0; i < batch; ++i) {
+        Item& it = st->items[i];
+        it.n_samples = n[i];
+        if (n[i] <= kNFFT / 2) {  // cannot reflect-pad: whisper.cpp reports "failed to compute log mel spectrogram"
+            it.rc = OH_ERR_MEL;
+            it.done = true;
+            it.n_len = it.n_len_org = it.n_active = 0;
+        } else {
+            it.n_len = (n[i] + kSampleRate * 30) / kHop;
+            it.n_len_org = 1 + (n[i] + kNFFT / 2 - kNFFT) / kHop;
+            it.n_active = std::min((n[i] + kNFFT / 2) / kHop + 1, it.n_len);
+        }
+        off[i] = stage_floats;
+        stage_floats += rup((size_t)std::max(n[i], 0), 4);
+        max_active = std::max(max_active, it.n_active);
+    }
+    st->mel_clips = batch;
+    st->mel_ld = (int)rup(std::max(max_active, 1), 32);
+    int rc;
+    const size_t cap = std::max<size_t>(batch, st->max_batch);
+    if ((rc = ensure(st->clip_meta, clip_meta_bytes(cap)))) return rc;
+    if ((rc = ensure(st->mel_raw, (size_t)batch * n_mel * st->mel_ld * 4))) return rc;
+    ClipMeta cm = clip_meta_view(st->clip_meta.p, cap);
+
+    std::vector<const float*> ptrs(batch);
+    std::vector<int> ns(batch), na(batch), nl(batch);
+    if (!pcm_on_device) {
+        if ((rc = ensure(st->pcm_stage, std::max<size_t>(stage_floats, 4) * 4))) return rc;
+        for (int i = 0; i < batch; ++i) {
+            ptrs[i] = (const float*)st->pcm_stage.p + off[i];
+            if (n[i] > 0)
+                OH_CUDA_CHECK(cudaMemcpyAsync((float*)st->pcm_stage.p + off[i], pcm[i], (size_t)n[i] * 4, cudaMemcpyHostToDevice, st->stream));
+        }
+    } else {
+        for (int i = 0; i < batch; ++i) ptrs[i] = pcm[i];
+    }
+    for (int i = 0; i < batch; ++i) {
+        ns[i] = st->items[i].n_samples;
+        na[i] = st->items[i].n_active;
+        nl[i] = st->items[i].n_len;
+    }
+    OH_CUDA_CHECK(cudaMemcpyAsync(cm.pcm, ptrs.data(), batch * 8, cudaMemcpyHostToDevice, st->stream));
+    OH_CUDA_CHECK(cudaMemcpyAsync(cm.n_samples, ns.data(), batch * 4, cudaMemcpyHostToDevice, st->stream));
+    OH_CUDA_CHECK(cudaMemcpyAsync(cm.n_active, na.data(), batch * 4, cudaMemcpyHostToDevice, st->stream));
+    OH_CUDA_CHECK(cudaMemcpyAsync(cm.n_len, nl.data(), batch * 4, cudaMemcpyHostToDevice, st->stream));
+    // the vectors above must outlive the async copies from pageable memory: those are staged synchronously by the runtime
+    MelArgs a;
+    a.pcm = cm.pcm;
+    a.n_samples = cm.n_samples;
+    a.n_active = cm.n_active;
+    a.raw = (float*)st->mel_raw.p;
+    a.ld = st->mel_ld;
+    a.max_key = cm.max_key;
+    a.n_mel = n_mel;
+    a.twiddle = st->ctx->d_twiddle;
+    a.hann = st->ctx->d_hann;
+    a.filt_start = m.mel.start;
+    a.filt_count = m.mel.count;
+    a.filt_off = m.mel.offset;
+    a.filt_w = m.mel.weights;
+    a.n_filt_w = m.mel.n_weights;
+    if (max_active > 0) {
+        if ((rc = launch_mel_frames(a, batch, max_active, st->stream))) return rc;
+    }
+    return OH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ GEMM dispatch
+static int gemm(oh_state* st, GemmArgs g) {
+    const Model& m = *st->ctx->model;
+    const int act = st->ctx->act_type;
+    g.w_type = m.compute_type == OH_COMPUTE_BF16 ? DT_BF16 : DT_F16;
+    g.lut = m.gelu_lut;
+    g.round_type = act;
+    if (g.gelu != GELU_NONE) g.gelu = act == DT_F32 ? GELU_LUT : GELU_FAST;
+    if (act != DT_F32 && st->gemm_mode == 0 && gemm_tc_available()) {
+        int rc = launch_gemm_tc(g, st->stream);
+        if (rc != OH_ERR_UNSUPPORTED) return rc;
+    }
+    return launch_gemm_simt(g, st->stream);
+}
+
+// ------------------------------------------------------------------------------------------------ encoder
+int run_encoder(oh_state* st, int nw, int slot0, float* d_enc_f32_out) {
+    const Model& m = *st->ctx->model;
+    const HParams& hp = m.hp;
+    const int d = hp.n_audio_state, C = hp.n_mels, T = hp.n_audio_ctx, act = st->ctx->act_type;
+    const size_t e = st->esz;
+    cudaStream_t s = st->stream;
+    int rc;
+    char* x1 = (char*)st->x1.p;
+    float* x = (float*)st->x.p;
+    {  // conv1: k3 s1 p1 as a mat-mul over 3-row views of the zero-framed channel-last window; + bias, GELU
+        GemmArgs g;
+        g.A = st->xin.p;
+        g.a_type = act;
+        g.a_bstride = (long long)(kChunkFrames + 2) * C;
+        g.lda = C;
+        g.batch = nw;
+        g.rows = kChunkFrames;
+        g.W = m.conv1.w;
+        g.N = d;
+        g.K = 3 * C;
+        g.bias = m.conv1.b;
+        g.C = x1 + (size_t)d * e;  // row 1 of each window (row 0 and row 3001 stay zero)
+        g.c_type = act;
+        g.c_bstride = (long long)(kChunkFrames + 2) * d;
+        g.ldc = d;
+        g.gelu = 1;
+        if ((rc = gemm(st, g))) return rc;
+    }
+    {  // conv2: k3 s2 p1: row i of the output reads rows 2i-1..2i+1 = 3d contiguous elements starting at padded row 2i
+        GemmArgs g;
+        g.A = x1;
+        g.a_type = act;
+        g.a_bstride = (long long)(kChunkFrames + 2) * d;
+        g.lda = 2 * d;
+        g.batch = nw;
+        g.rows = T;
+        g.W = m.conv2.w;
+        g.N = d;
+        g.K = 3 * d;
+        g.bias = m.conv2.b;
+        g.C = x;
+        g.c_type = DT_F32;
+        g.c_bstride = (long long)T * d;
+        g.ldc = d;
+        g.gelu = 1;
+        g.R = m.enc_pos;  // + positional embedding, broadcast over the batch
+        g.r_bstride = 0;
+        g.ldr = d;
+        if ((rc = gemm(st, g))) return rc;
+    }
+    const int M = nw * T;
+    for (const EncLayer& L : m.enc) {
+        if ((rc = launch_layernorm(x, M, d, L.ln1.w, L.ln1.b, st->h.p, act, s))) return rc;
+        GemmArgs g;
+        g.A = st->h.p; g.a_type = act; g.lda = d; g.rows = M;
+        g.W = L.qkv.w; g.N = 3 * d; g.K = d; g.bias = L.qkv.b;
+        g.C = st->qkv.p; g.c_type = act; g.ldc = 3 * d;
+        if ((rc = gemm(st, g))) return rc;
+        if (act != DT_F32 && st->attn_mode == 0) rc = launch_encoder_attention_mma(st->qkv.p, st->h.p, act, nw, T, d, s);
+        else rc = launch_encoder_attention_simple(st->qkv.p, st->h.p, act, nw, T, d, s);
+        if (rc) return rc;
+        GemmArgs o;
+        o.A = st->h.p; o.a_type = act; o.lda = d; o.rows = M;
+        o.W = L.out.w; o.N = d; o.K = d; o.bias = L.out.b;
+        o.C = x; o.c_type = DT_F32; o.ldc = d; o.R = x; o.ldr = d;
+        if ((rc = gemm(st, o))) return rc;
+        if ((rc = launch_layernorm(x, M, d, L.ln2.w, L.ln2.b, st->h.p, act, s))) return rc;
+        GemmArgs f0;
+        f0.A = st->h.p; f0.a_type = act; f0.lda = d; f0.rows = M;
+        f0.W = L.mlp0.w; f0.N = 4 * d; f0.K = d; f0.bias = L.mlp0.b;
+        f0.C = st->hid.p; f0.c_type = act; f0.ldc = 4 * d; f0.gelu = 1;
+        if ((rc = gemm(st, f0))) return rc;
+        GemmArgs f2;
+        f2.A = st->hid.p; f2.a_type = act; f2.lda = 4 * d; f2.rows = M;
+        f2.W = L.mlp2.w; f2.N = d; f2.K = 4 * d; f2.bias = L.mlp2.b;
+        f2.C = x; f2.c_type = DT_F32; f2.ldc = d; f2.R = x; f2.ldr = d;
+        if ((rc = gemm(st, f2))) return rc;
+    }
+    if ((rc = launch_layernorm(x, M, d, m.ln_post.w, m.ln_post.b, st->h.p, act, s))) return rc;
+    if (d_enc_f32_out) {
+        if ((rc = launch_layernorm(x, M, d, m.ln_post.w, m.ln_post.b, d_enc_f32_out, DT_F32, s))) return rc;
+    }
+    // cross-attention K/V of every decoder layer, straight into the slots' caches: [L][slots][T][2d]
+    for (int l = 0; l < hp.n_text_layer; ++l) {
+        const DecLayer& D = m.dec[l];
+        GemmArgs g;
+        g.A = st->h.p; g.a_type = act; g.lda = d; g.rows = M;
+        g.W = D.xkv.w; g.N = 2 * d; g.K = d; g.bias = D.xkv.b;
+        g.C = (char*)st->xkv.p + ((size_t)l * st->max_batch + slot0) * T * 2 * d * e;
+        g.c_type = act; g.ldc = 2 * d;
+        if ((rc = gemm(st, g))) return rc;
+    }
+    return OH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ decoder step
+static int decode_step_launch(oh_state* st, int rows, bool with_k9, bool dump) {
+    const Model& m = *st->ctx->model;
+    const HParams& hp = m.hp;
+    const int d = hp.n_text_state, T = hp.n_audio_ctx, act = st->ctx->act_type, NC = hp.n_text_ctx;
+    const size_t e = st->esz;
+    cudaStream_t s = st->stream;
+    float* x = (float*)st->dx.p;
+    int rc;
+    if ((rc = launch_embed(m.tok_emb.w, m.compute_type == OH_COMPUTE_BF16 ? DT_BF16 : DT_F16, m.dec_pos, st->seq, rows, d, x, s))) return rc;
+    for (int l = 0; l < hp.n_text_layer; ++l) {
+        const DecLayer& D = m.dec[l];
+        if ((rc = launch_layernorm(x, rows, d, D.ln1.w, D.ln1.b, st->dh.p, act, s))) return rc;
+        GemmArgs g;
+        g.A = st->dh.p; g.a_type = act; g.lda = d; g.rows = rows;
+        g.W = D.qkv.w; g.N = 3 * d; g.K = d; g.bias = D.qkv.b;
+        g.C = st->dqkv.p; g.c_type = act; g.ldc = 3 * d;
+        if ((rc = gemm(st, g))) return rc;
+        char* kc = (char*)st->kself.p + (size_t)l * st->max_batch * NC * d * e;
+        char* vc = (char*)st->vself.p + (size_t)l * st->max_batch * NC * d * e;
+        if ((rc = launch_self_attention_decode(st->dqkv.p, kc, vc, act, st->seq, rows, d, NC, st->datt.p, s))) return rc;
+        GemmArgs o;
+        o.A = st->datt.p; o.a_type = act; o.lda = d; o.rows = rows;
+        o.W = D.out.w; o.N = d; o.K = d; o.bias = D.out.b;
+        o.C = x; o.c_type = DT_F32; o.ldc = d; o.R = x; o.ldr = d;
+        if ((rc = gemm(st, o))) return rc;
+
+        if ((rc = launch_layernorm(x, rows, d, D.lnx.w, D.lnx.b, st->dh.p, act, s))) return rc;
+        GemmArgs q;
+        q.A = st->dh.p; q.a_type = act; q.lda = d; q.rows = rows;
+        q.W = D.xq.w; q.N = d; q.K = d; q.bias = D.xq.b;
+        q.C = st->dq.p; q.c_type = act; q.ldc = d;
+        if ((rc = gemm(st, q))) return rc;
+        const char* xkv = (const char*)st->xkv.p + (size_t)l * st->max_batch * T * 2 * d * e;
+        if ((rc = launch_cross_attention_decode(st->dq.p, xkv, act, st->seq, rows, d, T, st->datt.p, s))) return rc;
+        GemmArgs xo;
+        xo.A = st->datt.p; xo.a_type = act; xo.lda = d; xo.rows = rows;
+        xo.W = D.xout.w; xo.N = d; xo.K = d; xo.bias = D.xout.b;
+        xo.C = x; xo.c_type = DT_F32; xo.ldc = d; xo.R = x; xo.ldr = d;
+        if ((rc = gemm(st, xo))) return rc;
+
+        if ((rc = launch_layernorm(x, rows, d, D.ln2.w, D.ln2.b, st->dh.p, act, s))) return rc;
+        GemmArgs f0;
+        f0.A = st->dh.p; f0.a_type = act; f0.lda = d; f0.rows = rows;
+        f0.W = D.mlp0.w; f0.N = 4 * d; f0.K = d; f0.bias = D.mlp0.b;
+        f0.C = st->dhid.p; f0.c_type = act; f0.ldc = 4 * d; f0.gelu = 1;
+        if ((rc = gemm(st, f0))) return rc;
+        GemmArgs f2;
+        f2.A = st->dhid.p; f2.a_type = act; f2.lda = 4 * d; f2.rows = rows;
+        f2.W = D.mlp2.w; f2.N = d; f2.K = 4 * d; f2.bias = D.mlp2.b;
+        f2.C = x; f2.c_type = DT_F32; f2.ldc = d; f2.R = x; f2.ldr = d;
+        if ((rc = gemm(st, f2))) return rc;
+    }
+    if ((rc = launch_layernorm(x, rows, d, m.ln.w, m.ln.b, st->dh.p, act, s))) return rc;
+    GemmArgs lg;
+    lg.A = st->dh.p; lg.a_type = act; lg.lda = d; lg.rows = rows;
+    lg.W = m.tok_emb.w; lg.N = hp.n_vocab; lg.K = d;
+    lg.C = st->logits.p; lg.c_type = DT_F32; lg.ldc = st->ld_logits;
+    if ((rc = gemm(st, lg))) return rc;
+    if (with_k9) {
+        float* lp = nullptr;
+        float* pr = nullptr;
+        if (dump) {
+            if ((rc = ensure(st->dump_lp, (size_t)st->max_batch * st->ld_logits * 4))) return rc;
+            if ((rc = ensure(st->dump_p, (size_t)st->max_batch * st->ld_logits * 4))) return rc;
+            lp = (float*)st->dump_lp.p;
+            pr = (float*)st->dump_p.p;
+        }
+        if ((rc = launch_logits_step((const float*)st->logits.p, st->ld_logits, st->seq, (const DecodeRules*)st->rules_dev.p, rows, lp, pr, s)))
+            return rc;
+    }
+    return OH_OK;
+}
+
+int run_decode_step(oh_state* st, int rows, bool dump_probs) { return decode_step_launch(st, rows, true, dump_probs); }
+
+static int run_decode_step_graph(oh_state* st, int rows) {
+    if (!st->use_graphs) return decode_step_launch(st, rows, true, false);
+    auto it = st->step_graphs.find(rows);
+    if (it == st->step_graphs.end()) {
+        // first use of this row count: one direct step (sets kernel attributes, faults in lazily allocated
+        // buffers), capture on the second, replay from then on
+        if (!st->warmed_rows.count(rows)) {
+            st->warmed_rows.insert(rows);
+            return decode_step_launch(st, rows, true, false);
+        }
+        cudaGraph_t graph = nullptr;
+        const long long launches_before = g_launch_count;
+        OH_CUDA_CHECK(cudaStreamBeginCapture(st->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = decode_step_launch(st, rows, true, false);
+        cudaError_t ce = cudaStreamEndCapture(st->stream, &graph);
+        g_launch_count = launches_before;  // nothing ran during capture
+        if (rc) {
+            if (graph) cudaGraphDestroy(graph);
+            return rc;
+        }
+        OH_CUDA_CHECK(ce);
+        cudaGraphExec_t exec = nullptr;
+        OH_CUDA_CHECK(cudaGraphInstantiate(&exec, graph, 0));
+        cudaGraphDestroy(graph);
+        it = st->step_graphs.emplace(rows, exec).first;
+    }
+    OH_CUDA_CHECK(cudaGraphLaunch(it->second, st->stream));
+    g_launch_count += 11LL * st->ctx->model->hp.n_text_layer + 4;  // kernels inside one replayed step
+    return OH_OK;
+}
+
+const int* clip_max_key(oh_state* st, int batch, int clip) {
+    ClipMeta cm = clip_meta_view(st->clip_meta.p, std::max<size_t>(batch, st->max_batch));
+    return cm.max_key + clip;
+}
+
+// stage API: feed tokens[batch][n_tokens] at positions n_past.. and return the logits of the last position
+int decode_tokens_stage(oh_state* st, const int* tokens, int n_tokens, int n_past, int batch, float* out_logits) {
+    SeqLayout lay(st->max_batch);
+    int32_t* hb = (int32_t*)st->pinned;
+    DecodeSeqState hs = seq_view(hb, lay);
+    memset(hb, 0, seqlay::N_SCALARS * lay.rows * 4);
+    cudaStream_t s = st->stream;
+    int rc;
+    for (int i = 0; i < n_tokens; ++i) {
+        for (int r = 0; r < batch; ++r) {
+            hs.slot[r] = r;
+            hs.active[r] = 1;
+            hs.pos[r] = n_past + i;
+            hs.cur_token[r] = tokens[(size_t)r * n_tokens + i];
+        }
+        OH_CUDA_CHECK(cudaMemcpyAsync(st->seq_dev.p, hb, seqlay::N_SCALARS * lay.rows * 4, cudaMemcpyHostToDevice, s));
+        if ((rc = decode_step_launch(st, batch, false, false))) return rc;
+        OH_CUDA_CHECK(cudaStreamSynchronize(s));
+    }
+    if (out_logits) {
+        const int V = st->ctx->model->hp.n_vocab;
+        OH_CUDA_CHECK(cudaMemcpy2DAsync(out_logits, (size_t)V * 4, st->logits.p, (size_t)st->ld_logits * 4, (size_t)V * 4, batch,
+                                        cudaMemcpyDeviceToHost, s));
+        OH_CUDA_CHECK(cudaStreamSynchronize(s));
+    }
+    return OH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ full()
+namespace {
+
+struct PassRow {
+    int item, slot;
+    std::vector<int> prompt;
+};
+struct PassResult {
+    std::vector<TokenData> tokens;
+    int result_len = 0, seek_delta = 0;
+    bool has_ts = false, failed = false, completed = false;
+    double sum_logprobs = 0, avg_logprobs = 0, entropy = 0, score = 0;
+};
+
+void sequence_score(const oh_full_params& p, PassResult& r) {  // A.8
+    const int n = r.result_len;
+    double sum = 0.0;
+    for (int i = 0; i < n && i < (int)r.tokens.size(); ++i) sum += r.tokens[i].plog;
+    r.sum_logprobs = sum;
+    r.avg_logprobs = n > 0 ? sum / n : -INFINITY;
+    double penalty = n;
+    if (p.length_penalty > 0.0f) penalty = std::pow((5.0 + n) / 6.0, (double)p.length_penalty);
+    r.score = n > 0 ? sum / penalty : -INFINITY;
+    std::map<int, int> counts;
+    int cnt = 0;
+    for (int i = std::max(0, n - 32); i < n; ++i) {
+        counts[r.tokens[i].id]++;
+        cnt++;
+    }
+    double ent = 0.0;
+    for (auto& kv : counts) {
+        const double q = (double)kv.second / cnt;
+        ent -= q * std::log(q);
+    }
+    r.entropy = ent;
+}
+
+void emit_segments(const Model& m, const oh_full_params& p, Item& it, const PassResult& best, const std::vector<int>& prompt, int n_prompt_init) {
+    const Vocab& vc = m.vocab;
+    const auto& tk = best.tokens;
+    std::vector<int> new_past;
+    if (!prompt.empty() && prompt.front() == vc.token_prev) new_past.insert(new_past.end(), prompt.begin() + 1, prompt.end() - n_prompt_init);
+    for (int i = 0; i < best.result_len && i < (int)tk.size(); ++i) new_past.push_back(tk[i].id);
+    it.prompt_past.swap(new_past);
+    const int seek = it.seek;
+    if (!tk.empty()) {
+        int i0 = 0;
+        int64_t t0 = seek + 2 * (tk.front().tid - vc.token_beg);
+        std::string text;
+        for (int i = 0; i < (int)tk.size(); ++i) {
+            if (p.print_special || tk[i].id < vc.token_eot) text += vc.id_to_token[tk[i].id];
+            if (tk[i].id > vc.token_beg && !p.single_segment) {
+                const int64_t t1 = seek + 2 * (tk[i].tid - vc.token_beg);
+                if (!text.empty()) {
+                    Segment s;
+                    s.t0 = t0;
+                    s.t1 = t1;
+                    s.text = text;
+                    for (int j = i0; j <= i; ++j) s.tokens.push_back(tk[j]);
+                    it.segments.push_back(std::move(s));
+                }
+                text.clear();
+                while (i < (int)tk.size() && tk[i].id > vc.token_beg) i++;
+                i--;
+                t0 = t1;
+                i0 = i + 1;
+            }
+        }
+        if (!text.empty()) {
+            Segment s;
+            s.t0 = t0;
+            s.t1 = seek + best.seek_delta;
+            s.text = text;
+            for (int j = i0; j < (int)tk.size(); ++j) s.tokens.push_back(tk[j]);
+            it.segments.push_back(std::move(s));
+        }
+    }
+    it.seek += best.seek_delta;
+}
+
+// host side of one sampled token (A.7, t > 0): std::discrete_distribution over the row's probabilities
+TokenData sample_on_host(const Vocab& vc, const float* probs, const float* logprobs, std::mt19937& rng) {
+    TokenData r;
+    {
+        double sum_ts = 0.0, max_ts = 0.0;
+        for (int i = vc.token_beg; i < vc.n_vocab; ++i) {
+            sum_ts += probs[i];
+            if (max_ts < probs[i]) {
+                max_ts = probs[i];
+                r.tid = i;
+            }
+        }
+        r.pt = (float)(max_ts / (sum_ts + 1e-10));
+        r.ptsum = (float)sum_ts;
+    }
+    std::discrete_distribution<> dist(probs, probs + vc.n_vocab);
+    r.id = dist(rng);
+    r.p = probs[r.id];
+    r.plog = logprobs[r.id];
+    if (r.id >= vc.token_beg) {
+        r.tid = r.id;
+        r.pt = r.p;
+    }
+    return r;
+}
+
+}  // namespace
+
+static int decode_pass(oh_state* st, const oh_full_params& p, bool no_timestamps, const std::vector<PassRow>& rows_in, float temperature,
+                       std::vector<PassResult>& out) {
+    const Model& m = *st->ctx->model;
+    const Vocab& vc = m.vocab;
+    const int rows = (int)rows_in.size();
+    const int n_max = m.hp.n_text_ctx / 2 - 4;
+    SeqLayout lay(st->max_batch);
+    int32_t* hb = (int32_t*)st->pinned;
+    DecodeSeqState hs = seq_view(hb, lay);
+    memset(hb, 0, lay.total_words * 4);
+    int max_prompt = 0;
+    for (int r = 0; r < rows; ++r) {
+        const PassRow& pr = rows_in[r];
+        const Item& it = st->items[pr.item];
+        const int pl = (int)pr.prompt.size();
+        if (pl > kMaxPrompt || pl < 1) {
+            set_error("prompt too long");
+            return OH_ERR_DECODE;
+        }
+        max_prompt = std::max(max_prompt, pl);
+        hs.slot[r] = pr.slot;
+        hs.active[r] = 1;
+        hs.pos[r] = 0;
+        hs.cur_token[r] = pr.prompt[0];
+        hs.prompt_len[r] = pl;
+        for (int i = 0; i < pl; ++i) hs.prompt[(size_t)r * kMaxPrompt + i] = pr.prompt[i];
+        hs.seek_delta[r] = 100 * 30;
+        hs.seek[r] = it.seek;
+        hs.seek_end[r] = it.seek_end;
+    }
+    *hs.n_active_total = rows;
+    DecodeRules R;
+    R.n_vocab = vc.n_vocab; R.eot = vc.token_eot; R.sot = vc.token_sot; R.translate = vc.token_translate; R.transcribe = vc.token_transcribe;
+    R.solm = vc.token_solm; R.prev = vc.token_prev; R.nosp = vc.token_nosp; R.tok_not = vc.token_not; R.beg = vc.token_beg;
+    R.blank = vc.token_blank; R.n_lang = vc.num_languages();
+    R.no_timestamps = no_timestamps; R.suppress_blank = p.suppress_blank; R.single_segment = p.single_segment; R.max_tokens = p.max_tokens;
+    R.n_max = n_max;
+    R.tid0_initial = p.max_initial_ts > 0.0f ? (int)std::round(p.max_initial_ts / (30.0f / (float)m.hp.n_audio_ctx)) : -1;
+    R.temperature = temperature;
+    cudaStream_t s = st->stream;
+    OH_CUDA_CHECK(cudaMemcpyAsync(st->seq_dev.p, hb, lay.total_words * 4, cudaMemcpyHostToDevice, s));
+    OH_CUDA_CHECK(cudaMemcpyAsync(st->rules_dev.p, &R, sizeof R, cudaMemcpyHostToDevice, s));
+    OH_CUDA_CHECK(cudaStreamSynchronize(s));  // R and hb are reused below
+
+    const int max_steps = max_prompt + n_max - 1;
+    int rc;
+    if (temperature < 1e-6f) {
+        int* counter = (int*)((char*)st->pinned + lay.total_words * 4 + 64);
+        for (int step = 0; step < max_steps; ++step) {
+            if ((rc = run_decode_step_graph(st, rows))) return rc;
+            st->timings.n_decode_steps++;
+            if ((step & 3) == 3 || step == max_steps - 1) {
+                OH_CUDA_CHECK(cudaMemcpyAsync(counter, st->seq.n_active_total, 4, cudaMemcpyDeviceToHost, s));
+                OH_CUDA_CHECK(cudaStreamSynchronize(s));
+                if (*counter <= 0) break;
+            }
+        }
+        OH_CUDA_CHECK(cudaMemcpyAsync(hb, st->seq_dev.p, lay.total_words * 4, cudaMemcpyDeviceToHost, s));
+        OH_CUDA_CHECK(cudaStreamSynchronize(s));
+    } else {
+        // t > 0: probabilities come back to the host and are sampled with the same libstdc++ calls as upstream
+        std::vector<float> probs((size_t)rows * st->ld_logits), logprobs((size_t)rows * st->ld_logits);
+        int n_live = rows;
+        for (int step = 0; step < max_steps && n_live > 0; ++step) {
+            if ((rc = decode_step_launch(st, rows, true, true))) return rc;
+            st->timings.n_decode_steps++;
+            OH_CUDA_CHECK(cudaMemcpyAsync(probs.data(), st->dump_p.p, probs.size() * 4, cudaMemcpyDeviceToHost, s));
+            OH_CUDA_CHECK(cudaMemcpyAsync(logprobs.data(), st->dump_lp.p, logprobs.size() * 4, cudaMemcpyDeviceToHost, s));
+            OH_CUDA_CHECK(cudaStreamSynchronize(s));
+            for (int r = 0; r < rows; ++r) {
+                if (!hs.active[r]) continue;
+                const int pos = hs.pos[r];
+                if (pos + 1 < hs.prompt_len[r]) {  // mirrors the kernel's prompt feeding
+                    hs.pos[r] = pos + 1;
+                    hs.cur_token[r] = hs.prompt[(size_t)r * kMaxPrompt + pos + 1];
+                    continue;
+                }
+                TokenData t = sample_on_host(vc, probs.data() + (size_t)r * st->ld_logits, logprobs.data() + (size_t)r * st->ld_logits,
+                                             st->rngs[hs.slot[r]]);
+                const int i = hs.n_gen[r];
+                const size_t o = (size_t)r * kMaxGen + i;
+                hs.tok_id[o] = t.id; hs.tok_tid[o] = t.tid; hs.tok_p[o] = t.p; hs.tok_plog[o] = t.plog; hs.tok_pt[o] = t.pt; hs.tok_ptsum[o] = t.ptsum;
+                hs.n_gen[r] = i + 1;
+                SeqFlags f{hs.has_ts[r], hs.seek_delta[r], hs.result_len[r], 0, 0};
+                const bool live = apply_token_rules(f, t.id, i, hs.seek[r], hs.seek_end[r], vc.token_beg, vc.token_eot, p.max_tokens, no_timestamps,
+                                                    p.single_segment, n_max);
+                hs.has_ts[r] = f.has_ts; hs.seek_delta[r] = f.seek_delta; hs.result_len[r] = f.result_len;
+                hs.failed[r] = f.failed; hs.completed[r] = f.completed;
+                if (live) {
+                    hs.cur_token[r] = t.id;
+                    hs.pos[r] = pos + 1;
+                } else {
+                    hs.active[r] = 0;
+                    n_live--;
+                }
+            }
+            // scalars + token ids (the kernel reads the last two sampled ids)
+            OH_CUDA_CHECK(cudaMemcpyAsync(st->seq_dev.p, hb, (lay.tok_off[1]) * 4, cudaMemcpyHostToDevice, s));
+            OH_CUDA_CHECK(cudaStreamSynchronize(s));
+        }
+    }
+    out.assign(rows, PassResult());
+    for (int r = 0; r < rows; ++r) {
+        PassResult& pr = out[r];
+        const int ng = hs.n_gen[r];
+        pr.tokens.resize(ng);
+        for (int i = 0; i < ng; ++i) {
+            const size_t o = (size_t)r * kMaxGen + i;
+            pr.tokens[i] = TokenData{hs.tok_id[o], hs.tok_tid[o], hs.tok_p[o], hs.tok_plog[o], hs.tok_pt[o], hs.tok_ptsum[o]};
+        }
+        pr.result_len = hs.result_len[r];
+        pr.seek_delta = hs.seek_delta[r];
+        pr.has_ts = hs.has_ts[r];
+        pr.failed = hs.failed[r];
+        pr.completed = hs.completed[r];
+        st->timings.n_tokens += ng;
+    }
+    return OH_OK;
+}
+
+int run_full(oh_state* st, const oh_full_params& p, const float* const* pcm, const int* n, int batch, bool pcm_on_device) {
+    using clk = std::chrono::steady_clock;
+    const Model& m = *st->ctx->model;
+    const Vocab& vc = m.vocab;
+    const HParams& hp = m.hp;
+    if (batch < 1 || batch > st->max_batch) {
+        set_error("batch exceeds oh_context_params.max_batch");
+        return OH_ERR_INVALID;
+    }
+    if (p.strategy != OH_SAMPLING_GREEDY) {
+        set_error("beam search is not implemented yet");
+        return OH_ERR_UNSUPPORTED;
+    }
+    if (p.suppress_non_speech_tokens || p.offset_ms != 0 || p.duration_ms != 0) {
+        set_error("unsupported oh_full_params (suppress_non_speech_tokens / offset_ms / duration_ms)");
+        return OH_ERR_UNSUPPORTED;
+    }
+    st->timings = oh_timings{};
+    const long long launches0 = g_launch_count;
+    auto t_begin = clk::now();
+    cudaStream_t s = st->stream;
+    int rc;
+
+    // the prompts of earlier calls survive only with no_context = false
+    std::vector<std::vector<int>> carried(batch);
+    if (!p.no_context)
+        for (int i = 0; i < batch && i < (int)st->items.size(); ++i) carried[i] = st->items[i].prompt_past;
+
+    if ((rc = run_mel(st, pcm, n, batch, pcm_on_device))) return rc;
+    OH_CUDA_CHECK(cudaStreamSynchronize(s));
+    auto t_mel = clk::now();
+    st->timings.mel_ms = std::chrono::duration<float, std::milli>(t_mel - t_begin).count();
+
+    std::vector<float> temperatures;
+    if (p.temperature_inc > 0.0f) {
+        for (float t = p.temperature; t < 1.0f + 1e-6f; t += p.temperature_inc) temperatures.push_back(t);
+    } else {
+        temperatures.push_back(p.temperature);
+    }
+    std::vector<int> prompt_init = {vc.token_sot};
+    bool no_timestamps = p.no_timestamps != 0;
+    int lang_id = 0;
+    if (vc.is_multilingual()) {
+        const char* lang = (p.language && strcmp(p.language, "auto") != 0 && p.language[0]) ? p.language : "en";
+        lang_id = lang_id_from_code(lang);
+        if (lang_id < 0 || lang_id >= vc.num_languages()) lang_id = 0;
+        prompt_init.push_back(vc.token_sot + 1 + lang_id);
+        prompt_init.push_back(p.translate ? vc.token_translate : vc.token_transcribe);
+    }
+    if (hp.n_text_layer == 2 && hp.n_vocab != 51866) no_timestamps = true;  // "distilled" heuristic (A.1)
+    if (no_timestamps) prompt_init.push_back(vc.token_not);
+
+    for (int i = 0; i < batch; ++i) {
+        Item& it = st->items[i];
+        it.lang_id = lang_id;
+        it.prompt_past = carried[i];
+        it.seek = 0;
+        it.seek_end = it.n_len_org;
+        if (!it.done && it.seek_end < 100) it.done = true;  // < 1 s: no segments, rc 0 (A.3 step 7)
+    }
+
+    ClipMeta cm = clip_meta_view(st->clip_meta.p, std::max<size_t>(batch, st->max_batch));
+    const int T = hp.n_audio_ctx;
+    std::vector<int> clip_of_slot, seek_of_slot;
+    while (true) {
+        std::vector<int> act;
+        for (int i = 0; i < batch; ++i) {
+            Item& it = st->items[i];
+            if (it.done) continue;
+            if (it.seek + 100 >= it.seek_end) {
+                it.done = true;
+                continue;
+            }
+            act.push_back(i);
+        }
+        if (act.empty()) break;
+        auto t0 = clk::now();
+        // ---- encoder over the active windows, enc_chunk at a time; slot = index in `act`
+        clip_of_slot.assign(act.begin(), act.end());
+        seek_of_slot.resize(act.size());
+        for (size_t k = 0; k < act.size(); ++k) seek_of_slot[k] = st->items[act[k]].seek;
+        OH_CUDA_CHECK(cudaMemcpyAsync(cm.clip_of_slot, clip_of_slot.data(), act.size() * 4, cudaMemcpyHostToDevice, s));
+        OH_CUDA_CHECK(cudaMemcpyAsync(cm.seek_of_slot, seek_of_slot.data(), act.size() * 4, cudaMemcpyHostToDevice, s));
+        for (size_t c0 = 0; c0 < act.size(); c0 += st->enc_chunk) {
+            const int nw = (int)std::min<size_t>(st->enc_chunk, act.size() - c0);
+            WindowGatherArgs wa;
+            wa.raw = (const float*)st->mel_raw.p;
+            wa.ld = st->mel_ld;
+            wa.n_mel = hp.n_mels;
+            wa.max_key = cm.max_key;
+            wa.n_active = cm.n_active;
+            wa.n_len = cm.n_len;
+            wa.clip_of_slot = cm.clip_of_slot + c0;
+            wa.seek_of_slot = cm.seek_of_slot + c0;
+            if ((rc = launch_window_gather(wa, nw, st->xin.p, st->ctx->act_type, s))) return rc == OH_ERR_CUDA ? rc : OH_ERR_ENCODE;
+            if ((rc = run_encoder(st, nw, (int)c0, nullptr))) return rc == OH_ERR_CUDA ? rc : OH_ERR_ENCODE;
+            st->timings.n_windows += nw;
+        }
+        OH_CUDA_CHECK(cudaStreamSynchronize(s));
+        auto t1 = clk::now();
+        st->timings.encode_ms += std::chrono::duration<float, std::milli>(t1 - t0).count();
+
+        // ---- decode with the temperature ladder
+        for (size_t k = 0; k < act.size(); ++k) {
+            Item& it = st->items[act[k]];
+            if (it.seek > 0 && it.seek + 500 >= it.seek_end) it.prompt_past.clear();  // short tail: drop the prompt (upstream behaviour)
+        }
+        std::vector<PassRow> pending;
+        for (size_t k = 0; k < act.size(); ++k) pending.push_back(PassRow{act[k], (int)k, {}});
+        std::vector<PassResult> accepted(act.size());
+        std::vector<std::vector<int>> accepted_prompt(act.size());
+        for (size_t ti = 0; ti < temperatures.size() && !pending.empty(); ++ti) {
+            const float t_cur = temperatures[ti];
+            for (PassRow& pr : pending) {
+                const Item& it = st->items[pr.item];
+                pr.prompt.clear();
+                if (!it.prompt_past.empty() && t_cur < 0.5f && p.n_max_text_ctx > 0) {
+                    const int n_take = std::min(std::min(p.n_max_text_ctx, hp.n_text_ctx / 2), (int)it.prompt_past.size());
+                    pr.prompt.push_back(vc.token_prev);
+                    pr.prompt.insert(pr.prompt.end(), it.prompt_past.end() - n_take, it.prompt_past.end());
+                }
+                pr.prompt.insert(pr.prompt.end(), prompt_init.begin(), prompt_init.end());
+            }
+            std::vector<PassResult> res;
+            if ((rc = decode_pass(st, p, no_timestamps, pending, t_cur, res))) return rc == OH_ERR_CUDA ? rc : OH_ERR_DECODE;
+            std::vector<PassRow> next;
+            for (size_t r = 0; r < pending.size(); ++r) {
+                PassResult& pr = res[r];
+                if (!pr.failed) {
+                    pr.tokens.resize(std::min<size_t>(pr.tokens.size(), (size_t)pr.result_len));
+                    sequence_score(p, pr);
+                    if (pr.result_len > 32 && pr.entropy < p.entropy_thold) pr.failed = true;
+                }
+                bool success = true;
+                if (ti + 1 != temperatures.size()) {
+                    if (pr.failed || pr.avg_logprobs < p.logprob_thold) success = false;
+                }
+                if (success) {
+                    accepted[pending[r].slot] = std::move(pr);
+                    accepted_prompt[pending[r].slot] = pending[r].prompt;
+                } else {
+                    st->timings.n_fallbacks++;
+                    next.push_back(pending[r]);
+                }
+            }
+            pending.swap(next);
+        }
+        for (size_t k = 0; k < act.size(); ++k) emit_segments(m, p, st->items[act[k]], accepted[k], accepted_prompt[k], (int)prompt_init.size());
+        st->timings.decode_ms += std::chrono::duration<float, std::milli>(clk::now() - t1).count();
+    }
+    st->timings.total_ms = std::chrono::duration<float, std::milli>(clk::now() - t_begin).count();
+    st->timings.n_kernel_launches = g_launch_count - launches0;
+    return OH_OK;
+}
+
+}  // namespace oh
