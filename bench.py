@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's metric on BASELINE.json's config.
+
+Metric: audio-seconds transcribed per second (1/RTF; RTF as the reference prints it,
+/root/reference/src/main.rs:1048-1049), whisper large-v3, batched greedy, independent 30 s windows of a long
+synthetic recording, data-parallel over N GPUs (weak scaling: every rank transcribes its own windows; the only
+collective is the gather of segment records, off the math path).
+
+  python bench.py --gpus N --steps K --warmup W            our arm  (one "step" = one oh_full_batch over `--batch` windows)
+  python bench.py --impl reference --gpus N ...             reference arm: the CPU port of the reference path (oracle/),
+                                                            all host threads, rank 0 only, one window per step
+
+Prints ONE JSON line (rank 0).  `value` = inputs resident in HBM; `e2e` = host PCM through the C ABI with the
+H2D copy and the result read-back inside the timed region.  See DESIGN.md §Measurement.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WINDOW_S = 30.0
+N_SAMPLES = 480000
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons), samples=len(sm))
+
+
+def make_windows(first: int, count: int, pinned: bool):
+    """`count` synthetic 30 s windows; window w of the recording has seed w+1."""
+    import torch
+    from openhush_b200 import synth
+    t = torch.empty((count, N_SAMPLES), dtype=torch.float32, pin_memory=pinned)
+    arr = t.numpy()
+    lib = synth._lib()
+    for i in range(count):
+        lib.ohgen_audio(first + i + 1, N_SAMPLES, arr[i].ctypes.data)
+    return t
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference's own algorithm on the host cores (oracle port; the reference binary cannot be built
+    offline — DESIGN.md).  One window per step (bounded sample of the same workload), all host threads."""
+    if rank != 0:
+        return
+    from openhush_b200 import default_full_params, synth
+    from oracle import oracle as O
+    path = synth.model_path(args.arch)
+    om = O.OracleModel(path)
+    ost = O.OracleState(om)  # ggml-faithful numerics: f16 activations at mat-muls, GELU table
+    p = default_full_params()
+    p.temperature_inc = 0.0
+    cores = os.cpu_count() or 1
+    times, toks = [], 0
+    for s in range(args.warmup + args.steps):
+        clip = synth.audio(s + 1)
+        t0 = time.perf_counter()
+        rc = ost.full(clip, p)
+        dt = time.perf_counter() - t0
+        assert rc == 0
+        if s >= args.warmup:
+            times.append(dt)
+            toks += sum(len(x["tokens"]) for x in ost.segments())
+    total = sum(times)
+    value = WINDOW_S * len(times) / total
+    line = dict(metric="audio_seconds_per_second", value=value, unit="audio-s/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1000.0 * total / len(times), higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f16-weights/f32-accum (CPU)",
+                data="synthetic", impl="reference",
+                config=dict(workload=f"whisper {args.arch} greedy (temperature_inc=0), independent 30 s windows, 1 window per step on the host CPU",
+                            arch=args.arch, windows_per_step=1),
+                cpu_baseline=dict(value=value, unit="audio-s/s", cores=cores, kind="port",
+                                  sample=f"{len(times)} windows of 30 s, one per step, restated reference path (not ggml), OpenMP all cores"),
+                e2e=dict(value=value, unit="audio-s/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0, tokens=toks)
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--arch", default="large-v3")
+    ap.add_argument("--batch", type=int, default=64, help="30 s windows per GPU per step")
+    ap.add_argument("--compute", default="f16", choices=["f16", "bf16", "f32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from openhush_b200 import COMPUTE_BF16, COMPUTE_F16, COMPUTE_F32, default_full_params, lib, synth
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    # model file: generated once per box (rank-local 0), everyone else waits
+    if local_rank == 0:
+        path = synth.model_path(args.arch)
+    barrier()
+    path = synth.model_path(args.arch)
+
+    B, K, W = args.batch, args.steps, args.warmup
+    ctype = {"f16": COMPUTE_F16, "bf16": COMPUTE_BF16, "f32": COMPUTE_F32}[args.compute]
+    ctx = lib.Context(path, compute_type=ctype, gpu_device=local_rank, max_batch=B)
+    st = lib.State(ctx)
+    stream = torch.cuda.current_stream()
+    st.set_stream(stream.cuda_stream)
+    p = default_full_params()
+    p.temperature_inc = 0.0  # no temperature fallback in throughput runs (both arms)
+
+    # windows of this rank: step s uses recording windows [(s*world + rank)*B, +B)
+    n_steps_total = W + K
+    host = torch.empty((n_steps_total * B, N_SAMPLES), dtype=torch.float32, pin_memory=True)
+    hv = host.numpy()
+    gen = synth._lib()
+    for s in range(n_steps_total):
+        for i in range(B):
+            w = (s * world + rank) * B + i
+            gen.ohgen_audio(w + 1, N_SAMPLES, hv[s * B + i].ctypes.data)
+    dev = host.cuda(non_blocking=False)
+    ns = [N_SAMPLES] * B
+
+    def step_device(s):
+        base = dev.data_ptr() + s * B * N_SAMPLES * 4
+        rc = st.full_batch_ptrs([base + i * N_SAMPLES * 4 for i in range(B)], ns, p, on_device=True)
+        assert rc == 0, (rc, st.lib.oh_last_error())
+
+    def step_host(s):
+        base = host.data_ptr() + s * B * N_SAMPLES * 4
+        rc = st.full_batch_ptrs([base + i * N_SAMPLES * 4 for i in range(B)], ns, p, on_device=False)
+        assert rc == 0, (rc, st.lib.oh_last_error())
+        return st.pack_records()  # the step's result: segment records (token ids, t0/t1) read back to the host
+
+    # ---------------- kernel-only value: inputs resident in HBM ----------------
+    for s in range(W):
+        step_device(s)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = tokens = windows = dsteps = 0
+    e0.record(stream)
+    for s in range(W, W + K):
+        step_device(s)
+        t = st.timings()
+        launches += t.n_kernel_launches
+        tokens += t.n_tokens
+        windows += t.n_windows
+        dsteps += t.n_decode_steps
+    e1.record(stream)
+    barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    last = dict(mel_ms=t.mel_ms, encode_ms=t.encode_ms, decode_ms=t.decode_ms, total_ms=t.total_ms)
+
+    # ---------------- end to end: host PCM through the C ABI ----------------
+    step_host(0)
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    h2d = d2h = 0
+    for s in range(W, W + K):
+        rec = step_host(s)
+        tt = st.timings()
+        h2d += tt.h2d_bytes
+        d2h += tt.d2h_bytes
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+
+    # ---------------- per-kernel profile of one step (events around every launch; graphs bypassed) ----------------
+    st.profile(True)
+    step_device(W)
+    rep = st.profile_report()
+    st.profile(False)
+    # exact-bytes measurement of the decode attention: a stage decode step with every row active
+    st.profile(True)
+    toks1 = np.full((B, 1), ctx.sot, dtype=np.int32)
+    for i in range(4):
+        st.decode(toks1, 8 + i)
+    rep_dec = st.profile_report()
+    st.profile(False)
+
+    # ---------------- reduce over ranks ----------------
+    if world > 1:
+        tms = torch.tensor([ms, e2e_s * 1000.0], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        cnt = torch.tensor([launches, tokens, windows, h2d, d2h], device="cuda", dtype=torch.float64)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        ms, e2e_ms = float(tms[0]), float(tms[1])
+        launches, tokens, windows = int(cnt[0]), int(cnt[1]), int(cnt[2])
+        h2d, d2h = int(cnt[3]) // world, int(cnt[4]) // world
+        # the path's only collective: gather of the fixed-size segment records (off the math path)
+        recs = torch.from_numpy(rec.astype(np.int64)).cuda()
+        n = torch.tensor([recs.numel()], device="cuda")
+        sizes = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(sizes, n)
+        pad = torch.zeros(int(max(int(x) for x in sizes)), dtype=torch.int64, device="cuda")
+        pad[:recs.numel()] = recs
+        allrec = [torch.zeros_like(pad) for _ in range(world)]
+        dist.all_gather(allrec, pad)
+    else:
+        e2e_ms = e2e_s * 1000.0
+
+    if rank == 0:
+        pk = peaks()
+        audio_s = WINDOW_S * B * world * K
+        value = audio_s / (ms / 1000.0)
+        e2e_val = audio_s / (e2e_ms / 1000.0)
+        rep_sorted = sorted(rep, key=lambda r: -r["total_ms"])
+        tot_ms = sum(r["total_ms"] for r in rep) or 1.0
+        top = rep_sorted[0]
+        hp = ctx
+        L, d, T = hp.n_text_layer, hp.n_text_state, hp.n_audio_ctx
+        esz = 4 if args.compute == "f32" else 2
+        if top["name"] in ("gemm_encoder", "gemm_decoder", "attention_encoder"):
+            achieved = top["work"] / (top["total_ms"] / 1e3) / 1e12
+            roof = dict(kernel=top["name"], bound="tensor", achieved=achieved, peak=pk["tf_sustained"], unit="TFLOP/s", frac=achieved / pk["tf_sustained"],
+                        traffic=None, peak_source=pk["src"] + ", sustained", share_of_step=top["total_ms"] / tot_ms,
+                        avg_launch_ms=top["total_ms"] / top["launches"], launches=top["launches"])
+        else:
+            src = next((r for r in rep_dec if r["name"] == top["name"]), top)
+            achieved = src["work"] / (src["total_ms"] / 1e3) / 1e9
+            roof = dict(kernel=top["name"], bound="hbm", achieved=achieved, peak=pk["hbm"], unit="GB/s", frac=achieved / pk["hbm"], traffic=None,
+                        peak_source=pk["src"], share_of_step=top["total_ms"] / tot_ms, avg_launch_ms=src["total_ms"] / src["launches"],
+                        launches=src["launches"], measured_on="stage decode step, all rows active")
+        kernels = {r["name"]: dict(ms=round(r["total_ms"], 3), launches=r["launches"], share=round(r["total_ms"] / tot_ms, 4),
+                                   rate=(round(r["work"] / (r["total_ms"] / 1e3) / 1e12, 2) if r["name"].startswith("gemm") or r["name"] == "attention_encoder"
+                                         else round(r["work"] / (r["total_ms"] / 1e3) / 1e9, 1)),
+                                   rate_unit=("TFLOP/s" if r["name"].startswith("gemm") or r["name"] == "attention_encoder" else "GB/s"))
+                   for r in rep_sorted}
+        xattn = next((r for r in rep_dec if r["name"] == "cross_attention_decode"), None)
+        line = dict(metric="audio_seconds_per_second", value=value, unit="audio-s/s", n_gpus=world, steps=K, warmup=W, ms_per_step=ms / K,
+                    higher_is_better=True, scaling="weak", vs_baseline=None, dtype=args.compute, data="synthetic",
+                    config=dict(workload=f"whisper {args.arch} batched greedy (temperature_inc=0), independent 30 s windows of a synthetic recording, "
+                                         f"{B} windows per GPU per step", arch=args.arch, windows_per_gpu_per_step=B, window_seconds=WINDOW_S,
+                                weights="random-init, ggml-<arch>.bin format, seed 1234", l2="per-step inputs and weights exceed the 126 MB L2",
+                                gemm_backend=st.gemm_backend()),
+                    clocks=clocks,
+                    e2e=dict(value=e2e_val, unit="audio-s/s", h2d_bytes_per_step=h2d // K, d2h_bytes_per_step=d2h // K, ms_per_step=e2e_ms / K),
+                    gpu_launches=launches, roofline=roof, tokens_per_s=tokens / (ms / 1000.0), windows=windows, decode_steps=dsteps,
+                    last_step_ms=last, kernels=kernels,
+                    cross_attention_decode_gbs=(xattn["work"] / (xattn["total_ms"] / 1e3) / 1e9 if xattn else None))
+        if not args.no_cpu_baseline and world == 1:
+            from oracle import oracle as O
+            om = O.OracleModel(path)
+            ost = O.OracleState(om)
+            t0 = time.perf_counter()
+            assert ost.full(hv[0], p) == 0
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = dict(value=WINDOW_S / dt, unit="audio-s/s", cores=os.cpu_count(), kind="port",
+                                        sample="1 window of 30 s (window 0 of the same recording), restated reference path (not ggml), OpenMP all cores")
+            ost.close()
+            om.close()
+        print(json.dumps(line), flush=True)
+    st.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -207,6 +207,7 @@ typedef struct oh_timings {
     float mel_ms, encode_ms, decode_ms, total_ms; /* CUDA-event times on the state's stream */
     int n_windows, n_decode_steps, n_tokens, n_fallbacks;
     long long n_kernel_launches;
+    long long h2d_bytes, d2h_bytes; /* host<->device traffic of the call (PCM in, decoder state / token records out) */
 } oh_timings;
 OH_API oh_timings oh_get_timings(oh_state* state);
 
@@ -214,6 +215,19 @@ OH_API oh_timings oh_get_timings(oh_state* state);
  * and the relative L2 error the tcgen05 kernel showed against the SIMT kernel in the start-up self-test (-1 if not run) */
 OH_API const char* oh_gemm_backend(oh_state* state);
 OH_API float oh_gemm_selftest_error(void);
+
+/* per-kernel CUDA-event timing for bench.py's roofline block: oh_profile(state, 1) brackets every kernel launch made
+ * by the calling thread with two events on the launching stream (CUDA graphs are bypassed meanwhile) until
+ * oh_profile(state, 0); oh_profile_report sums them per kernel.  `work` = algorithmic FLOPs for the mat-mul kernels,
+ * algorithmic bytes for the others (rows assumed active). */
+typedef struct oh_kernel_stat {
+    char name[32];
+    int launches;
+    float total_ms;
+    double work;
+} oh_kernel_stat;
+OH_API int oh_profile(oh_state* state, int on);
+OH_API int oh_profile_report(oh_state* state, oh_kernel_stat* out, int cap);
 
 /* run the library on a caller-provided CUDA stream (cudaStream_t as void*); NULL = the state's own */
 OH_API int oh_state_set_stream(oh_state* state, void* cuda_stream);

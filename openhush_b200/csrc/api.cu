@@ -401,6 +401,49 @@ OH_API const char* oh_gemm_backend(oh_state* st) {
 }
 OH_API float oh_gemm_selftest_error(void) { return g_selftest_err; }
 
+// ---- per-kernel timing
+static const char* k_cat_names[PC_COUNT] = {"mel_frames", "window_gather", "gemm_encoder", "gemm_decoder", "layernorm",
+                                            "attention_encoder", "self_attention_decode", "cross_attention_decode", "embed", "logits_step"};
+OH_API int oh_profile(oh_state* st, int on) {
+    if (!st) return OH_ERR_INVALID;
+    if (on) {
+        if (!st->prof) st->prof = new Profiler();
+        for (auto& r : st->prof->recs) {
+            st->prof->free_events.push_back(r.e0);
+            st->prof->free_events.push_back(r.e1);
+        }
+        st->prof->recs.clear();
+        g_prof = st->prof;
+        st->profiling = true;
+    } else {
+        g_prof = nullptr;
+        st->profiling = false;
+    }
+    return OH_OK;
+}
+OH_API int oh_profile_report(oh_state* st, oh_kernel_stat* out, int cap) {
+    if (!st || !st->prof) return 0;
+    if (select_device(st->ctx)) return 0;
+    cudaStreamSynchronize(st->stream);
+    oh_kernel_stat acc[PC_COUNT];
+    memset(acc, 0, sizeof acc);
+    for (int c = 0; c < PC_COUNT; ++c) strncpy(acc[c].name, k_cat_names[c], sizeof acc[c].name - 1);
+    for (auto& r : st->prof->recs) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) continue;
+        acc[r.cat].launches++;
+        acc[r.cat].total_ms += ms;
+        acc[r.cat].work += r.work;
+    }
+    int n = 0;
+    for (int c = 0; c < PC_COUNT; ++c)
+        if (acc[c].launches > 0) {
+            if (out && n < cap) out[n] = acc[c];
+            ++n;
+        }
+    return n;
+}
+
 OH_API oh_timings oh_get_timings(oh_state* st) { return st ? st->timings : oh_timings{}; }
 
 OH_API int oh_state_set_stream(oh_state* st, void* cuda_stream) {

@@ -109,6 +109,7 @@ int launch_simple_t(const void* qkv, void* out, int B, int Tn, int d, cudaStream
         attr = true;
     }
     dim3 grid((Tn + SQ - 1) / SQ, d / kHeadDim, B);
+    ProfScope ps(PC_ATTN_ENC, 4.0 * B * (double)Tn * Tn * d, st);
     encoder_attention_simple_kernel<T><<<grid, 256, smem, st>>>((const T*)qkv, (T*)out, Tn, d);
     OH_COUNT_LAUNCH();
     OH_CUDA_CHECK(cudaGetLastError());

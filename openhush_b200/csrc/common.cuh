@@ -6,6 +6,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <initializer_list>
 #include <string>
 #include <vector>
 
@@ -34,6 +35,46 @@ constexpr int kHeadDim = 64;        // every Whisper size
 extern thread_local long long g_launch_count;
 #define OH_COUNT_LAUNCH() (++::oh::g_launch_count)
 
+// Optional per-kernel timing (oh_profile): every launch wrapper opens a ProfScope, which brackets the launch with
+// two CUDA events on the launching stream when a profiler is attached to the calling thread (and costs one
+// thread-local load otherwise).  `work` is the launch's algorithmic work: FLOPs for mat-muls, bytes otherwise.
+enum ProfCat { PC_MEL = 0, PC_GATHER, PC_GEMM_ENC, PC_GEMM_DEC, PC_LN, PC_ATTN_ENC, PC_SELF_ATTN, PC_CROSS_ATTN, PC_EMBED, PC_LOGITS, PC_COUNT };
+struct Profiler {
+    struct Rec {
+        int cat;
+        double work;
+        cudaEvent_t e0, e1;
+    };
+    std::vector<Rec> recs;
+    std::vector<cudaEvent_t> free_events;
+};
+extern thread_local Profiler* g_prof;
+struct ProfScope {
+    int idx = -1;
+    cudaStream_t st;
+    ProfScope(int cat, double work, cudaStream_t s) : st(s) {
+        Profiler* p = g_prof;
+        if (!p) return;
+        Profiler::Rec r;
+        r.cat = cat;
+        r.work = work;
+        for (cudaEvent_t* e : {&r.e0, &r.e1}) {
+            if (!p->free_events.empty()) {
+                *e = p->free_events.back();
+                p->free_events.pop_back();
+            } else {
+                cudaEventCreate(e);
+            }
+        }
+        cudaEventRecord(r.e0, st);
+        idx = (int)p->recs.size();
+        p->recs.push_back(r);
+    }
+    ~ProfScope() {
+        if (idx >= 0 && g_prof) cudaEventRecord(g_prof->recs[idx].e1, st);
+    }
+};
+
 // ---- 16-bit activation type helpers ---------------------------------------------------------------
 template <typename T>
 struct Cvt;
@@ -60,6 +101,11 @@ __device__ __forceinline__ float gelu_lut(float x, const uint16_t* __restrict__ 
     if (x >= 10.0f) return x;
     unsigned short h = __half_as_ushort(__float2half_rn(x));
     return __half2float(__ushort_as_half(lut[h]));
+}
+// f32 parity mode: the same tanh formula evaluated in full f32 (no table, so no f16 rounding boundary that
+// would amplify summation-order noise into token flips)
+__device__ __forceinline__ float gelu_tanh(float x) {
+    return 0.5f * x * (1.0f + tanhf(0.79788456080286535587989211986876f * x * (1.0f + 0.044715f * x * x)));
 }
 __device__ __forceinline__ float gelu_fast(float x) {
     // 0.5 x (1 + tanh(u)) = x / (1 + exp(-2u)),  u = sqrt(2/pi) x (1 + 0.044715 x^2)

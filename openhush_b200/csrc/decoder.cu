@@ -421,6 +421,7 @@ __global__ void __launch_bounds__(K9_THREADS) logits_step_kernel(const float* __
 }  // namespace
 
 int launch_embed(const void* tok_emb, int w_type, const float* pos_emb, const DecodeSeqState& s, int rows, int d, float* x, cudaStream_t st) {
+    ProfScope ps(PC_EMBED, (double)rows * d * 10, st);
     if (w_type == DT_BF16) embed_kernel<__nv_bfloat16><<<rows, 256, 0, st>>>((const __nv_bfloat16*)tok_emb, pos_emb, s, d, x);
     else embed_kernel<__half><<<rows, 256, 0, st>>>((const __half*)tok_emb, pos_emb, s, d, x);
     OH_COUNT_LAUNCH();
@@ -432,6 +433,7 @@ int launch_self_attention_decode(const void* qkv, void* kcache, void* vcache, in
                                  void* out, cudaStream_t st) {
     dim3 grid(d / kHeadDim, rows);
     if (n_ctx > 448) return OH_ERR_INVALID;
+    ProfScope ps(PC_SELF_ATTN, 0.0, st);
     if (type == DT_F32) self_attention_decode_kernel<float><<<grid, 128, 0, st>>>((const float*)qkv, (float*)kcache, (float*)vcache, s, d, n_ctx, (float*)out);
     else if (type == DT_F16) self_attention_decode_kernel<__half><<<grid, 128, 0, st>>>((const __half*)qkv, (__half*)kcache, (__half*)vcache, s, d, n_ctx, (__half*)out);
     else self_attention_decode_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)kcache, (__nv_bfloat16*)vcache, s, d, n_ctx, (__nv_bfloat16*)out);
@@ -444,6 +446,8 @@ int launch_cross_attention_decode(const void* q, const void* xkv, int type, cons
                                   cudaStream_t st) {
     dim3 grid(d / kHeadDim, rows);
     if (T > 1504) return OH_ERR_INVALID;
+    // algorithmic bytes: every row streams its slot's K and V once (all rows assumed active)
+    ProfScope ps(PC_CROSS_ATTN, (double)rows * T * 2.0 * d * (type == DT_F32 ? 4 : 2), st);
     if (type == DT_F32) cross_attention_decode_kernel<float><<<grid, 128, 0, st>>>((const float*)q, (const float*)xkv, s, d, T, (float*)out);
     else if (type == DT_F16) cross_attention_decode_kernel<__half><<<grid, 128, 0, st>>>((const __half*)q, (const __half*)xkv, s, d, T, (__half*)out);
     else cross_attention_decode_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)xkv, s, d, T, (__nv_bfloat16*)out);
@@ -454,6 +458,7 @@ int launch_cross_attention_decode(const void* q, const void* xkv, int type, cons
 
 int launch_logits_step(const float* logits, int ld, const DecodeSeqState& s, const DecodeRules* r, int rows, float* dump_logprobs, float* dump_probs,
                        cudaStream_t st) {
+    ProfScope ps(PC_LOGITS, (double)rows * ld * 4.0 * 2, st);
     logits_step_kernel<<<rows, K9_THREADS, 0, st>>>(logits, ld, s, r, dump_logprobs, dump_probs);
     OH_COUNT_LAUNCH();
     OH_CUDA_CHECK(cudaGetLastError());

@@ -17,6 +17,7 @@
 namespace oh {
 
 thread_local long long g_launch_count = 0;
+thread_local Profiler* g_prof = nullptr;
 static thread_local std::string g_error;
 void set_error(const std::string& msg) { g_error = msg; }
 const std::string& get_error() { return g_error; }
@@ -98,6 +99,7 @@ int state_alloc(oh_state* st) {
     if (const char* s = getenv("OH_GEMM")) st->gemm_mode = strcmp(s, "simt") == 0 ? 1 : 0;
     if (const char* s = getenv("OH_ATTN")) st->attn_mode = strcmp(s, "simple") == 0 ? 1 : 0;
     if (const char* s = getenv("OH_GRAPHS")) st->use_graphs = atoi(s) != 0;
+    if (const char* s = getenv("OH_GELU")) st->gelu_lut_f32 = strcmp(s, "lut") == 0;
 
     OH_CUDA_CHECK(cudaStreamCreateWithFlags(&st->own_stream, cudaStreamNonBlocking));
     st->stream = st->own_stream;
@@ -144,6 +146,16 @@ void state_release(oh_state* st) {
     for (DevBuf* b : all) release(*b);
     if (st->pinned) cudaFreeHost(st->pinned);
     st->pinned = nullptr;
+    if (st->prof) {
+        if (g_prof == st->prof) g_prof = nullptr;
+        for (auto& r : st->prof->recs) {
+            cudaEventDestroy(r.e0);
+            cudaEventDestroy(r.e1);
+        }
+        for (auto& e : st->prof->free_events) cudaEventDestroy(e);
+        delete st->prof;
+        st->prof = nullptr;
+    }
     for (auto& ev : st->ev)
         if (ev) cudaEventDestroy(ev);
     if (st->own_stream) cudaStreamDestroy(st->own_stream);
@@ -214,7 +226,10 @@ int run_mel(oh_state* st, const float* const* pcm, const int* n, int batch, bool
         for (int i = 0; i < batch; ++i) {
             ptrs[i] = (const float*)st->pcm_stage.p + off[i];
             if (n[i] > 0)
+            {
                 OH_CUDA_CHECK(cudaMemcpyAsync((float*)st->pcm_stage.p + off[i], pcm[i], (size_t)n[i] * 4, cudaMemcpyHostToDevice, st->stream));
+                st->timings.h2d_bytes += (long long)n[i] * 4;
+            }
         }
     } else {
         for (int i = 0; i < batch; ++i) ptrs[i] = pcm[i];
@@ -257,7 +272,7 @@ static int gemm(oh_state* st, GemmArgs g) {
     g.w_type = m.compute_type == OH_COMPUTE_BF16 ? DT_BF16 : DT_F16;
     g.lut = m.gelu_lut;
     g.round_type = act;
-    if (g.gelu != GELU_NONE) g.gelu = act == DT_F32 ? GELU_LUT : GELU_FAST;
+    if (g.gelu != GELU_NONE) g.gelu = act == DT_F32 ? (st->gelu_lut_f32 ? GELU_LUT : GELU_TANH) : GELU_FAST;
     if (act != DT_F32 && st->gemm_mode == 0 && gemm_tc_available()) {
         int rc = launch_gemm_tc(g, st->stream);
         if (rc != OH_ERR_UNSUPPORTED) return rc;
@@ -438,7 +453,7 @@ static int decode_step_launch(oh_state* st, int rows, bool with_k9, bool dump) {
 int run_decode_step(oh_state* st, int rows, bool dump_probs) { return decode_step_launch(st, rows, true, dump_probs); }
 
 static int run_decode_step_graph(oh_state* st, int rows) {
-    if (!st->use_graphs) return decode_step_launch(st, rows, true, false);
+    if (!st->use_graphs || st->profiling) return decode_step_launch(st, rows, true, false);
     auto it = st->step_graphs.find(rows);
     if (it == st->step_graphs.end()) {
         // first use of this row count: one direct step (sets kernel attributes, faults in lazily allocated
@@ -651,6 +666,7 @@ static int decode_pass(oh_state* st, const oh_full_params& p, bool no_timestamps
     cudaStream_t s = st->stream;
     OH_CUDA_CHECK(cudaMemcpyAsync(st->seq_dev.p, hb, lay.total_words * 4, cudaMemcpyHostToDevice, s));
     OH_CUDA_CHECK(cudaMemcpyAsync(st->rules_dev.p, &R, sizeof R, cudaMemcpyHostToDevice, s));
+    st->timings.h2d_bytes += (long long)lay.total_words * 4 + (long long)sizeof R;
     OH_CUDA_CHECK(cudaStreamSynchronize(s));  // R and hb are reused below
 
     const int max_steps = max_prompt + n_max - 1;
@@ -662,11 +678,13 @@ static int decode_pass(oh_state* st, const oh_full_params& p, bool no_timestamps
             st->timings.n_decode_steps++;
             if ((step & 3) == 3 || step == max_steps - 1) {
                 OH_CUDA_CHECK(cudaMemcpyAsync(counter, st->seq.n_active_total, 4, cudaMemcpyDeviceToHost, s));
+                st->timings.d2h_bytes += 4;
                 OH_CUDA_CHECK(cudaStreamSynchronize(s));
                 if (*counter <= 0) break;
             }
         }
         OH_CUDA_CHECK(cudaMemcpyAsync(hb, st->seq_dev.p, lay.total_words * 4, cudaMemcpyDeviceToHost, s));
+        st->timings.d2h_bytes += (long long)lay.total_words * 4;
         OH_CUDA_CHECK(cudaStreamSynchronize(s));
     } else {
         // t > 0: probabilities come back to the host and are sampled with the same libstdc++ calls as upstream
@@ -677,6 +695,7 @@ static int decode_pass(oh_state* st, const oh_full_params& p, bool no_timestamps
             st->timings.n_decode_steps++;
             OH_CUDA_CHECK(cudaMemcpyAsync(probs.data(), st->dump_p.p, probs.size() * 4, cudaMemcpyDeviceToHost, s));
             OH_CUDA_CHECK(cudaMemcpyAsync(logprobs.data(), st->dump_lp.p, logprobs.size() * 4, cudaMemcpyDeviceToHost, s));
+            st->timings.d2h_bytes += (long long)probs.size() * 8;
             OH_CUDA_CHECK(cudaStreamSynchronize(s));
             for (int r = 0; r < rows; ++r) {
                 if (!hs.active[r]) continue;
@@ -707,6 +726,7 @@ static int decode_pass(oh_state* st, const oh_full_params& p, bool no_timestamps
             }
             // scalars + token ids (the kernel reads the last two sampled ids)
             OH_CUDA_CHECK(cudaMemcpyAsync(st->seq_dev.p, hb, (lay.tok_off[1]) * 4, cudaMemcpyHostToDevice, s));
+            st->timings.h2d_bytes += (long long)lay.tok_off[1] * 4;
             OH_CUDA_CHECK(cudaStreamSynchronize(s));
         }
     }

@@ -83,6 +83,9 @@ struct oh_state {
     bool use_graphs = true;
     int gemm_mode = 0;             // 0 auto (tcgen05 when 16-bit), 1 force SIMT
     int attn_mode = 0;             // 0 auto, 1 force the simple kernel
+    bool gelu_lut_f32 = false;     // OH_GELU=lut: f32 mode evaluates GELU through ggml's f16 table instead of f32 tanh
+    oh::Profiler* prof = nullptr;
+    bool profiling = false;
 
     // --- results
     std::vector<oh::Item> items;

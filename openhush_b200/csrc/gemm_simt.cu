@@ -121,9 +121,10 @@ __global__ void __launch_bounds__(THREADS) gemm_simt_kernel(GemmArgs g) {
             float v = acc[i][j];
             if (g.bias) v += g.bias[n];
             if (g.gelu == GELU_LUT) v = gelu_lut(v, g.lut);
+            else if (g.gelu == GELU_TANH) v = gelu_tanh(v);
             else if (g.gelu == GELU_FAST) {
                 if (g.round_type == DT_F16) v = __half2float(__float2half_rn(gelu_fast(__half2float(__float2half_rn(v)))));
-                else if (g.round_type == DT_BF16) v = __bfloat162float(__float2bfloat16_rn(gelu_fast(__bfloat162float(__float2bfloat16_rn(v)))));
+                else if (g.round_type == DT_BF16) v = __bfloat162float(__float2bfloat16_rn(gelu_fast(v)));
                 else v = gelu_fast(v);
             }
             if (rrow) v += rrow[n];
@@ -159,6 +160,7 @@ int launch_gemm_simt(const GemmArgs& g, cudaStream_t st) {
         return OH_ERR_INVALID;
     }
     dim3 grid((g.N + BN - 1) / BN, (M + BM - 1) / BM);
+    ProfScope ps(M <= 512 ? PC_GEMM_DEC : PC_GEMM_ENC, 2.0 * M * (double)g.N * g.K, st);
     switch (g.a_type) {
         case DT_F32: dispatch_w<float>(g, grid, st); break;
         case DT_F16: dispatch_w<__half>(g, grid, st); break;

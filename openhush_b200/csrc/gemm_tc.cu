@@ -126,9 +126,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
 
 __device__ __forceinline__ float epi_gelu(float v, int gelu, int round_type, const uint16_t* lut) {
     if (gelu == GELU_LUT) return gelu_lut(v, lut);
+    if (gelu == GELU_TANH) return gelu_tanh(v);
     if (gelu == GELU_FAST) {
         if (round_type == DT_F16) return __half2float(__float2half_rn(gelu_fast(__half2float(__float2half_rn(v)))));
-        if (round_type == DT_BF16) return __bfloat162float(__float2bfloat16_rn(gelu_fast(__bfloat162float(__float2bfloat16_rn(v)))));
+        if (round_type == DT_BF16) return __bfloat162float(__float2bfloat16_rn(gelu_fast(v)));
         return gelu_fast(v);
     }
     return v;
@@ -424,6 +425,7 @@ int launch_t(const GemmArgs& g, cudaStream_t st) {
     p.bias = g.bias; p.C = g.C; p.c_type = g.c_type; p.c_bstride = g.c_bstride; p.ldc = g.ldc;
     p.R = g.R; p.r_bstride = g.r_bstride; p.ldr = g.ldr; p.gelu = g.gelu; p.round_type = g.round_type; p.lut = g.lut;
     const int grid = std::min(p.num_tiles, g_num_sms);
+    ProfScope ps(g.batch * g.rows <= 512 ? PC_GEMM_DEC : PC_GEMM_ENC, 2.0 * g.batch * (double)g.rows * g.N * g.K, st);
     gemm_tc_kernel<BLOCK_N><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(ma[0], ma[1], ma[2], mw, p);
     OH_COUNT_LAUNCH();
     OH_CUDA_CHECK(cudaGetLastError());

@@ -38,7 +38,7 @@ int launch_window_from_mel(const float* mel, int n_mel, int n_slots, void* X, in
 // C(b,i,n) = [gelu]( sum_k A(b,i,k) W(n,k) + bias[n] ) + R(b,i,n)
 //   A(b,i,k) = A[b*a_bstride + i*lda + k]   (overlapping rows allowed: conv as mat-mul)
 //   C(b,i,n) = C[b*c_bstride + i*ldc + n],  R likewise with r_bstride / ldr (r_bstride = 0 broadcasts, e.g. pos-emb)
-enum { GELU_NONE = 0, GELU_LUT = 1, GELU_FAST = 2 };
+enum { GELU_NONE = 0, GELU_LUT = 1, GELU_FAST = 2, GELU_TANH = 3 };
 enum { DT_F32 = 0, DT_F16 = 1, DT_BF16 = 2 };
 struct GemmArgs {
     const void* A = nullptr;

@@ -236,7 +236,12 @@ int launch_mel_frames(const MelArgs& a, int batch, int max_active_frames, cudaSt
     mel_init_max_kernel<<<(batch + 127) / 128, 128, 0, st>>>(a.max_key, batch);
     OH_COUNT_LAUNCH();
     dim3 grid((max_active_frames + FB - 1) / FB, batch);
-    mel_frames_kernel<<<grid, MEL_THREADS, sizeof(MelSmem), st>>>(a);
+    {
+        // algorithmic bytes: PCM read once + raw log-mel written once (work is filled in by the caller's clip sizes:
+        // here the upper bound batch * (4 * 160 * frames + 4 * n_mel * frames))
+        ProfScope ps(PC_MEL, (double)batch * max_active_frames * (4.0 * kHop + 4.0 * a.n_mel), st);
+        mel_frames_kernel<<<grid, MEL_THREADS, sizeof(MelSmem), st>>>(a);
+    }
     OH_COUNT_LAUNCH();
     OH_CUDA_CHECK(cudaGetLastError());
     return OH_OK;
@@ -253,6 +258,7 @@ int launch_mel_normalize(const float* raw, int ld, int n_mel, int n_active, int 
 
 int launch_window_gather(const WindowGatherArgs& a, int n_slots, void* X, int act_type, cudaStream_t st) {
     dim3 grid((kChunkFrames + 31) / 32, n_slots);
+    ProfScope ps(PC_GATHER, (double)n_slots * kChunkFrames * a.n_mel * (4.0 + (act_type == OH_COMPUTE_F32 ? 4 : 2)), st);
     if (act_type == OH_COMPUTE_F32) window_gather_kernel<float><<<grid, 256, 0, st>>>(a, (float*)X);
     else if (act_type == OH_COMPUTE_F16) window_gather_kernel<__half><<<grid, 256, 0, st>>>(a, (__half*)X);
     else window_gather_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a, (__nv_bfloat16*)X);

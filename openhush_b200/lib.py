@@ -70,6 +70,8 @@ SYMBOLS = {
     "oh_decode_batch": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     "oh_gemm_backend": (C.c_char_p, [_vp]),
     "oh_gemm_selftest_error": (C.c_float, []),
+    "oh_profile": (C.c_int, [_vp, C.c_int]),
+    "oh_profile_report": (C.c_int, [_vp, _vp, C.c_int]),
     "oh_get_timings": (Timings, [_vp]),
     "oh_state_set_stream": (C.c_int, [_vp, _vp]),
 }
@@ -185,6 +187,16 @@ class State:
 
     def timings(self) -> Timings:
         return self.lib.oh_get_timings(self.h)
+
+    def profile(self, on: bool):
+        return self.lib.oh_profile(self.h, 1 if on else 0)
+
+    def profile_report(self):
+        """[{name, launches, total_ms, work}] per kernel since profile(True)."""
+        from ._abi import KernelStat
+        arr = (KernelStat * 16)()
+        n = self.lib.oh_profile_report(self.h, arr, 16)
+        return [dict(name=arr[i].name.decode(), launches=arr[i].launches, total_ms=arr[i].total_ms, work=arr[i].work) for i in range(min(n, 16))]
 
     def gemm_backend(self) -> str:
         return self.lib.oh_gemm_backend(self.h).decode()

@@ -68,6 +68,9 @@ def lib():
             "orc_full_window_seek": (C.c_int, [vp, C.c_int]),
             "orc_full_window_temperature": (C.c_float, [vp, C.c_int]),
             "orc_lang_id": (C.c_int, [C.c_char_p]),
+            "orc_full_window_n_tokens": (C.c_int, [vp, C.c_int]),
+            "orc_full_window_token": (C.c_int, [vp, C.c_int, C.c_int]),
+            "orc_model_round_weights_bf16": (None, [vp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -77,11 +80,13 @@ def lib():
 
 
 class OracleModel:
-    def __init__(self, path: str):
+    def __init__(self, path: str, bf16_weights: bool = False):
         self._l = lib()
         self.h = self._l.orc_model_load(path.encode())
         if not self.h:
             raise RuntimeError("oracle: " + self._l.orc_last_error().decode())
+        if bf16_weights:  # model of the product's OH_COMPUTE_BF16 mode (weights re-rounded at load)
+            self._l.orc_model_round_weights_bf16(self.h)
         hp = np.zeros(11, dtype=np.int32)
         self._l.orc_model_hparams(self.h, hp.ctypes.data)
         (self.n_vocab, self.n_audio_ctx, self.n_audio_state, self.n_audio_head, self.n_audio_layer, self.n_text_ctx,
@@ -192,6 +197,9 @@ class OracleState:
         return dict(n_encode=int(s[0]), n_decode_tokens=int(s[1]), n_fallbacks=int(s[2]),
                     seeks=[self._l.orc_full_window_seek(self.h, w) for w in range(nw)],
                     temps=[self._l.orc_full_window_temperature(self.h, w) for w in range(nw)])
+
+    def window_tokens(self, w: int):
+        return [self._l.orc_full_window_token(self.h, w, i) for i in range(self._l.orc_full_window_n_tokens(self.h, w))]
 
     def lang_id(self) -> int:
         return self._l.orc_full_lang_id(self.h)

@@ -169,4 +169,23 @@ ORC_API void orc_full_stats(void* sp, int* out4) {
 }
 ORC_API int orc_full_window_seek(void* sp, int w) { return ((State*)sp)->window_seeks[w]; }
 ORC_API float orc_full_window_temperature(void* sp, int w) { return ((State*)sp)->window_temps[w]; }
+ORC_API int orc_full_window_n_tokens(void* sp, int w) { return (int)((State*)sp)->window_tokens[w].size(); }
+ORC_API int orc_full_window_token(void* sp, int w, int i) { return ((State*)sp)->window_tokens[w][i]; }
+
+// models the bf16 compute mode of the product, which re-rounds the f16-stored weights to bf16 at load time
+// (a bf16-rounded f16 value is still exactly representable in f16, so the storage type does not change)
+static void round_mat_bf16(Mat& m) {
+    if (m.is_f16) for (auto& h : m.h) h = f32_to_f16(round_bf16(f16_to_f32(h)));
+    else for (auto& f : m.f) f = round_bf16(f);
+}
+ORC_API void orc_model_round_weights_bf16(void* mp) {
+    Model* m = (Model*)mp;
+    round_mat_bf16(m->conv1);
+    round_mat_bf16(m->conv2);
+    round_mat_bf16(m->tok_emb);
+    auto attn = [](AttnW& a) { round_mat_bf16(a.q); round_mat_bf16(a.k); round_mat_bf16(a.v); round_mat_bf16(a.o); };
+    for (auto& L : m->enc) { attn(L.attn); round_mat_bf16(L.mlp0); round_mat_bf16(L.mlp2); }
+    for (auto& L : m->dec) { attn(L.attn); attn(L.cross); round_mat_bf16(L.mlp0); round_mat_bf16(L.mlp2); }
+}
+
 ORC_API int orc_lang_id(const char* code) { return lang_id_from_code(code); }

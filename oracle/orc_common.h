@@ -196,6 +196,8 @@ struct State {
     int n_encode = 0, n_decode_tokens = 0, n_fallbacks = 0;
     std::vector<int> window_seeks;       // seek of every encoded window
     std::vector<float> window_temps;     // temperature finally accepted per window
+    std::vector<std::vector<int>> window_tokens;  // accepted decoder's raw token ids per window (segments drop the
+                                                  // second timestamp of a pair, so they cannot be teacher-forced)
 };
 
 void process_logits(const Model& m, const FullParams& p, Decoder& dec, float temperature, bool is_initial);

@@ -166,6 +166,7 @@ int full(State& st, const FullParams& p, const float* pcm, int n) {
     st.n_encode = st.n_decode_tokens = st.n_fallbacks = 0;
     st.window_seeks.clear();
     st.window_temps.clear();
+    st.window_tokens.clear();
     if (n <= 200) return -1;  // cannot reflect-pad: "failed to compute log mel spectrogram"
     if (p.strategy != 0) return -101;  // beam search: see orc_beam (not restated yet)
 
@@ -358,6 +359,11 @@ int full(State& st, const FullParams& p, const float* pcm, int n) {
             st.n_fallbacks++;
         }
         st.window_temps.push_back(t_accepted);
+        {
+            std::vector<int> ids;
+            for (const TokenData& t : st.decoders[best_decoder_id].tokens) ids.push_back(t.id);
+            st.window_tokens.push_back(std::move(ids));
+        }
 
         // output
         {

@@ -1,7 +1,8 @@
 """Freezes the oracle's own full() results on the `micro` model (token ids, segment times) into
 tests/golden/oracle_micro_full.npz so that (a) later edits of the oracle cannot drift silently and
 (b) the GPU parity tests have a committed vector besides the live comparison.
-fp32-parity numerics (gelu = f16 table, no activation rounding), temperature_inc = 0 (greedy only: the
+fp32-parity numerics (tanh GELU in f32, no activation rounding: IEEE-f32-clean, no f16 table whose rounding
+boundaries would amplify summation-order noise into token flips), temperature_inc = 0 (greedy only: the
 t>0 path draws from std::mt19937 whose stream depends on call history).
 Run from the repo root:  python tests/golden/make_oracle_golden.py
 """
@@ -18,7 +19,7 @@ from oracle import oracle as O  # noqa: E402
 seeds = [1, 2, 3, 4, 5, 6, 7]
 n_samples = [480000, 480000, 480000, 480000, 123457, 17600, 800000]
 m = O.OracleModel(synth.model_path("micro"))
-st = O.OracleState(m, gelu=O.GELU_TANH_F16LUT, act_round=O.ACT_NONE)
+st = O.OracleState(m, gelu=O.GELU_TANH, act_round=O.ACT_NONE)
 tokens, times, tok_off, seg_off = [], [], [0], [0]
 for seed, n in zip(seeds, n_samples):
     p = default_full_params()

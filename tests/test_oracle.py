@@ -193,7 +193,7 @@ def test_full_short_audio_returns_no_segments(micro_oracle):
 def test_full_golden(micro_oracle):
     """Token ids / timestamps of the oracle itself, frozen (tests/golden/make_oracle_golden.py)."""
     g = np.load(os.path.join(GOLD, "oracle_micro_full.npz"), allow_pickle=False)
-    st = O.OracleState(micro_oracle, gelu=O.GELU_TANH_F16LUT, act_round=O.ACT_NONE)
+    st = O.OracleState(micro_oracle, gelu=O.GELU_TANH, act_round=O.ACT_NONE)
     for k, seed in enumerate(g["seeds"]):
         p = default_full_params()
         p.temperature_inc = float(g["temperature_inc"])
