@@ -130,9 +130,3 @@ int launch_encoder_attention_simple(const void* qkv, void* out, int type, int B,
 
 }  // namespace oh
 
-namespace oh {
-// placeholder until the tensor-core flash kernel lands: same result through the simple kernel
-int launch_encoder_attention_mma(const void* qkv, void* out, int type, int B, int Tn, int d, cudaStream_t st) {
-    return launch_encoder_attention_simple(qkv, out, type, B, Tn, d, st);
-}
-}  // namespace oh

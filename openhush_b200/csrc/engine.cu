@@ -366,11 +366,15 @@ int run_encoder(oh_state* st, int nw, int slot0, float* d_enc_f32_out) {
     // cross-attention K/V of every decoder layer, straight into the slots' caches: [L][slots][T][2d]
     for (int l = 0; l < hp.n_text_layer; ++l) {
         const DecLayer& D = m.dec[l];
-        GemmArgs g;
-        g.A = st->h.p; g.a_type = act; g.lda = d; g.rows = M;
+        GemmArgs g;  // one "batch" per window so that the slot index separates from the row index
+        g.A = st->h.p; g.a_type = act; g.lda = d; g.batch = nw; g.rows = T; g.a_bstride = (long long)T * d;
         g.W = D.xkv.w; g.N = 2 * d; g.K = d; g.bias = D.xkv.b;
         g.C = (char*)st->xkv.p + ((size_t)l * st->max_batch + slot0) * T * 2 * d * e;
-        g.c_type = act; g.ldc = 2 * d;
+        g.c_type = act;
+        g.c_bstride = (long long)T * 2 * d;       // one slot: [2 (k,v)][heads][T][64]
+        g.c_hsplit = kHeadDim;                    // column n = (kv * heads + head) * 64 + c
+        g.c_hstride = (long long)T * kHeadDim;
+        g.ldc = kHeadDim;
         if ((rc = gemm(st, g))) return rc;
     }
     return OH_OK;

@@ -128,7 +128,8 @@ __global__ void __launch_bounds__(THREADS) gemm_simt_kernel(GemmArgs g) {
                 else v = gelu_fast(v);
             }
             if (rrow) v += rrow[n];
-            crow[n] = Cvt<TC>::from_f32(v);
+            if (g.c_hsplit > 0) crow[(long long)(n / g.c_hsplit) * g.c_hstride + (n % g.c_hsplit)] = Cvt<TC>::from_f32(v);
+            else crow[n] = Cvt<TC>::from_f32(v);
         }
     }
 }

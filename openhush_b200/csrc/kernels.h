@@ -64,6 +64,10 @@ struct GemmArgs {
     // above is unchanged; the tensor-core kernel loads tap t through its own tensor map based at A + t*tap_k.
     int n_taps = 1;
     int tap_k = 0;
+    // head-split store (cross-attention K/V cache, contiguous per head): when c_hsplit > 0 column n goes to
+    //   C[b*c_bstride + (n / c_hsplit) * c_hstride + i*ldc + (n % c_hsplit)]      (c_hsplit must be a multiple of 32)
+    int c_hsplit = 0;
+    long long c_hstride = 0;
 };
 // one-off numerical self-check of the tcgen05 path against the SIMT kernel (called at context creation)
 int gemm_tc_selftest(cudaStream_t st, float* max_rel_err);
