@@ -131,7 +131,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--arch", default="large-v3")
-    ap.add_argument("--batch", type=int, default=64, help="30 s windows per GPU per step")
+    ap.add_argument("--batch", type=int, default=256, help="30 s windows (independent transcription jobs) per GPU per step")
+    ap.add_argument("--slots", type=int, default=128, help="decoder rows / KV-cache slots resident per GPU (oh_context_params.max_batch)")
     ap.add_argument("--compute", default="f16", choices=["f16", "bf16", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -166,7 +167,8 @@ def main():
 
     B, K, W = args.batch, args.steps, args.warmup
     ctype = {"f16": COMPUTE_F16, "bf16": COMPUTE_BF16, "f32": COMPUTE_F32}[args.compute]
-    ctx = lib.Context(path, compute_type=ctype, gpu_device=local_rank, max_batch=B)
+    S = min(args.slots, B)
+    ctx = lib.Context(path, compute_type=ctype, gpu_device=local_rank, max_batch=S)
     st = lib.State(ctx)
     stream = torch.cuda.current_stream()
     st.set_stream(stream.cuda_stream)
@@ -242,7 +244,7 @@ def main():
     st.profile(False)
     # exact-bytes measurement of the decode attention: a stage decode step with every row active
     st.profile(True)
-    toks1 = np.full((B, 1), ctx.sot, dtype=np.int32)
+    toks1 = np.full((S, 1), ctx.sot, dtype=np.int32)
     for i in range(4):
         st.decode(toks1, 8 + i)
     rep_dec = st.profile_report()
@@ -300,7 +302,8 @@ def main():
         line = dict(metric="audio_seconds_per_second", value=value, unit="audio-s/s", n_gpus=world, steps=K, warmup=W, ms_per_step=ms / K,
                     higher_is_better=True, scaling="weak", vs_baseline=None, dtype=args.compute, data="synthetic",
                     config=dict(workload=f"whisper {args.arch} batched greedy (temperature_inc=0), independent 30 s windows of a synthetic recording, "
-                                         f"{B} windows per GPU per step", arch=args.arch, windows_per_gpu_per_step=B, window_seconds=WINDOW_S,
+                                         f"{B} windows per GPU per step over {S} resident decoder rows", arch=args.arch, windows_per_gpu_per_step=B,
+                                decoder_rows_per_gpu=S, window_seconds=WINDOW_S,
                                 weights="random-init, ggml-<arch>.bin format, seed 1234", l2="per-step inputs and weights exceed the 126 MB L2",
                                 gemm_backend=st.gemm_backend()),
                     clocks=clocks,

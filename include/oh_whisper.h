@@ -58,7 +58,8 @@ typedef struct oh_context_params {
     int flash_attn;   /* accepted for ABI shape; attention is always fused                            */
     int gpu_device;   /* CUDA ordinal; the multi-GPU workers set this (config.rs:921-929 gpu.devices) */
     int compute_type; /* enum oh_compute_type; default OH_COMPUTE_F16                                 */
-    int max_batch;    /* largest batch oh_full_batch will be given; sizes the KV caches (default 1)   */
+    int max_batch;    /* decoder rows / KV-cache slots resident on the GPU (default 1); oh_full_batch may be   */
+                      /* given more items than this: they queue for a free slot                                */
 } oh_context_params;
 
 enum oh_sampling_strategy { OH_SAMPLING_GREEDY = 0, OH_SAMPLING_BEAM_SEARCH = 1 };

@@ -1,4 +1,5 @@
 // extern "C" surface of libohwhisper.so — see include/oh_whisper.h for the whisper.h symbol each entry replaces.
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -73,6 +74,11 @@ OH_API oh_context* oh_init_from_file(const char* path_model, oh_context_params p
                 return nullptr;
             }
             selftest_rc = gemm_tc_selftest(nullptr, &selftest_err);
+            if (selftest_rc == OH_OK) {
+                float e2 = -1.0f;
+                selftest_rc = gemm_skinny_selftest(nullptr, &e2);
+                if (selftest_rc == OH_OK) selftest_err = std::max(selftest_err, e2);
+            }
             g_selftest_err = selftest_err;
         }
         if (!force_simt && (selftest_rc != OH_OK || !(selftest_err >= 0.0f && selftest_err < 2e-3f))) {

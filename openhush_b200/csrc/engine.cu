@@ -100,6 +100,7 @@ int state_alloc(oh_state* st) {
     if (const char* s = getenv("OH_ATTN")) st->attn_mode = strcmp(s, "simple") == 0 ? 1 : 0;
     if (const char* s = getenv("OH_GRAPHS")) st->use_graphs = atoi(s) != 0;
     if (const char* s = getenv("OH_GELU")) st->gelu_lut_f32 = strcmp(s, "lut") == 0;
+    if (const char* s = getenv("OH_SKINNY")) st->skinny_mode = atoi(s) == 0 ? 1 : 0;  // OH_SKINNY=0: decode mat-muls through the tcgen05 kernel
 
     OH_CUDA_CHECK(cudaStreamCreateWithFlags(&st->own_stream, cudaStreamNonBlocking));
     st->stream = st->own_stream;
@@ -274,6 +275,10 @@ static int gemm(oh_state* st, GemmArgs g) {
     g.round_type = act;
     if (g.gelu != GELU_NONE) g.gelu = act == DT_F32 ? (st->gelu_lut_f32 ? GELU_LUT : GELU_TANH) : GELU_FAST;
     if (act != DT_F32 && st->gemm_mode == 0 && gemm_tc_available()) {
+        if (g.batch * g.rows <= 256 && st->skinny_mode == 0) {
+            int rc = launch_gemm_skinny(g, st->stream);
+            if (rc != OH_ERR_UNSUPPORTED) return rc;
+        }
         int rc = launch_gemm_tc(g, st->stream);
         if (rc != OH_ERR_UNSUPPORTED) return rc;
     }
@@ -281,7 +286,7 @@ static int gemm(oh_state* st, GemmArgs g) {
 }
 
 // ------------------------------------------------------------------------------------------------ encoder
-int run_encoder(oh_state* st, int nw, int slot0, float* d_enc_f32_out) {
+int run_encoder(oh_state* st, int nw, int slot0, float* d_enc_f32_out, const int* slot_list) {
     const Model& m = *st->ctx->model;
     const HParams& hp = m.hp;
     const int d = hp.n_audio_state, C = hp.n_mels, T = hp.n_audio_ctx, act = st->ctx->act_type;
@@ -364,18 +369,28 @@ int run_encoder(oh_state* st, int nw, int slot0, float* d_enc_f32_out) {
         if ((rc = launch_layernorm(x, M, d, m.ln_post.w, m.ln_post.b, d_enc_f32_out, DT_F32, s))) return rc;
     }
     // cross-attention K/V of every decoder layer, straight into the slots' caches: [L][slots][T][2d]
-    for (int l = 0; l < hp.n_text_layer; ++l) {
-        const DecLayer& D = m.dec[l];
-        GemmArgs g;  // one "batch" per window so that the slot index separates from the row index
-        g.A = st->h.p; g.a_type = act; g.lda = d; g.batch = nw; g.rows = T; g.a_bstride = (long long)T * d;
-        g.W = D.xkv.w; g.N = 2 * d; g.K = d; g.bias = D.xkv.b;
-        g.C = (char*)st->xkv.p + ((size_t)l * st->max_batch + slot0) * T * 2 * d * e;
-        g.c_type = act;
-        g.c_bstride = (long long)T * 2 * d;       // one slot: [2 (k,v)][heads][T][64]
-        g.c_hsplit = kHeadDim;                    // column n = (kv * heads + head) * 64 + c
-        g.c_hstride = (long long)T * kHeadDim;
-        g.ldc = kHeadDim;
-        if ((rc = gemm(st, g))) return rc;
+    // slot_list (optional): window w goes to slot slot_list[w]; runs of consecutive slots share one mat-mul
+    for (int w0 = 0; w0 < nw;) {
+        int w1 = w0 + 1;
+        if (slot_list)
+            while (w1 < nw && slot_list[w1] == slot_list[w1 - 1] + 1) ++w1;
+        else
+            w1 = nw;
+        const int first_slot = slot_list ? slot_list[w0] : slot0;
+        for (int l = 0; l < hp.n_text_layer; ++l) {
+            const DecLayer& D = m.dec[l];
+            GemmArgs g;  // one "batch" per window so that the slot index separates from the row index
+            g.A = (char*)st->h.p + (size_t)w0 * T * d * e; g.a_type = act; g.lda = d; g.batch = w1 - w0; g.rows = T; g.a_bstride = (long long)T * d;
+            g.W = D.xkv.w; g.N = 2 * d; g.K = d; g.bias = D.xkv.b;
+            g.C = (char*)st->xkv.p + ((size_t)l * st->max_batch + first_slot) * T * 2 * d * e;
+            g.c_type = act;
+            g.c_bstride = (long long)T * 2 * d;       // one slot: [2 (k,v)][heads][T][64]
+            g.c_hsplit = kHeadDim;                    // column n = (kv * heads + head) * 64 + c
+            g.c_hstride = (long long)T * kHeadDim;
+            g.ldc = kHeadDim;
+            if ((rc = gemm(st, g))) return rc;
+        }
+        w0 = w1;
     }
     return OH_OK;
 }
@@ -758,8 +773,8 @@ int run_full(oh_state* st, const oh_full_params& p, const float* const* pcm, con
     const Model& m = *st->ctx->model;
     const Vocab& vc = m.vocab;
     const HParams& hp = m.hp;
-    if (batch < 1 || batch > st->max_batch) {
-        set_error("batch exceeds oh_context_params.max_batch");
+    if (batch < 1) {
+        set_error("empty batch");
         return OH_ERR_INVALID;
     }
     if (p.strategy != OH_SAMPLING_GREEDY) {
@@ -815,92 +830,259 @@ int run_full(oh_state* st, const oh_full_params& p, const float* const* pcm, con
     }
 
     ClipMeta cm = clip_meta_view(st->clip_meta.p, std::max<size_t>(batch, st->max_batch));
-    const int T = hp.n_audio_ctx;
-    std::vector<int> clip_of_slot, seek_of_slot;
+
+    // ------------------------------------------------------------------------------------------------------------
+    // Scheduler.  Every KV-cache slot is one decoder row.  Windows are admitted to free slots (encoder pass over the
+    // admitted windows, cross-KV straight into their slots), rows decode greedily under the device state machine, and
+    // every CHECK steps the host looks at the `active` flags: a finished row is scored, its segments are emitted, its
+    // item's seek advances, and the item's next window (A.5: windows of one call are sequentially dependent) is queued
+    // for admission while the other rows keep decoding — rows never wait for the slowest row of a "round".
+    // Rows that need a temperature fallback are parked and resolved together once the greedy rows have drained.
+    // ------------------------------------------------------------------------------------------------------------
+    struct SlotInfo {
+        int item = -1;
+        bool armed = false;
+        std::vector<int> prompt;
+    };
+    const int nslots = std::min(batch, st->max_batch);  // more items than slots: items queue for a free slot
+    const int n_max = hp.n_text_ctx / 2 - 4;
+    const bool lockstep = getenv("OH_SCHED") && strcmp(getenv("OH_SCHED"), "lockstep") == 0;
+    const int CHECK = 8;
+    const int admit_threshold = lockstep ? nslots : std::max(1, std::min(8, nslots / 8));
+    std::vector<SlotInfo> slots(nslots);
+    std::vector<int> free_slots;
+    for (int i = nslots - 1; i >= 0; --i) free_slots.push_back(i);  // pop_back yields ascending slot ids
+    std::vector<int> need_window;                                     // items whose next window awaits admission
+    for (int i = 0; i < batch; ++i) {
+        Item& it = st->items[i];
+        if (it.done) continue;
+        if (it.seek + 100 >= it.seek_end) it.done = true;
+        else need_window.push_back(i);
+    }
+    std::vector<PassRow> parked;  // rows waiting for a temperature fallback (slot stays reserved)
+    SeqLayout lay(st->max_batch);
+    int32_t* hb = (int32_t*)st->pinned;
+    DecodeSeqState hs = seq_view(hb, lay);
+    memset(hb, 0, lay.total_words * 4);
+    OH_CUDA_CHECK(cudaMemcpyAsync(st->seq_dev.p, hb, lay.total_words * 4, cudaMemcpyHostToDevice, s));
+    st->timings.h2d_bytes += (long long)lay.total_words * 4;
+    bool rules_dirty = true;
+    int n_armed = 0;
+    const size_t scalar_words = lay.prompt_off + (size_t)lay.rows * kMaxPrompt;  // scalars + prompts
+    const size_t token_words = lay.counter_off - lay.tok_off[0];
+
+    auto build_prompt = [&](const Item& it, float t_cur, std::vector<int>& prompt) {
+        prompt.clear();
+        if (!it.prompt_past.empty() && t_cur < 0.5f && p.n_max_text_ctx > 0) {
+            const int n_take = std::min(std::min(p.n_max_text_ctx, hp.n_text_ctx / 2), (int)it.prompt_past.size());
+            prompt.push_back(vc.token_prev);
+            prompt.insert(prompt.end(), it.prompt_past.end() - n_take, it.prompt_past.end());
+        }
+        prompt.insert(prompt.end(), prompt_init.begin(), prompt_init.end());
+    };
+    // accept a finished window: segments, prompt carry-over, seek advance, next window or done
+    auto finish_window = [&](int slot, const PassResult& res) {
+        SlotInfo& si = slots[slot];
+        Item& it = st->items[si.item];
+        emit_segments(m, p, it, res, si.prompt, (int)prompt_init.size());
+        if (it.seek + 100 >= it.seek_end) it.done = true;
+        else need_window.push_back(si.item);
+        si.item = -1;
+        si.armed = false;
+        free_slots.push_back(slot);
+    };
+    // score one t=0 result; returns true if it is accepted at this temperature index
+    auto evaluate = [&](PassResult& pr, size_t ti) {
+        if (!pr.failed) {
+            pr.tokens.resize(std::min<size_t>(pr.tokens.size(), (size_t)pr.result_len));
+            sequence_score(p, pr);
+            if (pr.result_len > 32 && pr.entropy < p.entropy_thold) pr.failed = true;
+        }
+        if (ti + 1 != temperatures.size() && (pr.failed || pr.avg_logprobs < p.logprob_thold)) return false;
+        return true;
+    };
+
     while (true) {
-        std::vector<int> act;
-        for (int i = 0; i < batch; ++i) {
-            Item& it = st->items[i];
-            if (it.done) continue;
-            if (it.seek + 100 >= it.seek_end) {
-                it.done = true;
+        // ---- admission: encode the next windows of waiting items into free slots
+        if (!need_window.empty() && !free_slots.empty() && (n_armed == 0 || (!lockstep && (int)need_window.size() >= admit_threshold))) {
+            auto t0 = clk::now();
+            const int k = (int)std::min(need_window.size(), free_slots.size());
+            std::sort(free_slots.begin(), free_slots.end(), std::greater<int>());
+            std::vector<int> win_item(need_window.begin(), need_window.begin() + k), win_slot(k), win_seek(k);
+            need_window.erase(need_window.begin(), need_window.begin() + k);
+            for (int i = 0; i < k; ++i) {
+                win_slot[i] = free_slots.back();
+                free_slots.pop_back();
+                win_seek[i] = st->items[win_item[i]].seek;
+            }
+            OH_CUDA_CHECK(cudaMemcpyAsync(cm.clip_of_slot, win_item.data(), k * 4, cudaMemcpyHostToDevice, s));
+            OH_CUDA_CHECK(cudaMemcpyAsync(cm.seek_of_slot, win_seek.data(), k * 4, cudaMemcpyHostToDevice, s));
+            for (int c0 = 0; c0 < k; c0 += st->enc_chunk) {
+                const int nw = std::min(st->enc_chunk, k - c0);
+                WindowGatherArgs wa;
+                wa.raw = (const float*)st->mel_raw.p;
+                wa.ld = st->mel_ld;
+                wa.n_mel = hp.n_mels;
+                wa.max_key = cm.max_key;
+                wa.n_active = cm.n_active;
+                wa.n_len = cm.n_len;
+                wa.clip_of_slot = cm.clip_of_slot + c0;
+                wa.seek_of_slot = cm.seek_of_slot + c0;
+                if ((rc = launch_window_gather(wa, nw, st->xin.p, st->ctx->act_type, s))) return rc == OH_ERR_CUDA ? rc : OH_ERR_ENCODE;
+                if ((rc = run_encoder(st, nw, 0, nullptr, win_slot.data() + c0))) return rc == OH_ERR_CUDA ? rc : OH_ERR_ENCODE;
+                st->timings.n_windows += nw;
+            }
+            // arm the rows (the host mirror of the scalars is current: nothing ran since the last download)
+            for (int i = 0; i < k; ++i) {
+                const int r = win_slot[i];
+                SlotInfo& si = slots[r];
+                Item& it = st->items[win_item[i]];
+                if (it.seek > 0 && it.seek + 500 >= it.seek_end) it.prompt_past.clear();  // short tail: drop the prompt (upstream behaviour)
+                si.item = win_item[i];
+                si.armed = true;
+                build_prompt(it, temperatures[0], si.prompt);
+                const int pl = (int)si.prompt.size();
+                if (pl > kMaxPrompt) {
+                    set_error("prompt too long");
+                    return OH_ERR_DECODE;
+                }
+                hs.slot[r] = r;
+                hs.active[r] = 1;
+                hs.pos[r] = 0;
+                hs.cur_token[r] = si.prompt[0];
+                hs.prompt_len[r] = pl;
+                for (int j = 0; j < pl; ++j) hs.prompt[(size_t)r * kMaxPrompt + j] = si.prompt[j];
+                hs.n_gen[r] = 0;
+                hs.has_ts[r] = 0;
+                hs.seek_delta[r] = 100 * 30;
+                hs.result_len[r] = 0;
+                hs.failed[r] = 0;
+                hs.completed[r] = 0;
+                hs.seek[r] = it.seek;
+                hs.seek_end[r] = it.seek_end;
+            }
+            OH_CUDA_CHECK(cudaMemcpyAsync(st->seq_dev.p, hb, scalar_words * 4, cudaMemcpyHostToDevice, s));
+            st->timings.h2d_bytes += (long long)scalar_words * 4;
+            n_armed += k;
+            OH_CUDA_CHECK(cudaStreamSynchronize(s));
+            st->timings.encode_ms += std::chrono::duration<float, std::milli>(clk::now() - t0).count();
+        }
+        if (n_armed == 0) {
+            if (!parked.empty()) {
+                // ---- temperature fallback for the parked rows, lock-step per temperature (A.5 ladder)
+                auto t0 = clk::now();
+                std::vector<PassRow> pending;
+                pending.swap(parked);
+                for (size_t ti = 1; ti < temperatures.size() && !pending.empty(); ++ti) {
+                    for (PassRow& pr : pending) {
+                        build_prompt(st->items[pr.item], temperatures[ti], pr.prompt);
+                        slots[pr.slot].prompt = pr.prompt;
+                    }
+                    std::vector<PassResult> res;
+                    if ((rc = decode_pass(st, p, no_timestamps, pending, temperatures[ti], res))) return rc == OH_ERR_CUDA ? rc : OH_ERR_DECODE;
+                    std::vector<PassRow> next;
+                    for (size_t r = 0; r < pending.size(); ++r) {
+                        if (evaluate(res[r], ti)) finish_window(pending[r].slot, res[r]);
+                        else {
+                            st->timings.n_fallbacks++;
+                            next.push_back(pending[r]);
+                        }
+                    }
+                    pending.swap(next);
+                }
+                rules_dirty = true;
+                memset(hb, 0, lay.total_words * 4);  // decode_pass reused the block: start the greedy rows from a clean slate
+                OH_CUDA_CHECK(cudaMemcpyAsync(st->seq_dev.p, hb, lay.total_words * 4, cudaMemcpyHostToDevice, s));
+                st->timings.decode_ms += std::chrono::duration<float, std::milli>(clk::now() - t0).count();
                 continue;
             }
-            act.push_back(i);
+            if (need_window.empty()) break;
+            continue;  // admission fires because nothing is armed
         }
-        if (act.empty()) break;
-        auto t0 = clk::now();
-        // ---- encoder over the active windows, enc_chunk at a time; slot = index in `act`
-        clip_of_slot.assign(act.begin(), act.end());
-        seek_of_slot.resize(act.size());
-        for (size_t k = 0; k < act.size(); ++k) seek_of_slot[k] = st->items[act[k]].seek;
-        OH_CUDA_CHECK(cudaMemcpyAsync(cm.clip_of_slot, clip_of_slot.data(), act.size() * 4, cudaMemcpyHostToDevice, s));
-        OH_CUDA_CHECK(cudaMemcpyAsync(cm.seek_of_slot, seek_of_slot.data(), act.size() * 4, cudaMemcpyHostToDevice, s));
-        for (size_t c0 = 0; c0 < act.size(); c0 += st->enc_chunk) {
-            const int nw = (int)std::min<size_t>(st->enc_chunk, act.size() - c0);
-            WindowGatherArgs wa;
-            wa.raw = (const float*)st->mel_raw.p;
-            wa.ld = st->mel_ld;
-            wa.n_mel = hp.n_mels;
-            wa.max_key = cm.max_key;
-            wa.n_active = cm.n_active;
-            wa.n_len = cm.n_len;
-            wa.clip_of_slot = cm.clip_of_slot + c0;
-            wa.seek_of_slot = cm.seek_of_slot + c0;
-            if ((rc = launch_window_gather(wa, nw, st->xin.p, st->ctx->act_type, s))) return rc == OH_ERR_CUDA ? rc : OH_ERR_ENCODE;
-            if ((rc = run_encoder(st, nw, (int)c0, nullptr))) return rc == OH_ERR_CUDA ? rc : OH_ERR_ENCODE;
-            st->timings.n_windows += nw;
-        }
-        OH_CUDA_CHECK(cudaStreamSynchronize(s));
+        // ---- CHECK greedy steps for every slot (inactive rows exit at once)
         auto t1 = clk::now();
-        st->timings.encode_ms += std::chrono::duration<float, std::milli>(t1 - t0).count();
-
-        // ---- decode with the temperature ladder
-        for (size_t k = 0; k < act.size(); ++k) {
-            Item& it = st->items[act[k]];
-            if (it.seek > 0 && it.seek + 500 >= it.seek_end) it.prompt_past.clear();  // short tail: drop the prompt (upstream behaviour)
+        if (rules_dirty) {
+            DecodeRules R;
+            R.n_vocab = vc.n_vocab; R.eot = vc.token_eot; R.sot = vc.token_sot; R.translate = vc.token_translate; R.transcribe = vc.token_transcribe;
+            R.solm = vc.token_solm; R.prev = vc.token_prev; R.nosp = vc.token_nosp; R.tok_not = vc.token_not; R.beg = vc.token_beg;
+            R.blank = vc.token_blank; R.n_lang = vc.num_languages();
+            R.no_timestamps = no_timestamps; R.suppress_blank = p.suppress_blank; R.single_segment = p.single_segment; R.max_tokens = p.max_tokens;
+            R.n_max = n_max;
+            R.tid0_initial = p.max_initial_ts > 0.0f ? (int)std::round(p.max_initial_ts / (30.0f / (float)hp.n_audio_ctx)) : -1;
+            R.temperature = temperatures[0];
+            OH_CUDA_CHECK(cudaMemcpyAsync(st->rules_dev.p, &R, sizeof R, cudaMemcpyHostToDevice, s));
+            OH_CUDA_CHECK(cudaStreamSynchronize(s));
+            rules_dirty = false;
         }
-        std::vector<PassRow> pending;
-        for (size_t k = 0; k < act.size(); ++k) pending.push_back(PassRow{act[k], (int)k, {}});
-        std::vector<PassResult> accepted(act.size());
-        std::vector<std::vector<int>> accepted_prompt(act.size());
-        for (size_t ti = 0; ti < temperatures.size() && !pending.empty(); ++ti) {
-            const float t_cur = temperatures[ti];
-            for (PassRow& pr : pending) {
-                const Item& it = st->items[pr.item];
-                pr.prompt.clear();
-                if (!it.prompt_past.empty() && t_cur < 0.5f && p.n_max_text_ctx > 0) {
-                    const int n_take = std::min(std::min(p.n_max_text_ctx, hp.n_text_ctx / 2), (int)it.prompt_past.size());
-                    pr.prompt.push_back(vc.token_prev);
-                    pr.prompt.insert(pr.prompt.end(), it.prompt_past.end() - n_take, it.prompt_past.end());
+        if (temperatures[0] >= 1e-6f) {
+            // a non-zero base temperature samples on the host from the first pass on: use the lock-step path for everything
+            for (int r = 0; r < nslots; ++r)
+                if (slots[r].armed) parked.push_back(PassRow{slots[r].item, r, slots[r].prompt});
+            memset(hb, 0, scalar_words * 4);
+            n_armed = 0;
+            // run them as "fallback index 0"
+            std::vector<PassRow> pending;
+            pending.swap(parked);
+            for (size_t ti = 0; ti < temperatures.size() && !pending.empty(); ++ti) {
+                for (PassRow& pr : pending) {
+                    build_prompt(st->items[pr.item], temperatures[ti], pr.prompt);
+                    slots[pr.slot].prompt = pr.prompt;
                 }
-                pr.prompt.insert(pr.prompt.end(), prompt_init.begin(), prompt_init.end());
+                std::vector<PassResult> res;
+                if ((rc = decode_pass(st, p, no_timestamps, pending, temperatures[ti], res))) return rc == OH_ERR_CUDA ? rc : OH_ERR_DECODE;
+                std::vector<PassRow> next;
+                for (size_t r = 0; r < pending.size(); ++r) {
+                    if (evaluate(res[r], ti)) finish_window(pending[r].slot, res[r]);
+                    else {
+                        st->timings.n_fallbacks++;
+                        next.push_back(pending[r]);
+                    }
+                }
+                pending.swap(next);
             }
-            std::vector<PassResult> res;
-            if ((rc = decode_pass(st, p, no_timestamps, pending, t_cur, res))) return rc == OH_ERR_CUDA ? rc : OH_ERR_DECODE;
-            std::vector<PassRow> next;
-            for (size_t r = 0; r < pending.size(); ++r) {
-                PassResult& pr = res[r];
-                if (!pr.failed) {
-                    pr.tokens.resize(std::min<size_t>(pr.tokens.size(), (size_t)pr.result_len));
-                    sequence_score(p, pr);
-                    if (pr.result_len > 32 && pr.entropy < p.entropy_thold) pr.failed = true;
+            rules_dirty = true;
+            memset(hb, 0, lay.total_words * 4);
+            OH_CUDA_CHECK(cudaMemcpyAsync(st->seq_dev.p, hb, lay.total_words * 4, cudaMemcpyHostToDevice, s));
+            continue;
+        }
+        for (int step = 0; step < CHECK; ++step) {
+            if ((rc = run_decode_step_graph(st, nslots))) return rc == OH_ERR_CUDA ? rc : OH_ERR_DECODE;
+            st->timings.n_decode_steps++;
+        }
+        OH_CUDA_CHECK(cudaMemcpyAsync(hb, st->seq_dev.p, scalar_words * 4, cudaMemcpyDeviceToHost, s));
+        OH_CUDA_CHECK(cudaStreamSynchronize(s));
+        st->timings.d2h_bytes += (long long)scalar_words * 4;
+        bool any_finished = false;
+        for (int r = 0; r < nslots; ++r)
+            if (slots[r].armed && !hs.active[r]) any_finished = true;
+        if (any_finished) {
+            OH_CUDA_CHECK(cudaMemcpyAsync(hb + lay.tok_off[0], (int32_t*)st->seq_dev.p + lay.tok_off[0], token_words * 4, cudaMemcpyDeviceToHost, s));
+            OH_CUDA_CHECK(cudaStreamSynchronize(s));
+            st->timings.d2h_bytes += (long long)token_words * 4;
+            for (int r = 0; r < nslots; ++r) {
+                if (!slots[r].armed || hs.active[r]) continue;
+                PassResult pr;
+                const int ng = hs.n_gen[r];
+                pr.tokens.resize(ng);
+                for (int i = 0; i < ng; ++i) {
+                    const size_t o = (size_t)r * kMaxGen + i;
+                    pr.tokens[i] = TokenData{hs.tok_id[o], hs.tok_tid[o], hs.tok_p[o], hs.tok_plog[o], hs.tok_pt[o], hs.tok_ptsum[o]};
                 }
-                bool success = true;
-                if (ti + 1 != temperatures.size()) {
-                    if (pr.failed || pr.avg_logprobs < p.logprob_thold) success = false;
-                }
-                if (success) {
-                    accepted[pending[r].slot] = std::move(pr);
-                    accepted_prompt[pending[r].slot] = pending[r].prompt;
-                } else {
+                pr.result_len = hs.result_len[r];
+                pr.seek_delta = hs.seek_delta[r];
+                pr.has_ts = hs.has_ts[r];
+                pr.failed = hs.failed[r];
+                pr.completed = hs.completed[r];
+                st->timings.n_tokens += ng;
+                slots[r].armed = false;
+                n_armed--;
+                if (evaluate(pr, 0)) finish_window(r, pr);
+                else {
                     st->timings.n_fallbacks++;
-                    next.push_back(pending[r]);
+                    parked.push_back(PassRow{slots[r].item, r, slots[r].prompt});
                 }
             }
-            pending.swap(next);
         }
-        for (size_t k = 0; k < act.size(); ++k) emit_segments(m, p, st->items[act[k]], accepted[k], accepted_prompt[k], (int)prompt_init.size());
         st->timings.decode_ms += std::chrono::duration<float, std::milli>(clk::now() - t1).count();
     }
     st->timings.total_ms = std::chrono::duration<float, std::milli>(clk::now() - t_begin).count();

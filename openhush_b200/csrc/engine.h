@@ -83,6 +83,7 @@ struct oh_state {
     bool use_graphs = true;
     int gemm_mode = 0;             // 0 auto (tcgen05 when 16-bit), 1 force SIMT
     int attn_mode = 0;             // 0 auto, 1 force the simple kernel
+    int skinny_mode = 0;           // 0: decode mat-muls use the weight-streaming kernel, 1: tcgen05 kernel
     bool gelu_lut_f32 = false;     // OH_GELU=lut: f32 mode evaluates GELU through ggml's f16 table instead of f32 tanh
     oh::Profiler* prof = nullptr;
     bool profiling = false;
@@ -102,7 +103,8 @@ void state_release(oh_state* st);
 
 // stages
 int run_mel(oh_state* st, const float* const* pcm, const int* n, int batch, bool pcm_on_device);
-int run_encoder(oh_state* st, int n_windows, int slot0, float* d_enc_f32_out /* nullable, [n_windows][1500][d] */);
+int run_encoder(oh_state* st, int n_windows, int slot0, float* d_enc_f32_out /* nullable, [n_windows][1500][d] */,
+                const int* slot_list = nullptr /* per-window KV slot; default slot0 + w */);
 int run_decode_step(oh_state* st, int rows, bool dump_probs);
 int run_full(oh_state* st, const oh_full_params& p, const float* const* pcm, const int* n, int batch, bool pcm_on_device);
 
