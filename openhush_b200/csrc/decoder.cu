@@ -377,6 +377,204 @@ __global__ void __launch_bounds__(128) attention_decode_online_kernel(const T* _
     }
 }
 
+// ------------------------------------------------- K8b (16-bit modes): cross attention fed by bulk async copies
+// The dominant HBM stream of a decode step: every row reads its slot's K and V (2 x 1500 x 64 per head, contiguous
+// per (slot, head)).  One CTA per (head, row): a producer warp keeps XA_STAGES bulk copies (cp.async.bulk, i.e. the
+// TMA engine in 1-D mode: global -> shared, completion on an mbarrier) in flight — 64 keys of K and of V per stage —
+// so the memory pipeline depth is set by shared memory, not by registers; 8 consumer warps (32 groups of 8 lanes)
+// read the staged rows with conflict-free 16-byte LDS, keep per-group online-softmax states and merge them at the end.
+constexpr int XA_STAGES = 6, XA_KEYS = 64, XA_CONSUMERS = 256, XA_THREADS = XA_CONSUMERS + 32;
+
+__device__ __forceinline__ uint32_t xa_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void xa_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void xa_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void xa_mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void xa_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) break;
+        if (clock64() - t0 > 8000000000LL) __trap();  // protocol bug: fail instead of hanging the GPU
+    }
+}
+__device__ __forceinline__ void xa_bulk_copy(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+template <typename T>
+__device__ __forceinline__ void xa_unpack8(const uint4& u, float (&v)[8]);
+template <>
+__device__ __forceinline__ void xa_unpack8<__half>(const uint4& u, float (&v)[8]) {
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(h[i]);
+        v[2 * i] = f.x;
+        v[2 * i + 1] = f.y;
+    }
+}
+template <>
+__device__ __forceinline__ void xa_unpack8<__nv_bfloat16>(const uint4& u, float (&v)[8]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(h[i]);
+        v[2 * i] = f.x;
+        v[2 * i + 1] = f.y;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(XA_THREADS) cross_attention_decode_bulk_kernel(const T* __restrict__ q, const T* __restrict__ xkv, DecodeSeqState s,
+                                                                                int d, int Tn, T* __restrict__ out) {
+    const int h = blockIdx.x, b = blockIdx.y;
+    if (!s.active[b]) return;
+    extern __shared__ __align__(128) uint8_t xa_smem[];
+    // layout: [stage][K 64x64 | V 64x64] (16 KB per stage), then merge scratch, then the barriers
+    constexpr int STAGE_BYTES = 2 * XA_KEYS * kHeadDim * 2;
+    T* stage0 = reinterpret_cast<T*>(xa_smem);
+    float* sm_o = reinterpret_cast<float*>(xa_smem + XA_STAGES * STAGE_BYTES);  // [32][64]
+    float* sm_m = sm_o + 32 * kHeadDim;                                           // [32]
+    float* sm_l = sm_m + 32;                                                      // [32]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm_l + 32);                      // full[STAGES], empty[STAGES]
+    const uint32_t bar0 = xa_smem_u32(bars);
+    auto full_bar = [&](int st) { return bar0 + 8u * st; };
+    auto empty_bar = [&](int st) { return bar0 + 8u * (XA_STAGES + st); };
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int H = d / kHeadDim;
+    const int slot = s.slot[b];
+    const T* Kg = xkv + (((size_t)slot * 2 + 0) * H + h) * Tn * kHeadDim;
+    const T* Vg = xkv + (((size_t)slot * 2 + 1) * H + h) * Tn * kHeadDim;
+    const int n_it = (Tn + XA_KEYS - 1) / XA_KEYS;
+
+    if (tid == 0) {
+        for (int st = 0; st < XA_STAGES; ++st) {
+            xa_mbar_init(full_bar(st), 1);
+            xa_mbar_init(empty_bar(st), XA_CONSUMERS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == XA_CONSUMERS / 32) {
+        // ===================== producer =====================
+        if (lane == 0) {
+            int st = 0;
+            uint32_t phase = 0;
+            for (int it = 0; it < n_it; ++it) {
+                xa_mbar_wait(empty_bar(st), phase ^ 1);
+                const int key0 = it * XA_KEYS;
+                const uint32_t bytes = (uint32_t)min(XA_KEYS, Tn - key0) * kHeadDim * 2;
+                const uint32_t dstK = xa_smem_u32(stage0) + st * STAGE_BYTES, dstV = dstK + STAGE_BYTES / 2;
+                xa_mbar_expect_tx(full_bar(st), 2 * bytes);
+                xa_bulk_copy(dstK, Kg + (size_t)key0 * kHeadDim, bytes, full_bar(st));
+                xa_bulk_copy(dstV, Vg + (size_t)key0 * kHeadDim, bytes, full_bar(st));
+                if (++st == XA_STAGES) {
+                    st = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else {
+        // ===================== consumers =====================
+        const int sub = lane & 7, grp = lane >> 3;
+        const int gidx = warp * 4 + grp;  // 0..31
+        float qv[8];
+        {
+            const T* qr = q + (size_t)b * d + h * kHeadDim + sub * 8;
+            const float sc = 0.125f * 1.44269504088896340736f;  // 1/sqrt(64) * log2(e)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) qv[i] = Cvt<T>::to_f32(qr[i]) * sc;
+        }
+        float m_run = -INFINITY, l_run = 0.0f, o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = 0.0f;
+        int st = 0;
+        uint32_t phase = 0;
+        for (int it = 0; it < n_it; ++it) {
+            xa_mbar_wait(full_bar(st), phase);
+            const uint8_t* sK = xa_smem + st * STAGE_BYTES;
+            const uint8_t* sV = sK + STAGE_BYTES / 2;
+            const int valid = min(XA_KEYS, Tn - it * XA_KEYS);
+            float sc2[2], kf[8];
+            uint4 vraw[2];
+            float mx = -INFINITY;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int key = gidx + 32 * u;
+                const uint4 kraw = *reinterpret_cast<const uint4*>(sK + key * 128 + sub * 16);
+                vraw[u] = *reinterpret_cast<const uint4*>(sV + key * 128 + sub * 16);
+                xa_unpack8<T>(kraw, kf);
+                float acc = 0.0f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc = fmaf(qv[i], kf[i], acc);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+                sc2[u] = key < valid ? acc : -INFINITY;
+                mx = fmaxf(mx, sc2[u]);
+            }
+            if (mx > -INFINITY) {
+                const float m_new = fmaxf(m_run, mx);
+                const float corr = exp2f(m_run - m_new);
+                m_run = m_new;
+                l_run *= corr;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] *= corr;
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    if (gidx + 32 * u < valid) {
+                        const float p = exp2f(sc2[u] - m_new);
+                        l_run += p;
+                        const float pr = Cvt<T>::to_f32(Cvt<T>::from_f32(p));
+                        float vf[8];
+                        xa_unpack8<T>(vraw[u], vf);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) o[i] = fmaf(pr, vf[i], o[i]);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) xa_mbar_arrive(empty_bar(st));  // this warp is done with the stage
+            if (++st == XA_STAGES) {
+                st = 0;
+                phase ^= 1;
+            }
+        }
+        if (sub == 0) {
+            sm_m[gidx] = m_run;
+            sm_l[gidx] = l_run;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sm_o[gidx * kHeadDim + sub * 8 + i] = o[i];
+    }
+    __syncthreads();
+    if (tid < kHeadDim) {
+        float M = -INFINITY;
+        for (int g2 = 0; g2 < 32; ++g2) M = fmaxf(M, sm_m[g2]);
+        float L = 0.0f, O = 0.0f;
+        for (int g2 = 0; g2 < 32; ++g2) {
+            const float w = sm_m[g2] == -INFINITY ? 0.0f : exp2f(sm_m[g2] - M);
+            L = fmaf(sm_l[g2], w, L);
+            O = fmaf(sm_o[g2 * kHeadDim + tid], w, O);
+        }
+        out[(size_t)b * d + h * kHeadDim + tid] = Cvt<T>::from_f32(O / L);
+    }
+}
+constexpr int XA_SMEM_BYTES = XA_STAGES * 2 * XA_KEYS * kHeadDim * 2 + 32 * kHeadDim * 4 + 64 * 4 + 2 * XA_STAGES * 8 + 64;
+
 // ------------------------------------------------------------------------------------------------ K9
 struct MaxIdx {
     float v;
@@ -610,7 +808,20 @@ int launch_cross_attention_decode(const void* q, const void* xkv, int type, cons
     if (T > 1504) return OH_ERR_INVALID;
     // algorithmic bytes: every row streams its slot's K and V once (all rows assumed active)
     ProfScope ps(PC_CROSS_ATTN, (double)rows * T * 2.0 * d * (type == DT_F32 ? 4 : 2), st);
+    static int use_bulk = -1;
+    if (use_bulk < 0) {
+        const char* e = getenv("OH_XATTN");
+        use_bulk = (e && strcmp(e, "online") == 0) ? 0 : 1;
+        if (cudaFuncSetAttribute(cross_attention_decode_bulk_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, XA_SMEM_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(cross_attention_decode_bulk_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, XA_SMEM_BYTES) != cudaSuccess)
+            use_bulk = 0;
+    }
     if (type == DT_F32) cross_attention_decode_kernel<float><<<grid, 128, 0, st>>>((const float*)q, (const float*)xkv, s, d, T, (float*)out);
+    else if (use_bulk && type == DT_F16)
+        cross_attention_decode_bulk_kernel<__half><<<grid, XA_THREADS, XA_SMEM_BYTES, st>>>((const __half*)q, (const __half*)xkv, s, d, T, (__half*)out);
+    else if (use_bulk)
+        cross_attention_decode_bulk_kernel<__nv_bfloat16><<<grid, XA_THREADS, XA_SMEM_BYTES, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)xkv, s, d, T,
+                                                                                                    (__nv_bfloat16*)out);
     else if (type == DT_F16)
         attention_decode_online_kernel<__half, false><<<grid, 128, 0, st>>>((const __half*)q, d, (const __half*)xkv, (const __half*)xkv, nullptr, nullptr, s, d, T,
                                                                              (__half*)out);
