@@ -101,19 +101,32 @@ def run_reference(args, rank, world):
     p = default_full_params()
     p.temperature_inc = 0.0
     cores = os.cpu_count() or 1
-    times, toks = [], 0
-    for s in range(args.warmup + args.steps):
-        clip = synth.audio(s + 1)
+    # bounded sample: one 30 s window per step; the whole run is kept within ~4 minutes of CPU time, so on a slow host
+    # fewer warm-up / timed steps are run than asked for and the line reports the numbers actually run
+    budget_s = float(os.environ.get("OH_REF_BUDGET_S", "240"))
+    def one(seed):
+        clip = synth.audio(seed)
         t0 = time.perf_counter()
-        rc = ost.full(clip, p)
-        dt = time.perf_counter() - t0
-        assert rc == 0
-        if s >= args.warmup:
+        assert ost.full(clip, p) == 0
+        return time.perf_counter() - t0, sum(len(x["tokens"]) for x in ost.segments())
+
+    dt0, tk0 = one(1)                                   # first window: sizes the rest of the run
+    allowed = max(2, int(budget_s // max(dt0, 1e-3)))   # windows that fit the budget (at least 2)
+    n_warm = max(1 if args.warmup > 0 else 0, min(args.warmup, allowed - args.steps))
+    n_timed = max(1, min(args.steps, allowed - n_warm))
+    times, toks = [], 0
+    if n_warm == 0:
+        times.append(dt0)
+        toks += tk0
+    for s in range(1, n_warm + n_timed):
+        dt, tk = one(s + 1)
+        if s >= n_warm:
             times.append(dt)
-            toks += sum(len(x["tokens"]) for x in ost.segments())
+            toks += tk
     total = sum(times)
     value = WINDOW_S * len(times) / total
-    line = dict(metric="audio_seconds_per_second", value=value, unit="audio-s/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+    line = dict(metric="audio_seconds_per_second", value=value, unit="audio-s/s", n_gpus=args.gpus, steps=len(times), warmup=n_warm,
+                steps_requested=args.steps, warmup_requested=args.warmup,
                 ms_per_step=1000.0 * total / len(times), higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f16-weights/f32-accum (CPU)",
                 data="synthetic", impl="reference",
                 config=dict(workload=f"whisper {args.arch} greedy (temperature_inc=0), independent 30 s windows, 1 window per step on the host CPU",
@@ -278,10 +291,14 @@ def main():
         e2e_val = audio_s / (e2e_ms / 1000.0)
         rep_sorted = sorted(rep, key=lambda r: -r["total_ms"])
         tot_ms = sum(r["total_ms"] for r in rep) or 1.0
-        top = rep_sorted[0]
-        hp = ctx
-        L, d, T = hp.n_text_layer, hp.n_text_state, hp.n_audio_ctx
-        esz = 4 if args.compute == "f32" else 2
+        # dominant kernel: the profiled step brackets every launch with events and bypasses the CUDA graph, so kernels of a
+        # few microseconds are CPU-launch-bound there and their event time is mostly gap; rank only the kernels whose
+        # launches are long enough to be timed (>= 50 us) — the ncu launch list in profiles/ has the same ordering
+        timed = [r for r in rep_sorted if r["total_ms"] / r["launches"] >= 0.05]
+        top = (timed or rep_sorted)[0]
+        # DRAM traffic per decoder row and launch of the cross-attention kernel from the committed `ncu --set full` capture
+        # (profiles/r01_ncu_full_decode_kernels.csv: 983.39 MB read + 4.70 MB written for 128 rows; algorithmic 983.04 MB)
+        XATTN_TRAFFIC_PER_ROW = (983.390208e6 + 4.695296e6) / 128
         if top["name"] in ("gemm_encoder", "gemm_decoder", "attention_encoder"):
             achieved = top["work"] / (top["total_ms"] / 1e3) / 1e12
             roof = dict(kernel=top["name"], bound="tensor", achieved=achieved, peak=pk["tf_sustained"], unit="TFLOP/s", frac=achieved / pk["tf_sustained"],
@@ -290,9 +307,11 @@ def main():
         else:
             src = next((r for r in rep_dec if r["name"] == top["name"]), top)
             achieved = src["work"] / (src["total_ms"] / 1e3) / 1e9
-            roof = dict(kernel=top["name"], bound="hbm", achieved=achieved, peak=pk["hbm"], unit="GB/s", frac=achieved / pk["hbm"], traffic=None,
+            traffic = XATTN_TRAFFIC_PER_ROW * S if (top["name"] == "cross_attention_decode" and args.arch == "large-v3" and args.compute != "f32") else None
+            roof = dict(kernel=top["name"], bound="hbm", achieved=achieved, peak=pk["hbm"], unit="GB/s", frac=achieved / pk["hbm"], traffic=traffic,
+                        algorithmic_bytes_per_launch=src["work"] / src["launches"],
                         peak_source=pk["src"], share_of_step=top["total_ms"] / tot_ms, avg_launch_ms=src["total_ms"] / src["launches"],
-                        launches=src["launches"], measured_on="stage decode step, all rows active")
+                        launches=src["launches"], measured_on="decode steps with every row active (stage API), CUDA events on the launching stream")
         kernels = {r["name"]: dict(ms=round(r["total_ms"], 3), launches=r["launches"], share=round(r["total_ms"] / tot_ms, 4),
                                    rate=(round(r["work"] / (r["total_ms"] / 1e3) / 1e12, 2) if r["name"].startswith("gemm") or r["name"] == "attention_encoder"
                                          else round(r["work"] / (r["total_ms"] / 1e3) / 1e9, 1)),

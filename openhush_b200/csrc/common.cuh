@@ -49,6 +49,8 @@ struct Profiler {
     std::vector<cudaEvent_t> free_events;
 };
 extern thread_local Profiler* g_prof;
+extern unsigned g_skip_mask;  // timing experiments: categories whose launches are skipped (results are then meaningless)
+#define OH_SKIP_IF(cat) do { if (::oh::g_skip_mask & (1u << (cat))) return OH_OK; } while (0)
 struct ProfScope {
     int idx = -1;
     cudaStream_t st;

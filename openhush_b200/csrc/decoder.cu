@@ -41,17 +41,18 @@ __global__ void __launch_bounds__(128) self_attention_decode_kernel(const T* __r
     const int pos = s.pos[b], slot = s.slot[b];
     const int n_kv = pos + 1;
     const T* row = qkv + (size_t)b * 3 * d;
-    T* K = kcache + (size_t)slot * n_ctx * d + h * kHeadDim;
-    T* V = vcache + (size_t)slot * n_ctx * d + h * kHeadDim;
+    // self cache of a slot: [heads][n_ctx][64] — contiguous per (slot, head), like the cross cache
+    T* K = kcache + ((size_t)slot * (d / kHeadDim) + h) * n_ctx * kHeadDim;
+    T* V = vcache + ((size_t)slot * (d / kHeadDim) + h) * n_ctx * kHeadDim;
     if (tid < kHeadDim) {
         q[tid] = Cvt<T>::to_f32(row[h * kHeadDim + tid]);
-        K[(size_t)pos * d + tid] = row[d + h * kHeadDim + tid];
-        V[(size_t)pos * d + tid] = row[2 * d + h * kHeadDim + tid];
+        K[(size_t)pos * kHeadDim + tid] = row[d + h * kHeadDim + tid];
+        V[(size_t)pos * kHeadDim + tid] = row[2 * d + h * kHeadDim + tid];
     }
     __syncthreads();
     float mx = -INFINITY;
     for (int j = tid; j < n_kv; j += 128) {
-        const T* kr = K + (size_t)j * d;
+        const T* kr = K + (size_t)j * kHeadDim;
         float acc = 0.0f;
 #pragma unroll 16
         for (int c = 0; c < kHeadDim; ++c) acc = fmaf(q[c], Cvt<T>::to_f32(kr[c]), acc);
@@ -78,7 +79,7 @@ __global__ void __launch_bounds__(128) self_attention_decode_kernel(const T* __r
     float acc = 0.0f;
     for (int j = half_id; j < n_kv; j += 2) {
         const float p = Cvt<T>::to_f32(Cvt<T>::from_f32(sc[j] * inv));
-        acc = fmaf(p, Cvt<T>::to_f32(V[(size_t)j * d + c]), acc);
+        acc = fmaf(p, Cvt<T>::to_f32(V[(size_t)j * kHeadDim + c]), acc);
     }
     part[half_id][c] = acc;
     __syncthreads();
@@ -275,13 +276,13 @@ __global__ void __launch_bounds__(128) attention_decode_online_kernel(const T* _
     if (IS_SELF) {
         const int pos = s.pos[b];
         n_kv = pos + 1;
-        ld = d;
-        T* K = kcache + (size_t)slot * n_ctx_or_T * d + h * kHeadDim;
-        T* V = vcache + (size_t)slot * n_ctx_or_T * d + h * kHeadDim;
+        ld = kHeadDim;
+        T* K = kcache + ((size_t)slot * H + h) * n_ctx_or_T * kHeadDim;
+        T* V = vcache + ((size_t)slot * H + h) * n_ctx_or_T * kHeadDim;
         if (tid < kHeadDim) {  // qsrc = qkv row of this step: q | k | v
             const T* row = qsrc + (size_t)b * q_ld;
-            K[(size_t)pos * d + tid] = row[d + h * kHeadDim + tid];
-            V[(size_t)pos * d + tid] = row[2 * d + h * kHeadDim + tid];
+            K[(size_t)pos * kHeadDim + tid] = row[d + h * kHeadDim + tid];
+            V[(size_t)pos * kHeadDim + tid] = row[2 * d + h * kHeadDim + tid];
         }
         __syncthreads();
         Kb = K + sub * 8;
@@ -374,6 +375,109 @@ __global__ void __launch_bounds__(128) attention_decode_online_kernel(const T* _
             O = fmaf(sm_o[g2][tid], w, O);
         }
         out[(size_t)b * d + h * kHeadDim + tid] = Cvt<T>::from_f32(O / L);
+    }
+}
+
+// ------------------------------------------------- K7+K8a (16-bit modes): self attention, one warp per (row, head)
+// The self cache is short (<= 448 keys, typically ~100) and L2-resident, so this kernel is latency-bound: one warp
+// per (row, head) with no block-level barrier, 4 groups of 8 lanes x 4 keys per sweep (8 independent 16-byte loads
+// per lane), per-group online softmax merged with shuffles at the end.  The step's k,v are appended first.
+template <typename T>
+__global__ void __launch_bounds__(128) self_attention_decode_warp_kernel(const T* __restrict__ qkv, T* kcache, T* vcache, DecodeSeqState s, int d,
+                                                                         int n_ctx, int rows, T* __restrict__ out) {
+    const int H = d / kHeadDim;
+    const int wid = blockIdx.x * 4 + (threadIdx.x >> 5);  // (row, head) index
+    if (wid >= rows * H) return;
+    const int b = wid / H, h = wid - b * H;
+    if (!s.active[b]) return;
+    const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
+    const int pos = s.pos[b], slot = s.slot[b];
+    const int n_kv = pos + 1;
+    const T* row = qkv + (size_t)b * 3 * d + h * kHeadDim;
+    T* K = kcache + ((size_t)slot * H + h) * n_ctx * kHeadDim;
+    T* V = vcache + ((size_t)slot * H + h) * n_ctx * kHeadDim;
+    if (lane < 8) *reinterpret_cast<uint4*>(K + (size_t)pos * kHeadDim + lane * 8) = *reinterpret_cast<const uint4*>(row + d + lane * 8);
+    else if (lane < 16) *reinterpret_cast<uint4*>(V + (size_t)pos * kHeadDim + (lane - 8) * 8) = *reinterpret_cast<const uint4*>(row + 2 * d + (lane - 8) * 8);
+    __syncwarp();
+    float qv[8];
+    {
+        const float sc = 0.125f * 1.44269504088896340736f;
+        Vec8<T> qq;
+        qq.load(row + sub * 8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) qv[i] = qq.v[i] * sc;
+    }
+    float m_run = -INFINITY, l_run = 0.0f, o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = 0.0f;
+    const T* Kb = K + sub * 8;
+    const T* Vb = V + sub * 8;
+    for (int base = 0; base < n_kv; base += 16) {  // warp-uniform trip count
+        Vec8<T> kv[4], vv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = base + grp + 4 * u;
+            if (j < n_kv) {
+                kv[u].load_cg(Kb + (size_t)j * kHeadDim);
+                vv[u].load_cg(Vb + (size_t)j * kHeadDim);
+            }
+        }
+        float sc4[4], mx = -INFINITY;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = base + grp + 4 * u;
+            float acc = 0.0f;
+            if (j < n_kv) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc = fmaf(qv[i], kv[u].v[i], acc);
+            }
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+            sc4[u] = j < n_kv ? acc : -INFINITY;
+            mx = fmaxf(mx, sc4[u]);
+        }
+        if (mx > -INFINITY) {
+            const float m_new = fmaxf(m_run, mx);
+            const float corr = exp2f(m_run - m_new);
+            m_run = m_new;
+            l_run *= corr;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] *= corr;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (base + grp + 4 * u < n_kv) {
+                    const float p = exp2f(sc4[u] - m_new);
+                    l_run += p;
+                    const float pr = Cvt<T>::to_f32(Cvt<T>::from_f32(p));
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) o[i] = fmaf(pr, vv[u].v[i], o[i]);
+                }
+            }
+        }
+    }
+    // merge the 4 groups (lanes sub, sub+8, sub+16, sub+24 hold the same channels)
+#pragma unroll
+    for (int off = 8; off <= 16; off <<= 1) {
+        const float m_o = __shfl_xor_sync(0xffffffffu, m_run, off);
+        const float l_o = __shfl_xor_sync(0xffffffffu, l_run, off);
+        const float m_new = fmaxf(m_run, m_o);
+        const float wa = m_run == -INFINITY ? 0.0f : exp2f(m_run - m_new);
+        const float wb = m_o == -INFINITY ? 0.0f : exp2f(m_o - m_new);
+        l_run = l_run * wa + l_o * wb;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float o_o = __shfl_xor_sync(0xffffffffu, o[i], off);
+            o[i] = o[i] * wa + o_o * wb;
+        }
+        m_run = m_new;
+    }
+    if (grp == 0) {
+        const float inv = 1.0f / l_run;
+        T res[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) res[i] = Cvt<T>::from_f32(o[i] * inv);
+        *reinterpret_cast<uint4*>(out + (size_t)b * d + h * kHeadDim + sub * 8) = *reinterpret_cast<const uint4*>(res);
     }
 }
 
@@ -789,14 +893,27 @@ int launch_self_attention_decode(const void* qkv, void* kcache, void* vcache, in
                                  void* out, cudaStream_t st) {
     dim3 grid(d / kHeadDim, rows);
     if (n_ctx > 448) return OH_ERR_INVALID;
+    OH_SKIP_IF(PC_SELF_ATTN);
     ProfScope ps(PC_SELF_ATTN, 0.0, st);
+    static int use_warp = -1;
+    if (use_warp < 0) {
+        const char* e = getenv("OH_SELFATTN");
+        use_warp = (e && strcmp(e, "online") == 0) ? 0 : 1;
+    }
     if (type == DT_F32) self_attention_decode_kernel<float><<<grid, 128, 0, st>>>((const float*)qkv, (float*)kcache, (float*)vcache, s, d, n_ctx, (float*)out);
-    else if (type == DT_F16)
+    else if (!use_warp && type == DT_F16)
         attention_decode_online_kernel<__half, true><<<grid, 128, 0, st>>>((const __half*)qkv, 3 * d, nullptr, nullptr, (__half*)kcache, (__half*)vcache, s, d,
                                                                             n_ctx, (__half*)out);
-    else
+    else if (!use_warp)
         attention_decode_online_kernel<__nv_bfloat16, true><<<grid, 128, 0, st>>>((const __nv_bfloat16*)qkv, 3 * d, nullptr, nullptr, (__nv_bfloat16*)kcache,
                                                                                    (__nv_bfloat16*)vcache, s, d, n_ctx, (__nv_bfloat16*)out);
+    else if (type == DT_F16)
+        self_attention_decode_warp_kernel<__half><<<(rows * (d / kHeadDim) + 3) / 4, 128, 0, st>>>((const __half*)qkv, (__half*)kcache, (__half*)vcache, s, d, n_ctx,
+                                                                                                    rows, (__half*)out);
+    else
+        self_attention_decode_warp_kernel<__nv_bfloat16><<<(rows * (d / kHeadDim) + 3) / 4, 128, 0, st>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)kcache,
+                                                                                                           (__nv_bfloat16*)vcache, s, d, n_ctx, rows,
+                                                                                                           (__nv_bfloat16*)out);
     OH_COUNT_LAUNCH();
     OH_CUDA_CHECK(cudaGetLastError());
     return OH_OK;
@@ -807,6 +924,7 @@ int launch_cross_attention_decode(const void* q, const void* xkv, int type, cons
     dim3 grid(d / kHeadDim, rows);
     if (T > 1504) return OH_ERR_INVALID;
     // algorithmic bytes: every row streams its slot's K and V once (all rows assumed active)
+    OH_SKIP_IF(PC_CROSS_ATTN);
     ProfScope ps(PC_CROSS_ATTN, (double)rows * T * 2.0 * d * (type == DT_F32 ? 4 : 2), st);
     static int use_bulk = -1;
     if (use_bulk < 0) {

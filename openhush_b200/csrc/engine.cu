@@ -18,6 +18,7 @@ namespace oh {
 
 thread_local long long g_launch_count = 0;
 thread_local Profiler* g_prof = nullptr;
+unsigned g_skip_mask = 0;  // OH_SKIP_CATS: timing experiments only (kernel categories that are not launched)
 static thread_local std::string g_error;
 void set_error(const std::string& msg) { g_error = msg; }
 const std::string& get_error() { return g_error; }
@@ -100,6 +101,7 @@ int state_alloc(oh_state* st) {
     if (const char* s = getenv("OH_ATTN")) st->attn_mode = strcmp(s, "simple") == 0 ? 1 : 0;
     if (const char* s = getenv("OH_GRAPHS")) st->use_graphs = atoi(s) != 0;
     if (const char* s = getenv("OH_GELU")) st->gelu_lut_f32 = strcmp(s, "lut") == 0;
+    if (const char* s = getenv("OH_SKIP_CATS")) g_skip_mask = (unsigned)strtoul(s, nullptr, 0);
     if (const char* s = getenv("OH_SKINNY")) st->skinny_mode = atoi(s) == 0 ? 1 : 0;  // OH_SKINNY=0: decode mat-muls through the tcgen05 kernel
 
     OH_CUDA_CHECK(cudaStreamCreateWithFlags(&st->own_stream, cudaStreamNonBlocking));
@@ -471,20 +473,21 @@ static int decode_step_launch(oh_state* st, int rows, bool with_k9, bool dump) {
 
 int run_decode_step(oh_state* st, int rows, bool dump_probs) { return decode_step_launch(st, rows, true, dump_probs); }
 
-static int run_decode_step_graph(oh_state* st, int rows) {
-    if (!st->use_graphs || st->profiling) return decode_step_launch(st, rows, true, false);
-    auto it = st->step_graphs.find(rows);
+static int run_decode_step_graph(oh_state* st, int rows, bool with_k9 = true) {
+    if (!st->use_graphs || st->profiling) return decode_step_launch(st, rows, with_k9, false);
+    const int key = rows * 2 + (with_k9 ? 1 : 0);
+    auto it = st->step_graphs.find(key);
     if (it == st->step_graphs.end()) {
         // first use of this row count: one direct step (sets kernel attributes, faults in lazily allocated
         // buffers), capture on the second, replay from then on
-        if (!st->warmed_rows.count(rows)) {
-            st->warmed_rows.insert(rows);
-            return decode_step_launch(st, rows, true, false);
+        if (!st->warmed_rows.count(key)) {
+            st->warmed_rows.insert(key);
+            return decode_step_launch(st, rows, with_k9, false);
         }
         cudaGraph_t graph = nullptr;
         const long long launches_before = g_launch_count;
         OH_CUDA_CHECK(cudaStreamBeginCapture(st->stream, cudaStreamCaptureModeThreadLocal));
-        int rc = decode_step_launch(st, rows, true, false);
+        int rc = decode_step_launch(st, rows, with_k9, false);
         cudaError_t ce = cudaStreamEndCapture(st->stream, &graph);
         g_launch_count = launches_before;  // nothing ran during capture
         if (rc) {
@@ -495,10 +498,10 @@ static int run_decode_step_graph(oh_state* st, int rows) {
         cudaGraphExec_t exec = nullptr;
         OH_CUDA_CHECK(cudaGraphInstantiate(&exec, graph, 0));
         cudaGraphDestroy(graph);
-        it = st->step_graphs.emplace(rows, exec).first;
+        it = st->step_graphs.emplace(key, exec).first;
     }
     OH_CUDA_CHECK(cudaGraphLaunch(it->second, st->stream));
-    g_launch_count += 11LL * st->ctx->model->hp.n_text_layer + 4;  // kernels inside one replayed step
+    g_launch_count += 11LL * st->ctx->model->hp.n_text_layer + (with_k9 ? 4 : 3);  // kernels inside one replayed step
     return OH_OK;
 }
 
@@ -523,7 +526,7 @@ int decode_tokens_stage(oh_state* st, const int* tokens, int n_tokens, int n_pas
             hs.cur_token[r] = tokens[(size_t)r * n_tokens + i];
         }
         OH_CUDA_CHECK(cudaMemcpyAsync(st->seq_dev.p, hb, seqlay::N_SCALARS * lay.rows * 4, cudaMemcpyHostToDevice, s));
-        if ((rc = decode_step_launch(st, batch, false, false))) return rc;
+        if ((rc = run_decode_step_graph(st, batch, false))) return rc;
         OH_CUDA_CHECK(cudaStreamSynchronize(s));
     }
     if (out_logits) {

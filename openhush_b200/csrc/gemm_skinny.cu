@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const SkParams 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     constexpr int MP = 16 * MT;
+    const int m0 = blockIdx.y * MP;  // this CTA's rows of X / C (the weights are re-read from L2 by the other row blocks)
     const int xs = (p.ks % 64 == 0) ? p.ks + 32 : p.ks;  // row stride of the staged X in halves: 2*xs = 64 (mod 128) bytes -> conflict-free 16-byte LDS
     T* Xs = reinterpret_cast<T*>(sk_smem);
     const T* __restrict__ A = reinterpret_cast<const T*>(p.A);
@@ -115,8 +116,8 @@ __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const SkParams 
         const int chunks_per_row = p.ks / 8;
         for (int idx = tid; idx < MP * chunks_per_row; idx += SK_THREADS) {
             const int r = idx / chunks_per_row, ch = idx - r * chunks_per_row;
-            const bool ok = r < p.M;
-            sk_cp_async16((uint32_t)__cvta_generic_to_shared(Xs + (size_t)r * xs + ch * 8), A + (size_t)(ok ? r : 0) * p.lda + k0 + ch * 8, ok);
+            const bool ok = m0 + r < p.M;
+            sk_cp_async16((uint32_t)__cvta_generic_to_shared(Xs + (size_t)r * xs + ch * 8), A + (size_t)(ok ? m0 + r : 0) * p.lda + k0 + ch * 8, ok);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -150,12 +151,20 @@ __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const SkParams 
     const int col = tid & 63;
     const int n = n_slice * SK_ROWS + col;
     const float bias = (p.bias && n < p.N) ? p.bias[n] : 0.0f;
-    for (int r = crank + cs * (tid >> 6); r < p.M; r += cs * (SK_THREADS / 64)) {
+    const float* remote[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) remote[c] = cluster.map_shared_rank(Ps, c < cs ? c : 0);
+    const int m_here = min(MP, p.M - m0);
+    for (int rl = crank + cs * (tid >> 6); rl < m_here; rl += cs * (SK_THREADS / 64)) {
+        const int r = m0 + rl;
+        // all peers' partials are requested before the first add (remote shared memory is ~200 cycles away);
+        // the summation order is fixed (rank 0..cs-1), so the result does not depend on timing
+        float part[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) part[c] = c < cs ? remote[c][(size_t)rl * SK_ROWS + col] : 0.0f;
         float v = 0.0f;
-        for (int c = 0; c < cs; ++c) {
-            const float* remote = cluster.map_shared_rank(Ps, c);
-            v += remote[(size_t)r * SK_ROWS + col];
-        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v += part[c];
         if (n < p.N) {
             v += bias;
             if (p.gelu != GELU_NONE) v = sk_gelu(v, p.gelu, p.round_type, p.lut);
@@ -180,7 +189,7 @@ int launch_mt(const SkParams& p, int cs, cudaStream_t st) {
     }
     const int n_slices = (p.N + SK_ROWS - 1) / SK_ROWS;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(n_slices * cs);
+    cfg.gridDim = dim3(n_slices * cs, (p.M + MP - 1) / MP);
     cfg.blockDim = dim3(SK_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
@@ -191,6 +200,7 @@ int launch_mt(const SkParams& p, int cs, cudaStream_t st) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    OH_SKIP_IF(PC_GEMM_DEC);
     ProfScope ps(PC_GEMM_DEC, 2.0 * p.M * (double)p.N * p.K, st);
     OH_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_skinny_kernel<T, MT>, p));
     OH_COUNT_LAUNCH();
@@ -199,6 +209,10 @@ int launch_mt(const SkParams& p, int cs, cudaStream_t st) {
 
 template <typename T>
 int launch_t(const SkParams& p, int cs, cudaStream_t st) {
+    // measured on B200 (scripts/bench_decode_step.py): one CTA column over all rows beats splitting the rows over
+    // grid.y — the kernel is bound by per-CTA latency and by the L2 re-reads of W, not by MMA issue
+    if (p.M <= 16) return launch_mt<T, 1>(p, cs, st);
+    if (p.M <= 32) return launch_mt<T, 2>(p, cs, st);
     if (p.M <= 64) return launch_mt<T, 4>(p, cs, st);
     if (p.M <= 128) return launch_mt<T, 8>(p, cs, st);
     return launch_mt<T, 16>(p, cs, st);
@@ -213,7 +227,12 @@ int launch_gemm_skinny(const GemmArgs& g, cudaStream_t st) {
     // cluster size: enough CTAs to cover the machine, K-range a multiple of 32
     const int n_slices = (g.N + SK_ROWS - 1) / SK_ROWS;
     int cs = 1;
-    while (cs < 8 && n_slices * cs < 148 && (g.K / (cs * 2)) % 32 == 0 && g.K / (cs * 2) >= 64) cs *= 2;
+    static int cs_cap = -1;
+    if (cs_cap < 0) {
+        const char* e = getenv("OH_SKINNY_CS");
+        cs_cap = e ? std::max(1, atoi(e)) : 8;
+    }
+    while (cs < cs_cap && n_slices * cs < 148 && (g.K / (cs * 2)) % 32 == 0 && g.K / (cs * 2) >= 64) cs *= 2;
     const int kc = g.K / cs;
     int ks = 0;
     for (int cand = std::min(kc, 32 * SK_MAXKB); cand >= 32; cand -= 32)

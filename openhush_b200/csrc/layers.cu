@@ -74,6 +74,7 @@ int launch_layernorm(const float* x, int rows, int d, const float* w, const floa
         return OH_ERR_INVALID;
     }
     const int warps = 8;
+    OH_SKIP_IF(PC_LN);
     ProfScope ps(PC_LN, (double)rows * d * (4.0 + (y_type == DT_F32 ? 4 : 2)), st);
     dim3 grid((rows + warps - 1) / warps);
     if (y_type == DT_F32) layernorm_kernel<float><<<grid, warps * 32, 0, st>>>(x, rows, d, w, b, (float*)y);
