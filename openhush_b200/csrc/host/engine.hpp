@@ -1,0 +1,226 @@
+// C++ host side above the C ABI: the reference's engine boundary restated for a compiled-language caller
+// (the reference is Rust; no Rust toolchain exists in this image — INTEGRATION.md has the Rust binding).
+//
+//   validate_audio / AudioValidationError      <- /root/reference/src/engine/validation.rs:9-136
+//   WhisperError, TranscriptionResult, BenchmarkResult, WhisperEngine{create, transcribe, benchmark}
+//                                               <- /root/reference/src/engine/whisper.rs:14-387
+//   TranscriptionJob / JobResult / process_job  <- /root/reference/src/queue/mod.rs:18-43, src/queue/worker.rs:119-193
+//
+// Header-only, depends only on include/oh_whisper.h; link with libohwhisper.so.  No arithmetic lives here.
+#pragma once
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <memory>
+#include <string>
+#include <sys/stat.h>
+#include <variant>
+#include <vector>
+
+#include "../../../include/oh_whisper.h"
+
+namespace openhush {
+
+constexpr float MAX_AUDIO_DURATION_SECS = 7200.0f;
+constexpr float MIN_AUDIO_DURATION_SECS = 0.1f;
+constexpr uint32_t EXPECTED_SAMPLE_RATE = 16000;
+
+struct AudioValidationError {
+    enum Kind { TooLong, TooShort, Empty, ContainsNaN, ContainsInfinite, InvalidSampleRate } kind;
+    double a = 0, b = 0;  // payload: (secs, limit) | count | (got, expected)
+    std::string message() const {
+        char buf[128];
+        switch (kind) {
+            case TooLong: snprintf(buf, sizeof buf, "Audio too long: %.1fs exceeds maximum %.1fs", a, b); break;
+            case TooShort: snprintf(buf, sizeof buf, "Audio too short: %.3fs below minimum %.3fs", a, b); break;
+            case Empty: snprintf(buf, sizeof buf, "Audio is empty (no samples)"); break;
+            case ContainsNaN: snprintf(buf, sizeof buf, "Audio contains %zu NaN values", (size_t)a); break;
+            case ContainsInfinite: snprintf(buf, sizeof buf, "Audio contains %zu infinite values", (size_t)a); break;
+            default: snprintf(buf, sizeof buf, "Unexpected sample rate: %uHz (expected %uHz)", (unsigned)a, (unsigned)b); break;
+        }
+        return buf;
+    }
+};
+struct AudioValidationInfo {
+    float duration_secs;
+    size_t sample_count;
+    float min_value, max_value, rms;
+};
+
+// same checks, same order as validation.rs:46-118
+inline std::variant<AudioValidationInfo, AudioValidationError> validate_audio(const float* samples, size_t n, uint32_t sample_rate) {
+    using E = AudioValidationError;
+    if (n == 0) return E{E::Empty};
+    if (sample_rate != EXPECTED_SAMPLE_RATE) return E{E::InvalidSampleRate, (double)sample_rate, (double)EXPECTED_SAMPLE_RATE};
+    const float duration = (float)n / (float)sample_rate;
+    if (duration > MAX_AUDIO_DURATION_SECS) return E{E::TooLong, duration, MAX_AUDIO_DURATION_SECS};
+    if (duration < MIN_AUDIO_DURATION_SECS) return E{E::TooShort, duration, MIN_AUDIO_DURATION_SECS};
+    size_t n_nan = 0, n_inf = 0;
+    float mn = 3.402823466e38f, mx = -3.402823466e38f;
+    double ss = 0.0;
+    for (size_t i = 0; i < n; ++i) {
+        const float s = samples[i];
+        if (std::isnan(s)) ++n_nan;
+        else if (std::isinf(s)) ++n_inf;
+        else {
+            mn = s < mn ? s : mn;
+            mx = s > mx ? s : mx;
+            ss += (double)s * (double)s;
+        }
+    }
+    if (n_nan) return E{E::ContainsNaN, (double)n_nan};
+    if (n_inf) return E{E::ContainsInfinite, (double)n_inf};
+    return AudioValidationInfo{duration, n, mn, mx, (float)std::sqrt(ss / (double)n)};
+}
+
+struct WhisperError {
+    enum Kind { ModelNotFound, LoadFailed, TranscriptionFailed, ValidationFailed } kind;
+    std::string detail;
+    std::string message() const {
+        switch (kind) {
+            case ModelNotFound: return "Model not found at " + detail;
+            case LoadFailed: return "Failed to load model: " + detail;
+            case TranscriptionFailed: return "Transcription failed: " + detail;
+            default: return "Audio validation failed: " + detail;
+        }
+    }
+};
+struct TranscriptionResult {
+    std::string text, language;
+    uint64_t duration_ms = 0;
+};
+struct BenchmarkResult {
+    float overhead_secs, recommended_chunk_interval, test_audio_secs;
+};
+struct AudioBuffer {
+    std::vector<float> samples;
+    uint32_t sample_rate = 16000;
+    float duration_secs() const { return (float)samples.size() / (float)sample_rate; }
+};
+
+template <class T>
+using Result = std::variant<T, WhisperError>;
+
+class WhisperEngine {
+  public:
+    // whisper.rs:129-179.  The engine may be created on one thread and used on another (daemon.rs:1803-1805): the
+    // library re-selects its CUDA device at every entry point.
+    static Result<std::unique_ptr<WhisperEngine>> create(const std::string& model_path, const std::string& language, bool translate,
+                                                         bool use_gpu, int gpu_device = 0, int max_batch = 1) {
+        struct stat sb;
+        if (stat(model_path.c_str(), &sb) != 0) {
+            std::string name = model_path.substr(model_path.find_last_of('/') + 1);
+            if (name.rfind("ggml-", 0) == 0) name = name.substr(5);
+            if (name.size() > 4 && name.substr(name.size() - 4) == ".bin") name.resize(name.size() - 4);
+            return WhisperError{WhisperError::ModelNotFound, model_path + ". Run 'openhush model download " + name + "'"};
+        }
+        oh_context_params cp = oh_context_default_params();
+        cp.use_gpu = use_gpu ? 1 : 0;
+        cp.gpu_device = gpu_device;
+        cp.max_batch = max_batch;
+        oh_context* ctx = oh_init_from_file(model_path.c_str(), cp);
+        if (!ctx) return WhisperError{WhisperError::LoadFailed, oh_last_error()};
+        oh_state* st = oh_init_state(ctx);
+        if (!st) {
+            oh_free(ctx);
+            return WhisperError{WhisperError::LoadFailed, oh_last_error()};
+        }
+        auto e = std::unique_ptr<WhisperEngine>(new WhisperEngine());
+        e->ctx_ = ctx;
+        e->state_ = st;
+        e->language_ = language;
+        e->translate_ = translate;
+        return e;
+    }
+    ~WhisperEngine() {
+        oh_free_state(state_);
+        oh_free(ctx_);
+    }
+    // whisper.rs:204-310
+    Result<TranscriptionResult> transcribe(const AudioBuffer& audio) const {
+        auto v = validate_audio(audio.samples.data(), audio.samples.size(), audio.sample_rate);
+        if (auto* err = std::get_if<AudioValidationError>(&v)) return WhisperError{WhisperError::ValidationFailed, err->message()};
+        const auto t0 = std::chrono::steady_clock::now();
+        oh_full_params p = oh_full_default_params(OH_SAMPLING_GREEDY);
+        p.greedy_best_of = 1;
+        if (language_ != "auto") p.language = language_.c_str();
+        p.translate = translate_ ? 0 : 1;  // whisper.rs:251-257 passes the inverted flag
+        const int rc = oh_full(ctx_, state_, p, audio.samples.data(), (int)audio.samples.size());
+        if (rc != 0) {
+            const char* name = rc == OH_ERR_MEL ? "UnableToCalculateSpectrogram" : rc == OH_ERR_ENCODE ? "FailedToEncode" : rc == OH_ERR_DECODE ? "FailedToDecode" : nullptr;
+            return WhisperError{WhisperError::TranscriptionFailed, name ? std::string(name) : "GenericError(" + std::to_string(rc) + ")"};
+        }
+        std::string text;
+        const int n = oh_full_n_segments(state_);
+        for (int i = 0; i < n; ++i) {
+            const char* s = oh_full_get_segment_text(state_, i);
+            if (s && valid_utf8(s)) text += s;  // whisper.rs:276-280: invalid UTF-8 segments are skipped
+        }
+        TranscriptionResult r;
+        r.text = trim(text);
+        r.language = language_ == "auto" ? "en" : language_;
+        r.duration_ms = (uint64_t)std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count();
+        return r;
+    }
+    // whisper.rs:334-387
+    BenchmarkResult benchmark(float safety_margin) const {
+        AudioBuffer a;
+        a.samples.assign(32000, 0.0f);
+        (void)transcribe(a);
+        uint64_t total = 0;
+        for (int i = 0; i < 3; ++i) {
+            const auto t0 = std::chrono::steady_clock::now();
+            (void)transcribe(a);
+            total += (uint64_t)std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count();
+        }
+        const float overhead = (float)(total / 3) / 1000.0f;
+        return BenchmarkResult{overhead, overhead * (1.0f + safety_margin), 2.0f};
+    }
+
+  private:
+    WhisperEngine() = default;
+    static bool valid_utf8(const char* s) {
+        const unsigned char* p = (const unsigned char*)s;
+        while (*p) {
+            int n = *p < 0x80 ? 0 : (*p >> 5) == 6 ? 1 : (*p >> 4) == 14 ? 2 : (*p >> 3) == 30 ? 3 : -1;
+            if (n < 0) return false;
+            ++p;
+            for (; n > 0; --n, ++p)
+                if ((*p >> 6) != 2) return false;
+        }
+        return true;
+    }
+    static std::string trim(const std::string& s) {
+        size_t a = s.find_first_not_of(" \t\r\n"), b = s.find_last_not_of(" \t\r\n");
+        return a == std::string::npos ? std::string() : s.substr(a, b - a + 1);
+    }
+    oh_context* ctx_ = nullptr;
+    oh_state* state_ = nullptr;
+    std::string language_;
+    bool translate_ = false;
+};
+
+// queue/mod.rs:18-43 and the hot-path caller queue/worker.rs:119-193
+struct TranscriptionJob {
+    AudioBuffer buffer;
+    uint64_t sequence_id = 0;
+    uint32_t chunk_id = 0;
+    bool is_final = true;
+};
+struct JobResult {
+    std::string text;
+    uint64_t sequence_id;
+    uint32_t chunk_id;
+    bool is_final;
+    float duration_secs;
+};
+inline JobResult process_job(const WhisperEngine* engine, const TranscriptionJob& job) {
+    JobResult r{"", job.sequence_id, job.chunk_id, job.is_final, job.buffer.duration_secs()};
+    if (!engine) return r;  // worker.rs:125-142: no engine -> empty result, the tracker never stalls
+    auto res = engine->transcribe(job.buffer);
+    if (auto* ok = std::get_if<TranscriptionResult>(&res)) r.text = ok->text;  // worker.rs:159-165: error -> logged + empty text
+    return r;
+}
+
+}  // namespace openhush

@@ -1,0 +1,69 @@
+// Native test driver of the C++ host mirror.  `host_test` alone: CPU checks (validation order / messages, missing model,
+// no-GPU load failure, worker without engine).  `host_test <model> <n_samples>`: additionally transcribes silence and a
+// ramp on the GPU and prints the text length (used by the -m gpu tests).
+#include <cstdlib>
+#include <cstring>
+
+#include "engine.hpp"
+
+using namespace openhush;
+#define CHECK(c)                                                          \
+    do {                                                                  \
+        if (!(c)) {                                                       \
+            fprintf(stderr, "CHECK failed at line %d: %s\n", __LINE__, #c); \
+            return 1;                                                     \
+        }                                                                 \
+    } while (0)
+
+int main(int argc, char** argv) {
+    {
+        std::vector<float> x(16000, 0.5f);
+        auto v = validate_audio(x.data(), x.size(), 16000);
+        auto* info = std::get_if<AudioValidationInfo>(&v);
+        CHECK(info && std::fabs(info->rms - 0.5f) < 1e-3f && info->sample_count == 16000);
+        CHECK(std::get<AudioValidationError>(validate_audio(x.data(), 0, 16000)).kind == AudioValidationError::Empty);
+        CHECK(std::get<AudioValidationError>(validate_audio(x.data(), 0, 8000)).kind == AudioValidationError::Empty);
+        CHECK(std::get<AudioValidationError>(validate_audio(x.data(), 800, 16000)).kind == AudioValidationError::TooShort);
+        auto e = std::get<AudioValidationError>(validate_audio(x.data(), x.size(), 44100));
+        CHECK(e.kind == AudioValidationError::InvalidSampleRate && e.message() == "Unexpected sample rate: 44100Hz (expected 16000Hz)");
+        x[3] = NAN;
+        x[4] = INFINITY;
+        auto en = std::get<AudioValidationError>(validate_audio(x.data(), x.size(), 16000));
+        CHECK(en.kind == AudioValidationError::ContainsNaN && en.message() == "Audio contains 1 NaN values");
+        x[3] = 0.f;
+        CHECK(std::get<AudioValidationError>(validate_audio(x.data(), x.size(), 16000)).kind == AudioValidationError::ContainsInfinite);
+    }
+    {
+        auto r = WhisperEngine::create("/nonexistent/ggml-base.bin", "en", false, true);
+        auto* err = std::get_if<WhisperError>(&r);
+        CHECK(err && err->kind == WhisperError::ModelNotFound && err->message().find("openhush model download base") != std::string::npos);
+        TranscriptionJob job;
+        job.buffer.samples.assign(16000, 0.f);
+        job.sequence_id = 9;
+        JobResult jr = process_job(nullptr, job);
+        CHECK(jr.text.empty() && jr.sequence_id == 9 && std::fabs(jr.duration_secs - 1.0f) < 1e-6f);
+    }
+    if (argc >= 2) {
+        auto r = WhisperEngine::create(argv[1], "en", false, argc >= 4 ? atoi(argv[3]) != 0 : true);
+        if (auto* err = std::get_if<WhisperError>(&r)) {
+            printf("LOAD_FAILED %s\n", err->message().c_str());
+            return argc >= 4 ? 0 : 2;
+        }
+        auto& eng = std::get<std::unique_ptr<WhisperEngine>>(r);
+        AudioBuffer a;
+        const int n = argc >= 3 ? atoi(argv[2]) : 32000;
+        a.samples.resize(n);
+        for (int i = 0; i < n; ++i) a.samples[i] = 0.1f * std::sin(0.05f * i) * (float)((i / 4000) % 2);
+        auto tr = eng->transcribe(a);
+        auto* ok = std::get_if<TranscriptionResult>(&tr);
+        CHECK(ok != nullptr);
+        printf("TEXT_LEN %zu LANG %s MS %llu\n", ok->text.size(), ok->language.c_str(), (unsigned long long)ok->duration_ms);
+        BenchmarkResult b = eng->benchmark(0.2f);
+        CHECK(b.test_audio_secs == 2.0f && b.recommended_chunk_interval >= b.overhead_secs);
+        a.samples[5] = NAN;
+        auto bad = eng->transcribe(a);
+        CHECK(std::get_if<WhisperError>(&bad) && std::get<WhisperError>(bad).kind == WhisperError::ValidationFailed);
+    }
+    printf("HOST_TEST_OK\n");
+    return 0;
+}

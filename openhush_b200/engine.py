@@ -1,0 +1,336 @@
+"""Host-side mirror of the reference's engine boundary, on top of the C ABI.
+
+Same names, argument meaning and error behaviour as the Rust types it mirrors, so the tests read like the
+reference's own (`src/engine/whisper.rs:741-997`, `src/engine/validation.rs:139-203`, `src/queue/worker.rs:319-538`):
+
+    validate_audio / AudioValidationError / AudioValidationInfo   <- src/engine/validation.rs:9-136
+    WhisperError, WhisperModel, TranscriptionResult, BenchmarkResult, WhisperEngine{new, transcribe, benchmark}
+                                                                  <- src/engine/whisper.rs:14-387
+    AudioBuffer                                                   <- src/input/audio.rs:55-61
+    TranscriptionJob / JobResult / TranscriptionWorker.process_job <- src/queue/mod.rs:18-43, src/queue/worker.rs:119-193
+
+The reference's toolchain (Rust) is not in this image; the Rust binding a maintainer would add is in INTEGRATION.md.
+This module contains no arithmetic: everything goes through libohwhisper.so (there is no CPU fallback).
+"""
+from __future__ import annotations
+
+import math
+import os
+import time
+from dataclasses import dataclass, field
+from enum import Enum
+
+import numpy as np
+
+from . import lib as _lib
+from ._abi import COMPUTE_F16
+
+MAX_AUDIO_DURATION_SECS = 7200.0   # validation.rs:9
+MIN_AUDIO_DURATION_SECS = 0.1      # validation.rs:12
+EXPECTED_SAMPLE_RATE = 16000       # validation.rs:15
+
+
+# ---------------------------------------------------------------------------------------------- validation.rs
+class AudioValidationError(Exception):
+    pass
+
+
+class TooLong(AudioValidationError):
+    def __init__(self, secs, limit):
+        super().__init__(f"Audio too long: {secs:.1f}s exceeds maximum {limit:.1f}s")
+        self.secs, self.limit = secs, limit
+
+
+class TooShort(AudioValidationError):
+    def __init__(self, secs, limit):
+        super().__init__(f"Audio too short: {secs:.3f}s below minimum {limit:.3f}s")
+        self.secs, self.limit = secs, limit
+
+
+class Empty(AudioValidationError):
+    def __init__(self):
+        super().__init__("Audio is empty (no samples)")
+
+
+class ContainsNaN(AudioValidationError):
+    def __init__(self, count):
+        super().__init__(f"Audio contains {count} NaN values")
+        self.count = count
+
+
+class ContainsInfinite(AudioValidationError):
+    def __init__(self, count):
+        super().__init__(f"Audio contains {count} infinite values")
+        self.count = count
+
+
+class InvalidSampleRate(AudioValidationError):
+    def __init__(self, got, expected):
+        super().__init__(f"Unexpected sample rate: {got}Hz (expected {expected}Hz)")
+        self.got, self.expected = got, expected
+
+
+@dataclass
+class AudioValidationInfo:
+    duration_secs: float
+    sample_count: int
+    min_value: float
+    max_value: float
+    rms: float
+
+
+def validate_audio(samples, sample_rate: int) -> AudioValidationInfo:
+    """Same checks in the same order as validation.rs:46-118: empty, sample rate, too long, too short, then one pass
+    counting NaN / Inf and accumulating min / max / sum of squares (f64) over the finite samples."""
+    x = np.asarray(samples, dtype=np.float32)
+    if x.size == 0:
+        raise Empty()
+    if sample_rate != EXPECTED_SAMPLE_RATE:
+        raise InvalidSampleRate(sample_rate, EXPECTED_SAMPLE_RATE)
+    duration = np.float32(x.size) / np.float32(sample_rate)
+    if duration > MAX_AUDIO_DURATION_SECS:
+        raise TooLong(float(duration), MAX_AUDIO_DURATION_SECS)
+    if duration < MIN_AUDIO_DURATION_SECS:
+        raise TooShort(float(duration), MIN_AUDIO_DURATION_SECS)
+    nan = np.isnan(x)
+    inf = np.isinf(x)
+    n_nan, n_inf = int(nan.sum()), int(inf.sum())
+    if n_nan > 0:
+        raise ContainsNaN(n_nan)
+    if n_inf > 0:
+        raise ContainsInfinite(n_inf)
+    rms = math.sqrt(float(np.sum(x.astype(np.float64) ** 2)) / x.size)
+    return AudioValidationInfo(float(duration), int(x.size), float(x.min()), float(x.max()), float(np.float32(rms)))
+
+
+# ---------------------------------------------------------------------------------------------- input/audio.rs
+@dataclass
+class AudioBuffer:
+    samples: np.ndarray
+    sample_rate: int = 16000
+
+    def duration_secs(self) -> float:
+        return len(self.samples) / float(self.sample_rate)
+
+
+# ---------------------------------------------------------------------------------------------- engine/whisper.rs
+class WhisperError(Exception):
+    pass
+
+
+class ModelNotFound(WhisperError):
+    def __init__(self, path, name):
+        super().__init__(f"Model not found at {path}. Run 'openhush model download {name}'")
+        self.path, self.name = path, name
+
+
+class LoadFailed(WhisperError):
+    def __init__(self, msg):
+        super().__init__(f"Failed to load model: {msg}")
+
+
+class TranscriptionFailed(WhisperError):
+    def __init__(self, msg):
+        super().__init__(f"Transcription failed: {msg}")
+
+
+class ValidationFailed(WhisperError):
+    def __init__(self, err: AudioValidationError):
+        super().__init__(f"Audio validation failed: {err}")
+        self.source = err
+
+
+class WhisperModel(Enum):
+    Tiny = "tiny"
+    Base = "base"
+    Small = "small"
+    Medium = "medium"
+    LargeV3 = "large-v3"
+
+    @staticmethod
+    def from_str(s: str) -> "WhisperModel":
+        m = {"tiny": WhisperModel.Tiny, "base": WhisperModel.Base, "small": WhisperModel.Small, "medium": WhisperModel.Medium,
+             "large": WhisperModel.LargeV3, "large-v3": WhisperModel.LargeV3, "largev3": WhisperModel.LargeV3}
+        try:
+            return m[s.lower()]
+        except KeyError:
+            raise ValueError(s) from None
+
+    def filename(self) -> str:
+        return f"ggml-{self.value}.bin"
+
+    def size_bytes(self) -> int:
+        return {"tiny": 75_000_000, "base": 142_000_000, "small": 466_000_000, "medium": 1_500_000_000, "large-v3": 3_000_000_000}[self.value]
+
+
+@dataclass
+class TranscriptionResult:
+    text: str
+    language: str
+    duration_ms: int
+    segments: list = field(default_factory=list)  # additive: (t0, t1, text) in 10 ms units — SURVEY.md §8f N1
+
+
+@dataclass
+class BenchmarkResult:
+    overhead_secs: float
+    recommended_chunk_interval: float
+    test_audio_secs: float
+
+
+# whisper-rs error names for the codes of whisper_full
+_FULL_ERRORS = {-1: "UnableToCalculateSpectrogram", -6: "FailedToEncode", 7: "FailedToEncode", -7: "FailedToDecode", 8: "FailedToDecode"}
+
+
+class WhisperEngine:
+    """whisper.rs:110-310.  Owns the context and ONE cached state (buffers allocated once, whisper.rs:162-169)."""
+
+    def __init__(self, model_path: str, language: str, translate: bool, use_gpu: bool, *, compute_type: int = COMPUTE_F16,
+                 gpu_device: int = 0, max_batch: int = 1):
+        if not os.path.exists(model_path):  # whisper.rs:141-154
+            name = os.path.basename(model_path)
+            name = name[5:] if name.startswith("ggml-") else name
+            name = name[:-4] if name.endswith(".bin") else name
+            raise ModelNotFound(model_path, name)
+        try:
+            self.context = _lib.Context(model_path, compute_type=compute_type, gpu_device=gpu_device, max_batch=max_batch, use_gpu=use_gpu)
+            self.state = _lib.State(self.context)
+        except _lib.OhError as e:
+            raise LoadFailed(str(e)) from None
+        self.language = language
+        self.translate = translate
+
+    @classmethod
+    def new(cls, model_path, language, translate, use_gpu, **kw):
+        return cls(model_path, language, translate, use_gpu, **kw)
+
+    def _params(self):
+        p = self.context.lib.oh_full_default_params(0)  # SamplingStrategy::Greedy { best_of: 1 }, whisper.rs:243
+        p.greedy_best_of = 1
+        if self.language != "auto":  # whisper.rs:246-248 — "auto" leaves the library default "en", no detection runs (A.2)
+            p.language = self.language.encode()
+        p.translate = 0 if self.translate else 1  # whisper.rs:251-257: the engine passes the INVERTED flag (SURVEY.md A.2 hazard)
+        return p
+
+    def transcribe(self, audio: AudioBuffer) -> TranscriptionResult:
+        try:
+            validate_audio(audio.samples, audio.sample_rate)  # whisper.rs:206
+        except AudioValidationError as e:
+            raise ValidationFailed(e) from None
+        t0 = time.perf_counter()
+        self._keepalive = self._params()
+        rc = self.state.full(np.ascontiguousarray(audio.samples, dtype=np.float32), self._keepalive)
+        if rc != 0:
+            raise TranscriptionFailed(_FULL_ERRORS.get(rc, f"GenericError({rc})"))
+        text, segs = "", []
+        for s in self.state.segments(0):
+            try:
+                piece = s["text"].decode("utf-8")  # whisper.rs:276-280: a segment that is not valid UTF-8 is skipped
+            except UnicodeDecodeError:
+                continue
+            text += piece
+            segs.append((s["t0"], s["t1"], piece))
+        lang = self.language
+        if self.language == "auto":  # whisper.rs:288-296
+            code = _lib.load().oh_full_lang_id(self.state.h)
+            lang = LANG_CODES[code] if 0 <= code < len(LANG_CODES) else "auto"
+        return TranscriptionResult(text.strip(), lang, int((time.perf_counter() - t0) * 1000), segs)
+
+    def benchmark(self, safety_margin: float) -> BenchmarkResult:
+        """whisper.rs:334-387: 1 warm-up + 3 timed transcriptions of 2 s of silence."""
+        audio = AudioBuffer(np.zeros(32000, np.float32), 16000)
+        try:
+            self.transcribe(audio)
+        except WhisperError:
+            pass
+        total_ms = 0
+        for _ in range(3):
+            t0 = time.perf_counter()
+            try:
+                self.transcribe(audio)
+            except WhisperError:
+                pass
+            total_ms += int((time.perf_counter() - t0) * 1000)
+        overhead = (total_ms // 3) / 1000.0
+        return BenchmarkResult(overhead, overhead * (1.0 + safety_margin), 2.0)
+
+    def close(self):
+        self.state.close()
+        self.context.close()
+
+
+# order of lang_id_to_code, whisper.rs:627-731
+LANG_CODES = ["en", "zh", "de", "es", "ru", "ko", "fr", "ja", "pt", "tr", "pl", "ca", "nl", "ar", "sv", "it", "id", "hi", "fi", "vi", "he", "uk",
+              "el", "ms", "cs", "ro", "da", "hu", "ta", "no", "th", "ur", "hr", "bg", "lt", "la", "mi", "ml", "cy", "sk", "te", "fa", "lv", "bn",
+              "sr", "az", "sl", "kn", "et", "mk", "br", "eu", "is", "hy", "ne", "mn", "bs", "kk", "sq", "sw", "gl", "mr", "pa", "si", "km", "sn",
+              "yo", "so", "af", "oc", "ka", "be", "tg", "sd", "gu", "am", "yi", "lo", "uz", "fo", "ht", "ps", "tk", "nn", "mt", "sa", "lb", "my",
+              "bo", "tl", "mg", "as", "tt", "haw", "ln", "ha", "ba", "jw", "su"]
+
+
+# ---------------------------------------------------------------------------------------------- queue/mod.rs, queue/worker.rs
+@dataclass
+class TranscriptionJob:
+    buffer: AudioBuffer
+    sequence_id: int
+    chunk_id: int = 0
+    is_final: bool = True
+
+
+@dataclass
+class JobResult:  # queue::TranscriptionResult, queue/mod.rs:31-43
+    text: str
+    sequence_id: int
+    chunk_id: int
+    is_final: bool
+    duration_secs: float
+
+
+class TranscriptionWorker:
+    """queue/worker.rs:85-193 reduced to the hot-path caller: one engine, jobs in, one result per job out — always,
+    so the tracker never stalls (engine missing → empty text, engine error → logged + empty text)."""
+
+    def __init__(self, engine: WhisperEngine | None):
+        self.engine = engine
+
+    def load_engine(self, engine: WhisperEngine):  # WorkerCommand::LoadEngine, worker.rs:100-103
+        self.engine = engine
+
+    def unload_engine(self):  # WorkerCommand::UnloadEngine, worker.rs:104-111
+        if self.engine is not None:
+            self.engine.close()
+        self.engine = None
+
+    def process_job(self, job: TranscriptionJob) -> JobResult:
+        dur = job.buffer.duration_secs()
+        text = ""
+        if self.engine is not None:
+            try:
+                text = self.engine.transcribe(job.buffer).text
+            except WhisperError:
+                text = ""
+        return JobResult(text, job.sequence_id, job.chunk_id, job.is_final, dur)
+
+
+def shard_jobs(n_jobs: int, rank: int, world: int):
+    """Static round-robin assignment of independent jobs to GPU workers: job j goes to rank j % world."""
+    return list(range(rank, n_jobs, world))
+
+
+def merge_records(per_rank_records, world: int):
+    """Inverse of the sharding after the gather of oh_full_pack_records blocks: rank r's local item i is global job
+    i * world + r.  Returns {job: [(t0, t1, [token ids]), ...]}."""
+    out = {}
+    for r, rec in enumerate(per_rank_records):
+        rec = [int(v) for v in rec]
+        k = 0
+        while k < len(rec):
+            item, n_seg = rec[k], rec[k + 1]
+            k += 2
+            segs = []
+            for _ in range(n_seg):
+                t0, t1, n_tok = rec[k], rec[k + 1], rec[k + 2]
+                k += 3
+                segs.append((t0, t1, rec[k:k + n_tok]))
+                k += n_tok
+            out[item * world + r] = segs
+    return out

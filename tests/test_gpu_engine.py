@@ -1,0 +1,77 @@
+"""GPU tests of the engine boundary mirror (WhisperEngine / TranscriptionWorker) on top of the C ABI."""
+import numpy as np
+import pytest
+
+from openhush_b200 import COMPUTE_F32, default_full_params, engine as E, synth
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng(micro_path):
+    e = E.WhisperEngine.new(micro_path, "en", False, True, compute_type=COMPUTE_F32)
+    yield e
+    e.close()
+
+
+def test_transcribe_text_matches_oracle(eng, micro_oracle):
+    """text = concatenated segment texts, trimmed (whisper.rs:276-283); the engine passes translate INVERTED
+    (whisper.rs:257), so config.translate = false reaches the library as translate = true."""
+    clip = synth.audio(21, 200000)
+    res = eng.transcribe(E.AudioBuffer(clip, 16000))
+    ost = O.OracleState(micro_oracle, gelu=O.GELU_TANH, act_round=O.ACT_NONE)
+    p = default_full_params()
+    p.translate = 1
+    assert ost.full(clip, p) == 0
+    ref = b"".join(s["text"] for s in ost.segments()).decode("utf-8").strip()
+    assert res.text == ref and res.language == "en" and res.duration_ms >= 0
+    assert [(a, b) for a, b, _ in res.segments] == [(s["t0"], s["t1"]) for s in ost.segments()]
+    ost.close()
+
+
+def test_transcribe_validation_errors(eng):
+    with pytest.raises(E.ValidationFailed) as ei:
+        eng.transcribe(E.AudioBuffer(np.zeros(0, np.float32), 16000))
+    assert isinstance(ei.value.source, E.Empty)
+    x = synth.audio(1, 32000)
+    x[10] = np.nan
+    with pytest.raises(E.ValidationFailed) as ei:
+        eng.transcribe(E.AudioBuffer(x, 16000))
+    assert isinstance(ei.value.source, E.ContainsNaN)
+    with pytest.raises(E.ValidationFailed):
+        eng.transcribe(E.AudioBuffer(synth.audio(1, 32000), 48000))
+
+
+def test_short_padded_clip_and_auto_language(micro_path):
+    e = E.WhisperEngine.new(micro_path, "auto", False, True, compute_type=COMPUTE_F32)
+    # the reference pads short input to 1.1 s before the engine (src/input/audio.rs:31-34, 415-424)
+    clip = np.concatenate([synth.audio(5, 8000), np.zeros(17600 - 8000, np.float32)])
+    res = e.transcribe(E.AudioBuffer(clip, 16000))
+    assert res.language == "en"  # "auto" never runs detection: the library default "en" is used
+    assert isinstance(res.text, str)
+    # below 1 s the library returns no segments and no error
+    res = e.transcribe(E.AudioBuffer(synth.audio(5, 12000), 16000))
+    assert res.text == ""
+    e.close()
+
+
+def test_benchmark_and_worker(eng):
+    b = eng.benchmark(0.2)
+    assert b.test_audio_secs == 2.0 and b.overhead_secs >= 0 and abs(b.recommended_chunk_interval - b.overhead_secs * 1.2) < 1e-6
+    w = E.TranscriptionWorker(eng)
+    job = E.TranscriptionJob(E.AudioBuffer(synth.audio(22, 100000), 16000), sequence_id=3, chunk_id=1, is_final=True)
+    r = w.process_job(job)
+    assert r.sequence_id == 3 and r.chunk_id == 1 and r.is_final and r.text == eng.transcribe(job.buffer).text
+    bad = E.TranscriptionJob(E.AudioBuffer(np.full(32000, np.inf, np.float32), 16000), sequence_id=4)
+    assert w.process_job(bad).text == ""  # engine error -> logged + empty text, the worker keeps running (worker.rs:159-165)
+
+
+def test_cpp_host_mirror_gpu(micro_path):
+    import os
+    import subprocess
+
+    from openhush_b200 import lib
+    exe = os.path.join(lib.CSRC, "host", "host_test")
+    r = subprocess.run([exe, micro_path, "200000"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "HOST_TEST_OK" in r.stdout and "TEXT_LEN" in r.stdout, r.stdout + r.stderr
