@@ -183,7 +183,8 @@ def main():
     S = min(args.slots, B)
     ctx = lib.Context(path, compute_type=ctype, gpu_device=local_rank, max_batch=S)
     st = lib.State(ctx)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()  # a real (non-default) stream: the library launches on it and the timing events are recorded on it
+    torch.cuda.set_stream(stream)
     st.set_stream(stream.cuda_stream)
     p = default_full_params()
     p.temperature_inc = 0.0  # no temperature fallback in throughput runs (both arms)

@@ -308,6 +308,8 @@ int run_encoder(oh_state* st, int nw, int slot0, float* d_enc_f32_out, const int
         g.W = m.conv1.w;
         g.N = d;
         g.K = 3 * C;
+        g.n_taps = 3;  // TMA path: one tensor map per tap over the overlapping 3-row view
+        g.tap_k = C;
         g.bias = m.conv1.b;
         g.C = x1 + (size_t)d * e;  // row 1 of each window (row 0 and row 3001 stay zero)
         g.c_type = act;
@@ -327,6 +329,8 @@ int run_encoder(oh_state* st, int nw, int slot0, float* d_enc_f32_out, const int
         g.W = m.conv2.w;
         g.N = d;
         g.K = 3 * d;
+        g.n_taps = 3;
+        g.tap_k = d;
         g.bias = m.conv2.b;
         g.C = x;
         g.c_type = DT_F32;

@@ -18,7 +18,8 @@ rows = int(sys.argv[2]) if len(sys.argv) > 2 else 128
 n_past0 = int(sys.argv[3]) if len(sys.argv) > 3 else 100
 path = synth.model_path(arch)
 ctx = lib.Context(path, compute_type=COMPUTE_F16, max_batch=rows)
-stream = torch.cuda.current_stream()
+stream = torch.cuda.Stream()
+torch.cuda.set_stream(stream)
 mel = None
 CATS = {"gemm_decoder": 3, "layernorm": 4, "self_attention": 6, "cross_attention": 7, "embed": 8}
 variants = [("all kernels", 0)] + [("without " + k, 1 << v) for k, v in CATS.items()] + [("without all five", sum(1 << v for v in CATS.values()))]
