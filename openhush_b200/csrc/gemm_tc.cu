@@ -4,10 +4,11 @@
 // (reference arithmetic: whisper.cpp mat-muls with f16 operands and f32 accumulation,
 // reached from /root/reference/src/engine/whisper.rs:266).
 //
-// One persistent CTA per SM, 192 threads, warp-specialised:
+// One persistent CTA per SM, 320 threads, warp-specialised:
 //   warp 0      TMA producer: per k-block one A box [128 rows][64 k] and one W box [BLOCK_N rows][64 k]
 //   warp 1      TMEM allocator + single-thread MMA issuer (4 x tcgen05.mma M128 N=BLOCK_N K16 per k-block)
-//   warps 2..5  epilogue: each owns 32 TMEM lanes (= 32 output rows); 32 columns per tcgen05.ld
+//   warps 2..9  epilogue: warp % 4 selects the 32 TMEM lanes (= 32 output rows) it may read; the two warps of a
+//               lane group alternate over the 32-column chunks of the tile (one tcgen05.ld each)
 // Pipelines: smem ring (full/empty mbarriers, freed by tcgen05.commit), and two TMEM accumulator buffers so the
 // epilogue of tile i overlaps the MMAs of tile i+1.
 // Tiles: 128 x BLOCK_N, ordered n-fastest so the CTAs in flight share A rows and the whole of W through L2.
@@ -28,7 +29,7 @@ namespace oh {
 namespace {
 
 constexpr int BLOCK_M = 128, BLOCK_K = 64, UMMA_K = 16;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
 constexpr int SMEM_BUDGET = 200 * 1024;
 
 struct TcParams {
@@ -182,7 +183,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), 4);
+            mbar_init(tempty_bar(a), 8);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -254,7 +255,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         __syncwarp();
     } else {
         // ===================== epilogue =====================
-        const int lane_grp = warp & 3;  // TMEM lanes [32*lane_grp, +32) are the only ones this warp may read
+        // 8 warps: TMEM lanes [32*lane_grp, +32) are the only ones a warp may read (lane_grp = warp % 4); the two warps
+        // of a lane group take alternate 32-column chunks.  The residual of the next chunk is loaded before the
+        // current one is finished so its latency overlaps, and the GELU variant is chosen once per chunk so that
+        // the 32 elements form independent instruction chains.
+        const int lane_grp = warp & 3, col_half = (warp - 2) >> 2;
+        constexpr int N_CHUNKS = BLOCK_N >= 32 ? BLOCK_N / 32 : 1;
+        const int gelu_mode = p.gelu == GELU_FAST ? (p.round_type == DT_F16 ? 4 : (p.round_type == DT_BF16 ? 5 : GELU_FAST)) : p.gelu;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -262,12 +269,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             const int b = m_blk / p.tiles_per_batch, i0 = (m_blk % p.tiles_per_batch) * BLOCK_M;
             const int row = i0 + lane_grp * 32 + lane;
             const bool row_ok = row < p.rows;
-            mbar_wait(tfull_bar(acc), acc_phase);
-            tc_fence_after();
             const long long c_off = (long long)b * p.c_bstride + (long long)row * p.ldc;
             const float* rrow = (p.R && row_ok) ? p.R + (long long)b * p.r_bstride + (long long)row * p.ldr : nullptr;
+            const int n_lim = min(p.N, (n_blk + 1) * BLOCK_N);  // columns of this tile only
+            float4 rnext[8];
+            auto res_prefetch = [&](int chunk) {
+                const int n0 = n_blk * BLOCK_N + chunk * 32;
+                if (rrow && chunk < N_CHUNKS && n0 + 32 <= n_lim) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) rnext[j] = *reinterpret_cast<const float4*>(rrow + n0 + 4 * j);
+                }
+            };
+            res_prefetch(col_half);  // does not depend on the accumulator
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
 #pragma unroll 1
-            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+            for (int chunk = col_half; chunk < N_CHUNKS; chunk += 2) {
+                const int c0 = chunk * 32;
                 uint32_t v[32];
                 const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0);
                 if constexpr (BLOCK_N >= 32) {
@@ -277,9 +295,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 #pragma unroll
                     for (int j = 16; j < 32; ++j) v[j] = 0u;
                 }
+                float4 rcur[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) rcur[j] = rnext[j];
+                res_prefetch(chunk + 2);
                 tc_wait_ld();
                 const int n0 = n_blk * BLOCK_N + c0;
-                const int n_lim = min(p.N, (n_blk + 1) * BLOCK_N);  // columns of this tile only
                 // column offset inside the output row (head-split stores keep the 32-column chunk inside one head)
                 const long long n_off = p.c_hsplit > 0 ? (long long)(n0 / p.c_hsplit) * p.c_hstride + (n0 % p.c_hsplit) : (long long)n0;
                 if (row_ok && n0 < p.N) {
@@ -300,16 +321,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                                 if (n0 + j < n_lim) f[j] += p.bias[n0 + j];
                         }
                     }
-                    if (p.gelu != GELU_NONE) {
+                    switch (gelu_mode) {  // warp-uniform; each case is straight-line code over the 32 elements
+                        case GELU_LUT:
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = epi_gelu(f[j], p.gelu, p.round_type, p.lut);
+                            for (int j = 0; j < 32; ++j) f[j] = gelu_lut(f[j], p.lut);
+                            break;
+                        case GELU_TANH:
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) f[j] = gelu_tanh(f[j]);
+                            break;
+                        case GELU_FAST:
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) f[j] = gelu_fast(f[j]);
+                            break;
+                        case 4:
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) f[j] = __half2float(__float2half_rn(gelu_fast(__half2float(__float2half_rn(f[j])))));
+                            break;
+                        case 5:
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) f[j] = __bfloat162float(__float2bfloat16_rn(gelu_fast(f[j])));
+                            break;
+                        default:
+                            break;
                     }
                     if (rrow) {
                         if (full) {
 #pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                const float4 rr = *reinterpret_cast<const float4*>(rrow + n0 + j);
-                                f[j] += rr.x; f[j + 1] += rr.y; f[j + 2] += rr.z; f[j + 3] += rr.w;
+                            for (int j = 0; j < 8; ++j) {
+                                f[4 * j] += rcur[j].x; f[4 * j + 1] += rcur[j].y; f[4 * j + 2] += rcur[j].z; f[4 * j + 3] += rcur[j].w;
                             }
                         } else {
 #pragma unroll
