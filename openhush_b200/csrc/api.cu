@@ -79,6 +79,11 @@ OH_API oh_context* oh_init_from_file(const char* path_model, oh_context_params p
                 selftest_rc = gemm_skinny_selftest(nullptr, &e2);
                 if (selftest_rc == OH_OK) selftest_err = std::max(selftest_err, e2);
             }
+            if (selftest_rc == OH_OK) {
+                float e3 = -1.0f;
+                selftest_rc = gemm_splitk_selftest(nullptr, &e3);
+                if (selftest_rc == OH_OK) selftest_err = std::max(selftest_err, e3);
+            }
             g_selftest_err = selftest_err;
         }
         if (!force_simt && (selftest_rc != OH_OK || !(selftest_err >= 0.0f && selftest_err < 2e-3f))) {

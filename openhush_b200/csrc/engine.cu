@@ -102,7 +102,8 @@ int state_alloc(oh_state* st) {
     if (const char* s = getenv("OH_GRAPHS")) st->use_graphs = atoi(s) != 0;
     if (const char* s = getenv("OH_GELU")) st->gelu_lut_f32 = strcmp(s, "lut") == 0;
     if (const char* s = getenv("OH_SKIP_CATS")) g_skip_mask = (unsigned)strtoul(s, nullptr, 0);
-    if (const char* s = getenv("OH_SKINNY")) st->skinny_mode = atoi(s) == 0 ? 1 : 0;  // OH_SKINNY=0: decode mat-muls through the tcgen05 kernel
+    if (const char* s = getenv("OH_SKINNY")) st->skinny_mode = atoi(s) == 0 ? 1 : 0;  // OH_SKINNY=0: decode mat-muls through the persistent tcgen05 kernel
+    if (const char* s = getenv("OH_DECODE_GEMM")) st->skinny_mode = strcmp(s, "skinny") == 0 ? 0 : (strcmp(s, "tc") == 0 ? 1 : 2);
 
     OH_CUDA_CHECK(cudaStreamCreateWithFlags(&st->own_stream, cudaStreamNonBlocking));
     st->stream = st->own_stream;
@@ -277,8 +278,8 @@ static int gemm(oh_state* st, GemmArgs g) {
     g.round_type = act;
     if (g.gelu != GELU_NONE) g.gelu = act == DT_F32 ? (st->gelu_lut_f32 ? GELU_LUT : GELU_TANH) : GELU_FAST;
     if (act != DT_F32 && st->gemm_mode == 0 && gemm_tc_available()) {
-        if (g.batch * g.rows <= 256 && st->skinny_mode == 0) {
-            int rc = launch_gemm_skinny(g, st->stream);
+        if (g.batch * g.rows <= 256 && st->skinny_mode != 1) {
+            int rc = st->skinny_mode == 2 ? launch_gemm_splitk(g, st->stream) : launch_gemm_skinny(g, st->stream);
             if (rc != OH_ERR_UNSUPPORTED) return rc;
         }
         int rc = launch_gemm_tc(g, st->stream);

@@ -1,0 +1,393 @@
+// K4 (decode) on the 5th-generation tensor cores — mat-muls of the autoregressive step with M = resident decoder rows
+// (<= 256).  The weight matrix is read exactly once; what bounds a plain tiled kernel at this shape is that EVERY CTA
+// has to pull all of X[M][K] through its own L2 port (M x K x 2 bytes per SM, 1.3 MB for the MLP down-projection).
+// Here a thread-block CLUSTER of CS CTAs shares one 128 x 64 output tile and splits K, so a CTA ingests only
+// X[:, K/CS] and W[64][K/CS]; the CS partial tiles meet in distributed shared memory:
+//
+//   warp 0      TMA producer: k-blocks (64 wide) of this CTA's K-range, A box [128][64] + W box [64][64], 4-stage ring
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (M128 N64 K16, f32 accumulator in TMEM)
+//   warps 2..5  tcgen05.ld the 128 x 64 partial tile into shared memory (aliases the drained ring)
+//   cluster.sync
+//   all warps   CTA r reduces rows [r*128/CS, +128/CS) over the CS partial tiles in rank order (deterministic; no
+//               partial sum touches HBM), then bias / GELU / residual / type conversion and 16-byte coalesced stores
+//
+// The K-split depends on (N, K) only, never on M, and tensor-core rows are independent of each other, so a row's
+// result does not depend on which other rows share the batch.
+// (reference arithmetic: whisper.cpp decoder mat-muls, f16 operands with f32 accumulation, reached
+// from /root/reference/src/engine/whisper.rs:266.)
+#include <cooperative_groups.h>
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <algorithm>
+#include <cmath>
+#include <mutex>
+#include <vector>
+
+#include "../../include/oh_whisper.h"
+#include "kernels.h"
+#include "tc_ptx.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace oh {
+
+namespace {
+
+using namespace tcx;
+
+constexpr int SPK_M = 128, SPK_N = 64, SPK_K = 64, SPK_UMMA_K = 16;
+constexpr int SPK_THREADS = 192;
+constexpr int SPK_STAGES = 4;
+constexpr int SPK_A_BYTES = SPK_M * SPK_K * 2, SPK_B_BYTES = SPK_N * SPK_K * 2, SPK_STAGE_BYTES = SPK_A_BYTES + SPK_B_BYTES;
+constexpr int SPK_PS = SPK_N + 4;  // row stride (floats) of the partial tile: 16-byte aligned, spreads rows over banks
+constexpr int SPK_TMEM_COLS = 64;
+constexpr int SPK_SMEM_BYTES = SPK_STAGES * SPK_STAGE_BYTES + 1024 /*align slack*/ + 128 /*barriers*/;
+static_assert(SPK_M * SPK_PS * 4 <= SPK_STAGES * SPK_STAGE_BYTES, "partial tile must fit in the drained ring");
+
+struct SpkParams {
+    int M, N, K, num_kb;
+    uint32_t idesc;
+    const float* bias;
+    void* C;
+    int c_type, ldc;
+    const float* R;
+    int ldr;
+    int gelu, round_type;
+    const uint16_t* lut;
+};
+
+__global__ void __launch_bounds__(SPK_THREADS, 2)
+gemm_splitk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const SpkParams p) {
+    extern __shared__ uint8_t spk_smem_raw[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int cs = (int)cluster.num_blocks();
+    const int crank = (int)cluster.block_rank();
+    const int n_blk = blockIdx.x / cs, m_blk = blockIdx.y;
+    const uint32_t smem_base = (smem_u32(spk_smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
+    uint8_t* smem_gen = spk_smem_raw + (smem_base - smem_u32(spk_smem_raw));
+    const uint32_t bar_base = smem_base + SPK_STAGES * SPK_STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (SPK_STAGES + s); };
+    const uint32_t tfull_bar = bar_base + 8u * (2 * SPK_STAGES);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * SPK_STAGES + 1);
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+    float* Ps = reinterpret_cast<float*>(smem_gen);  // partial tile [128][SPK_PS], valid once the MMAs have drained the ring
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // this CTA's k-blocks: an even split of the num_kb blocks in rank order (a function of K and CS only)
+    const int kb_base = p.num_kb / cs, kb_rem = p.num_kb % cs;
+    const int kb0 = crank * kb_base + min(crank, kb_rem);
+    const int n_kb = kb_base + (crank < kb_rem ? 1 : 0);
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < SPK_STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(tfull_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)SPK_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int i = 0; i < n_kb; ++i) {
+                mbar_wait(empty_bar(stage), phase ^ 1);
+                const uint32_t sa = smem_base + stage * SPK_STAGE_BYTES, sb = sa + SPK_A_BYTES;
+                mbar_arrive_expect_tx(full_bar(stage), SPK_STAGE_BYTES);
+                const int kc = (kb0 + i) * SPK_K;
+                tma_load_2d(&map_w, sb, full_bar(stage), kc, n_blk * SPK_N);
+                tma_load_2d(&map_a, sa, full_bar(stage), kc, m_blk * SPK_M);
+                if (++stage == SPK_STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0 && n_kb > 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int i = 0; i < n_kb; ++i) {
+                mbar_wait(full_bar(stage), phase);
+                tc_fence_after();
+                const uint32_t sa = smem_base + stage * SPK_STAGE_BYTES, sb = sa + SPK_A_BYTES;
+                const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sb);
+#pragma unroll
+                for (int k = 0; k < SPK_K / SPK_UMMA_K; ++k) tc_mma_f16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (i | k) != 0 ? 1u : 0u);
+                tc_commit(empty_bar(stage));
+                if (++stage == SPK_STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            tc_commit(tfull_bar);  // arrives once every MMA above has completed (operands consumed, accumulator final)
+        }
+        __syncwarp();
+    } else {
+        // partial tile TMEM -> shared memory; thread = one accumulator row
+        const int lane_grp = warp & 3;  // TMEM lanes [32*lane_grp, +32) are the only ones this warp may read
+        const int row = lane_grp * 32 + lane;
+        float* prow = Ps + (size_t)row * SPK_PS;
+        if (n_kb > 0) {
+            mbar_wait(tfull_bar, 0);
+            tc_fence_after();
+#pragma unroll
+            for (int c0 = 0; c0 < SPK_N; c0 += 32) {
+                uint32_t v[32];
+                tc_ld_32x32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)c0, v);
+                tc_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(prow + c0 + j) =
+                        make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            }
+        } else {  // K-range empty (more ranks than k-blocks): contributes zeros
+#pragma unroll
+            for (int j = 0; j < SPK_N; j += 4) *reinterpret_cast<float4*>(prow + j) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    tc_fence_before();
+    cluster.sync();  // every partial tile is complete and visible cluster-wide
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)SPK_TMEM_COLS) : "memory");
+    }
+
+    // ---- fixed-order reduction of this CTA's rows across the cluster + epilogue
+    const int rows_per = SPK_M / cs;
+    const float* remote[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) remote[c] = cluster.map_shared_rank(Ps, c < cs ? c : 0);
+    const int m_lim = min(p.M - m_blk * SPK_M, SPK_M);
+    for (int idx = threadIdx.x; idx < rows_per * (SPK_N / 4); idx += SPK_THREADS) {
+        const int rl = crank * rows_per + idx / (SPK_N / 4), c4 = (idx % (SPK_N / 4)) * 4;
+        const int n = n_blk * SPK_N + c4;
+        if (rl >= m_lim || n >= p.N) continue;
+        float4 part[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            if (c < cs) part[c] = *reinterpret_cast<const float4*>(remote[c] + (size_t)rl * SPK_PS + c4);
+        float f[4] = {part[0].x, part[0].y, part[0].z, part[0].w};
+#pragma unroll
+        for (int c = 1; c < 8; ++c)
+            if (c < cs) {
+                f[0] += part[c].x; f[1] += part[c].y; f[2] += part[c].z; f[3] += part[c].w;
+            }
+        const int r = m_blk * SPK_M + rl;
+        const bool full = n + 4 <= p.N;
+        if (full) {
+            if (p.bias) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                f[0] += bb.x; f[1] += bb.y; f[2] += bb.z; f[3] += bb.w;
+            }
+            if (p.gelu != GELU_NONE) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) f[j] = epi_gelu(f[j], p.gelu, p.round_type, p.lut);
+            }
+            if (p.R) {
+                const float4 rr = *reinterpret_cast<const float4*>(p.R + (size_t)r * p.ldr + n);
+                f[0] += rr.x; f[1] += rr.y; f[2] += rr.z; f[3] += rr.w;
+            }
+            if (p.c_type == DT_F32) {
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + (size_t)r * p.ldc + n) = make_float4(f[0], f[1], f[2], f[3]);
+            } else if (p.c_type == DT_F16) {
+                __half2 h[2] = {__floats2half2_rn(f[0], f[1]), __floats2half2_rn(f[2], f[3])};
+                *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.C) + (size_t)r * p.ldc + n) = *reinterpret_cast<uint2*>(h);
+            } else {
+                __nv_bfloat162 h[2] = {__floats2bfloat162_rn(f[0], f[1]), __floats2bfloat162_rn(f[2], f[3])};
+                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)r * p.ldc + n) = *reinterpret_cast<uint2*>(h);
+            }
+        } else {
+            for (int j = 0; j < 4 && n + j < p.N; ++j) {
+                float v = f[j];
+                if (p.bias) v += p.bias[n + j];
+                if (p.gelu != GELU_NONE) v = epi_gelu(v, p.gelu, p.round_type, p.lut);
+                if (p.R) v += p.R[(size_t)r * p.ldr + n + j];
+                if (p.c_type == DT_F32) reinterpret_cast<float*>(p.C)[(size_t)r * p.ldc + n + j] = v;
+                else if (p.c_type == DT_F16) reinterpret_cast<__half*>(p.C)[(size_t)r * p.ldc + n + j] = __float2half_rn(v);
+                else reinterpret_cast<__nv_bfloat16*>(p.C)[(size_t)r * p.ldc + n + j] = __float2bfloat16_rn(v);
+            }
+        }
+    }
+    cluster.sync();  // nobody leaves while a peer may still read its partial tile
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 g_spk_encode = nullptr;
+int g_spk_state = 0;  // 0 unknown, 1 usable, -1 unusable
+std::once_flag g_spk_once;
+
+void spk_init_once() {
+    cudaDriverEntryPointQueryResult qres;
+    void* fn = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+        g_spk_state = -1;
+        return;
+    }
+    g_spk_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess || prop.major != 10) {
+        g_spk_state = -1;
+        return;
+    }
+    g_spk_state = cudaFuncSetAttribute(gemm_splitk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SPK_SMEM_BYTES) == cudaSuccess ? 1 : -1;
+}
+
+bool spk_encode_map(CUtensorMap* map, CUtensorMapDataType dt, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems, uint32_t box_outer) {
+    const uint64_t dims[2] = {inner, outer};
+    const uint64_t strides[1] = {ld_elems * 2};
+    const uint32_t box[2] = {SPK_K, box_outer};
+    const uint32_t estr[2] = {1, 1};
+    return g_spk_encode(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+// cluster size for an (N, K) problem: the largest power of two <= 8 that keeps every rank at least one k-block and the
+// grid within one resident wave (2 CTAs per SM)
+int gemm_splitk_cluster_size(int N, int K) {
+    static int cap = -1;
+    if (cap < 0) {
+        const char* e = getenv("OH_SPLITK_CS");
+        cap = e ? std::max(1, std::min(8, atoi(e))) : 8;
+    }
+    const int n_tiles = (N + SPK_N - 1) / SPK_N, num_kb = (K + SPK_K - 1) / SPK_K;
+    int cs = 1;
+    while (cs * 2 <= cap && cs * 2 <= num_kb && n_tiles * cs * 2 <= 296) cs *= 2;
+    return cs;
+}
+
+int launch_gemm_splitk(const GemmArgs& g, cudaStream_t st) {
+    std::call_once(g_spk_once, spk_init_once);
+    if (g_spk_state != 1) return OH_ERR_UNSUPPORTED;
+    const int M = g.batch * g.rows;
+    if (g.a_type == DT_F32 || g.a_type != g.w_type || g.batch != 1 || M < 1 || M > 256 || g.n_taps != 1 || g.c_hsplit != 0) return OH_ERR_UNSUPPORTED;
+    const int c_es = g.c_type == DT_F32 ? 4 : 2;
+    if ((reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.W) & 15) || (g.lda % 8) || (g.K % 8) || g.lda < g.K ||
+        ((size_t)g.ldc * c_es % 16) || (reinterpret_cast<uintptr_t>(g.C) & 15) || (g.R && ((g.ldr % 4) || (reinterpret_cast<uintptr_t>(g.R) & 15))) ||
+        (g.bias && (reinterpret_cast<uintptr_t>(g.bias) & 15)))
+        return OH_ERR_UNSUPPORTED;
+    const int n_tiles = (g.N + SPK_N - 1) / SPK_N;
+    if (n_tiles > 296) return OH_ERR_UNSUPPORTED;  // wide outputs (the logit projection) stay on the persistent kernel
+    const CUtensorMapDataType dt = g.a_type == DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    CUtensorMap ma, mw;
+    if (!spk_encode_map(&ma, dt, g.A, (uint64_t)g.K, (uint64_t)M, (uint64_t)g.lda, SPK_M)) return OH_ERR_UNSUPPORTED;
+    if (!spk_encode_map(&mw, dt, g.W, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.K, SPK_N)) return OH_ERR_UNSUPPORTED;
+    SpkParams p;
+    p.M = M; p.N = g.N; p.K = g.K; p.num_kb = (g.K + SPK_K - 1) / SPK_K;
+    const uint32_t fmt = g.a_type == DT_BF16 ? 1u : 0u;
+    p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(SPK_N >> 3) << 17) | ((uint32_t)(SPK_M >> 4) << 24);
+    p.bias = g.bias; p.C = g.C; p.c_type = g.c_type; p.ldc = g.ldc; p.R = g.R; p.ldr = g.ldr;
+    p.gelu = g.gelu; p.round_type = g.round_type; p.lut = g.lut;
+    const int cs = gemm_splitk_cluster_size(g.N, g.K);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(n_tiles * cs, (M + SPK_M - 1) / SPK_M);
+    cfg.blockDim = dim3(SPK_THREADS);
+    cfg.dynamicSmemBytes = SPK_SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    OH_SKIP_IF(PC_GEMM_DEC);
+    ProfScope ps(PC_GEMM_DEC, 2.0 * M * (double)g.N * g.K, st);
+    OH_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_splitk_kernel, ma, mw, p));
+    OH_COUNT_LAUNCH();
+    return OH_OK;
+}
+
+// start-up check against the SIMT kernel: every cluster size, M / N / K tails, GELU, residual, both output types
+int gemm_splitk_selftest(cudaStream_t st, float* max_rel_err) {
+    struct Case {
+        int M, N, K, c_type, gelu;
+    };
+    const Case cases[6] = {{64, 1280, 1280, DT_F32, 0}, {100, 3840, 1280, DT_F16, 0}, {37, 5120, 1280, DT_F16, 1},
+                           {128, 1280, 5120, DT_F32, 0}, {200, 1300, 264, DT_F32, 0}, {3, 384, 384, DT_F16, 1}};
+    float worst = 0.0f;
+    for (const Case& c : cases) {
+        std::vector<__half> hA((size_t)c.M * c.K), hW((size_t)c.N * c.K);
+        std::vector<float> hb(c.N), hR((size_t)c.M * c.N);
+        uint32_t s = 4242u + (uint32_t)c.N + (uint32_t)c.K;
+        auto rnd = [&]() {
+            s = s * 1664525u + 1013904223u;
+            return ((s >> 8) & 0xFFFF) / 32768.0f - 1.0f;
+        };
+        for (auto& v : hA) v = __float2half_rn(rnd());
+        for (auto& v : hW) v = __float2half_rn(rnd() * 0.1f);
+        for (auto& v : hb) v = rnd();
+        for (auto& v : hR) v = rnd();
+        const size_t c_es = c.c_type == DT_F32 ? 4 : 2;
+        void *dA = nullptr, *dW = nullptr, *db = nullptr, *dR = nullptr, *dC0 = nullptr, *dC1 = nullptr;
+        OH_CUDA_CHECK(cudaMalloc(&dA, hA.size() * 2));
+        OH_CUDA_CHECK(cudaMalloc(&dW, hW.size() * 2));
+        OH_CUDA_CHECK(cudaMalloc(&db, hb.size() * 4));
+        OH_CUDA_CHECK(cudaMalloc(&dR, hR.size() * 4));
+        OH_CUDA_CHECK(cudaMalloc(&dC0, (size_t)c.M * c.N * c_es));
+        OH_CUDA_CHECK(cudaMalloc(&dC1, (size_t)c.M * c.N * c_es));
+        OH_CUDA_CHECK(cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice));
+        OH_CUDA_CHECK(cudaMemcpy(dW, hW.data(), hW.size() * 2, cudaMemcpyHostToDevice));
+        OH_CUDA_CHECK(cudaMemcpy(db, hb.data(), hb.size() * 4, cudaMemcpyHostToDevice));
+        OH_CUDA_CHECK(cudaMemcpy(dR, hR.data(), hR.size() * 4, cudaMemcpyHostToDevice));
+        OH_CUDA_CHECK(cudaMemset(dC0, 0, (size_t)c.M * c.N * c_es));
+        OH_CUDA_CHECK(cudaMemset(dC1, 0, (size_t)c.M * c.N * c_es));
+        GemmArgs g;
+        g.A = dA; g.a_type = DT_F16; g.lda = c.K; g.rows = c.M; g.W = dW; g.w_type = DT_F16; g.N = c.N; g.K = c.K; g.bias = (const float*)db;
+        g.c_type = c.c_type; g.ldc = c.N; g.R = (const float*)dR; g.ldr = c.N; g.gelu = c.gelu ? GELU_FAST : GELU_NONE; g.round_type = DT_F16;
+        g.C = dC0;
+        int rc = launch_gemm_simt(g, st);
+        g.C = dC1;
+        if (rc == OH_OK) rc = launch_gemm_splitk(g, st);
+        cudaError_t ce = cudaStreamSynchronize(st);
+        std::vector<float> r0((size_t)c.M * c.N), r1((size_t)c.M * c.N);
+        if (rc == OH_OK && ce == cudaSuccess) {
+            if (c.c_type == DT_F32) {
+                cudaMemcpy(r0.data(), dC0, r0.size() * 4, cudaMemcpyDeviceToHost);
+                cudaMemcpy(r1.data(), dC1, r1.size() * 4, cudaMemcpyDeviceToHost);
+            } else {
+                std::vector<__half> t0(r0.size()), t1(r0.size());
+                cudaMemcpy(t0.data(), dC0, t0.size() * 2, cudaMemcpyDeviceToHost);
+                cudaMemcpy(t1.data(), dC1, t1.size() * 2, cudaMemcpyDeviceToHost);
+                for (size_t i = 0; i < t0.size(); ++i) {
+                    r0[i] = __half2float(t0[i]);
+                    r1[i] = __half2float(t1[i]);
+                }
+            }
+            double num = 0.0, den = 0.0;
+            for (size_t i = 0; i < r0.size(); ++i) {
+                num += (double)(r0[i] - r1[i]) * (r0[i] - r1[i]);
+                den += (double)r0[i] * r0[i];
+            }
+            const float e = (float)std::sqrt(num / std::max(den, 1e-30));
+            if (!(e < 2e-3f)) fprintf(stderr, "[ohwhisper] split-K tcgen05 self-test case M=%d N=%d K=%d: rel err %g\n", c.M, c.N, c.K, e);
+            worst = std::max(worst, e);
+        }
+        cudaFree(dA); cudaFree(dW); cudaFree(db); cudaFree(dR); cudaFree(dC0); cudaFree(dC1);
+        if (rc != OH_OK) return rc;
+        if (ce != cudaSuccess) {
+            set_error(std::string("gemm_splitk_selftest: ") + cudaGetErrorString(ce));
+            return OH_ERR_CUDA;
+        }
+    }
+    if (max_rel_err) *max_rel_err = worst;
+    return worst < 2e-3f ? OH_OK : OH_ERR_CUDA;
+}
+
+}  // namespace oh

@@ -74,6 +74,9 @@ int gemm_tc_selftest(cudaStream_t st, float* max_rel_err);
 // decode-time mat-muls (M <= 256 rows): weight-streaming kernel with cluster split-K (gemm_skinny.cu)
 int launch_gemm_skinny(const GemmArgs& g, cudaStream_t st);
 int gemm_skinny_selftest(cudaStream_t st, float* max_rel_err);
+// decode-time mat-muls on tcgen05 with cluster split-K and a DSMEM reduction (gemm_splitk.cu); the default for M <= 256
+int launch_gemm_splitk(const GemmArgs& g, cudaStream_t st);
+int gemm_splitk_selftest(cudaStream_t st, float* max_rel_err);
 int launch_gemm_simt(const GemmArgs& g, cudaStream_t st);
 // tcgen05/TMEM/TMA path; requires 16-bit A of the same type as W.  Returns OH_ERR_UNSUPPORTED for shapes it does not take.
 int launch_gemm_tc(const GemmArgs& g, cudaStream_t st);
