@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <initializer_list>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace oh {
@@ -76,6 +77,33 @@ struct ProfScope {
         if (idx >= 0 && g_prof) cudaEventRecord(g_prof->recs[idx].e1, st);
     }
 };
+
+// ---- programmatic dependent launch (decode step) ----------------------------------------------------
+// The decoder step is a chain of ~360 short kernels.  Inside the step every kernel is launched with the
+// programmatic-stream-serialization attribute: it may be scheduled while its predecessor is still running, does
+// whatever does not depend on it (barrier / TMEM set-up, weight loads), and blocks in pdl_wait() until the predecessor
+// has completed and flushed.  Rules every kernel of the chain follows: pdl_wait() before the first read of anything an
+// earlier kernel wrote and before the first global write, on every path (early exits included) — that also keeps the
+// ordering transitive.  Both instructions are no-ops in a kernel launched without the attribute.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+extern thread_local int g_pdl;  // > 0 while the calling thread is inside a decode step (set by decode_step_launch)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_pdl > 0 ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
 
 // ---- 16-bit activation type helpers ---------------------------------------------------------------
 template <typename T>

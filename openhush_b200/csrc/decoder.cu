@@ -18,6 +18,8 @@ namespace {
 // ------------------------------------------------------------------------------------------------- embed
 template <typename TW>
 __global__ void embed_kernel(const TW* __restrict__ emb, const float* __restrict__ pos_emb, DecodeSeqState s, int d, float* __restrict__ x) {
+    pdl_wait();  // programmatic dependent launch: nothing above depends on the preceding kernel (see common.cuh)
+    pdl_launch_dependents();
     const int b = blockIdx.x;
     if (!s.active[b]) return;
     const int tok = s.cur_token[b], pos = s.pos[b];
@@ -31,6 +33,8 @@ __global__ void embed_kernel(const TW* __restrict__ emb, const float* __restrict
 template <typename T>
 __global__ void __launch_bounds__(128) self_attention_decode_kernel(const T* __restrict__ qkv, T* __restrict__ kcache, T* __restrict__ vcache,
                                                                     DecodeSeqState s, int d, int n_ctx, T* __restrict__ out) {
+    pdl_wait();  // programmatic dependent launch: nothing above depends on the preceding kernel (see common.cuh)
+    pdl_launch_dependents();
     const int h = blockIdx.x, b = blockIdx.y;
     if (!s.active[b]) return;
     __shared__ float q[kHeadDim];
@@ -154,6 +158,8 @@ __device__ __forceinline__ void Vec8<__nv_bfloat16>::load(const __nv_bfloat16* p
 template <typename T>
 __global__ void __launch_bounds__(128) cross_attention_decode_kernel(const T* __restrict__ q, const T* __restrict__ xkv, DecodeSeqState s, int d,
                                                                      int Tn, T* __restrict__ out) {
+    pdl_wait();  // programmatic dependent launch: nothing above depends on the preceding kernel (see common.cuh)
+    pdl_launch_dependents();
     const int h = blockIdx.x, b = blockIdx.y;
     if (!s.active[b]) return;
     __shared__ float sc[1504];
@@ -261,6 +267,8 @@ template <typename T, bool IS_SELF>
 __global__ void __launch_bounds__(128) attention_decode_online_kernel(const T* __restrict__ qsrc, int q_ld, const T* kbase, const T* vbase,
                                                                       T* kcache, T* vcache, DecodeSeqState s, int d, int n_ctx_or_T,
                                                                       T* __restrict__ out) {
+    pdl_wait();  // programmatic dependent launch: nothing above depends on the preceding kernel (see common.cuh)
+    pdl_launch_dependents();
     const int h = blockIdx.x, b = blockIdx.y;
     if (!s.active[b]) return;
     __shared__ float sm_m[16], sm_l[16];
@@ -385,6 +393,8 @@ __global__ void __launch_bounds__(128) attention_decode_online_kernel(const T* _
 template <typename T>
 __global__ void __launch_bounds__(128) self_attention_decode_warp_kernel(const T* __restrict__ qkv, T* kcache, T* vcache, DecodeSeqState s, int d,
                                                                          int n_ctx, int rows, T* __restrict__ out) {
+    pdl_wait();  // programmatic dependent launch: nothing above depends on the preceding kernel (see common.cuh)
+    pdl_launch_dependents();
     const int H = d / kHeadDim;
     const int wid = blockIdx.x * 4 + (threadIdx.x >> 5);  // (row, head) index
     if (wid >= rows * H) return;
@@ -542,8 +552,15 @@ __device__ __forceinline__ void xa_unpack8<__nv_bfloat16>(const uint4& u, float 
 template <typename T>
 __global__ void __launch_bounds__(XA_THREADS) cross_attention_decode_bulk_kernel(const T* __restrict__ q, const T* __restrict__ xkv, DecodeSeqState s,
                                                                                 int d, int Tn, T* __restrict__ out) {
+    // Programmatic dependent launch: the only input written by the preceding kernel (the q projection) is q.  The
+    // row state was last written by the previous step's K9 and the cross K/V by the encoder, both complete before the
+    // predecessor passed its own pdl_wait, so the producer warp starts streaming K/V at once and only the consumers
+    // wait, right before they read q.
     const int h = blockIdx.x, b = blockIdx.y;
-    if (!s.active[b]) return;
+    if (!s.active[b]) {
+        pdl_wait();
+        return;
+    }
     extern __shared__ __align__(128) uint8_t xa_smem[];
     // layout: [stage][K 64x64 | V 64x64] (16 KB per stage), then merge scratch, then the barriers
     constexpr int STAGE_BYTES = 2 * XA_KEYS * kHeadDim * 2;
@@ -596,6 +613,8 @@ __global__ void __launch_bounds__(XA_THREADS) cross_attention_decode_bulk_kernel
         const int sub = lane & 7, grp = lane >> 3;
         const int gidx = warp * 4 + grp;  // 0..31
         float qv[8];
+        pdl_wait();
+        pdl_launch_dependents();
         {
             const T* qr = q + (size_t)b * d + h * kHeadDim + sub * 8;
             const float sc = 0.125f * 1.44269504088896340736f;  // 1/sqrt(64) * log2(e)
@@ -719,6 +738,8 @@ constexpr int K9_THREADS = 1024;
 __global__ void __launch_bounds__(K9_THREADS) logits_step_kernel(const float* __restrict__ logits, int ld, DecodeSeqState s,
                                                                 const DecodeRules* __restrict__ rp, float* __restrict__ dump_logprobs,
                                                                 float* __restrict__ dump_probs) {
+    pdl_wait();  // programmatic dependent launch: nothing above depends on the preceding kernel (see common.cuh)
+    pdl_launch_dependents();
     const int b = blockIdx.x;
     if (!s.active[b]) return;
     const DecodeRules r = *rp;
@@ -882,8 +903,8 @@ __global__ void __launch_bounds__(K9_THREADS) logits_step_kernel(const float* __
 
 int launch_embed(const void* tok_emb, int w_type, const float* pos_emb, const DecodeSeqState& s, int rows, int d, float* x, cudaStream_t st) {
     ProfScope ps(PC_EMBED, (double)rows * d * 10, st);
-    if (w_type == DT_BF16) embed_kernel<__nv_bfloat16><<<rows, 256, 0, st>>>((const __nv_bfloat16*)tok_emb, pos_emb, s, d, x);
-    else embed_kernel<__half><<<rows, 256, 0, st>>>((const __half*)tok_emb, pos_emb, s, d, x);
+    if (w_type == DT_BF16) OH_CUDA_CHECK(launch_k(embed_kernel<__nv_bfloat16>, rows, 256, 0, st, (const __nv_bfloat16*)tok_emb, pos_emb, s, d, x));
+    else OH_CUDA_CHECK(launch_k(embed_kernel<__half>, rows, 256, 0, st, (const __half*)tok_emb, pos_emb, s, d, x));
     OH_COUNT_LAUNCH();
     OH_CUDA_CHECK(cudaGetLastError());
     return OH_OK;
@@ -900,20 +921,15 @@ int launch_self_attention_decode(const void* qkv, void* kcache, void* vcache, in
         const char* e = getenv("OH_SELFATTN");
         use_warp = (e && strcmp(e, "online") == 0) ? 0 : 1;
     }
-    if (type == DT_F32) self_attention_decode_kernel<float><<<grid, 128, 0, st>>>((const float*)qkv, (float*)kcache, (float*)vcache, s, d, n_ctx, (float*)out);
+    if (type == DT_F32) OH_CUDA_CHECK(launch_k(self_attention_decode_kernel<float>, grid, 128, 0, st, (const float*)qkv, (float*)kcache, (float*)vcache, s, d, n_ctx, (float*)out));
     else if (!use_warp && type == DT_F16)
-        attention_decode_online_kernel<__half, true><<<grid, 128, 0, st>>>((const __half*)qkv, 3 * d, nullptr, nullptr, (__half*)kcache, (__half*)vcache, s, d,
-                                                                            n_ctx, (__half*)out);
+        OH_CUDA_CHECK(launch_k(attention_decode_online_kernel<__half, true>, grid, 128, 0, st, (const __half*)qkv, 3 * d, nullptr, nullptr, (__half*)kcache, (__half*)vcache, s, d, n_ctx, (__half*)out));
     else if (!use_warp)
-        attention_decode_online_kernel<__nv_bfloat16, true><<<grid, 128, 0, st>>>((const __nv_bfloat16*)qkv, 3 * d, nullptr, nullptr, (__nv_bfloat16*)kcache,
-                                                                                   (__nv_bfloat16*)vcache, s, d, n_ctx, (__nv_bfloat16*)out);
+        OH_CUDA_CHECK(launch_k(attention_decode_online_kernel<__nv_bfloat16, true>, grid, 128, 0, st, (const __nv_bfloat16*)qkv, 3 * d, nullptr, nullptr, (__nv_bfloat16*)kcache, (__nv_bfloat16*)vcache, s, d, n_ctx, (__nv_bfloat16*)out));
     else if (type == DT_F16)
-        self_attention_decode_warp_kernel<__half><<<(rows * (d / kHeadDim) + 3) / 4, 128, 0, st>>>((const __half*)qkv, (__half*)kcache, (__half*)vcache, s, d, n_ctx,
-                                                                                                    rows, (__half*)out);
+        OH_CUDA_CHECK(launch_k(self_attention_decode_warp_kernel<__half>, (rows * (d / kHeadDim) + 3) / 4, 128, 0, st, (const __half*)qkv, (__half*)kcache, (__half*)vcache, s, d, n_ctx, rows, (__half*)out));
     else
-        self_attention_decode_warp_kernel<__nv_bfloat16><<<(rows * (d / kHeadDim) + 3) / 4, 128, 0, st>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)kcache,
-                                                                                                           (__nv_bfloat16*)vcache, s, d, n_ctx, rows,
-                                                                                                           (__nv_bfloat16*)out);
+        OH_CUDA_CHECK(launch_k(self_attention_decode_warp_kernel<__nv_bfloat16>, (rows * (d / kHeadDim) + 3) / 4, 128, 0, st, (const __nv_bfloat16*)qkv, (__nv_bfloat16*)kcache, (__nv_bfloat16*)vcache, s, d, n_ctx, rows, (__nv_bfloat16*)out));
     OH_COUNT_LAUNCH();
     OH_CUDA_CHECK(cudaGetLastError());
     return OH_OK;
@@ -934,18 +950,15 @@ int launch_cross_attention_decode(const void* q, const void* xkv, int type, cons
             cudaFuncSetAttribute(cross_attention_decode_bulk_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, XA_SMEM_BYTES) != cudaSuccess)
             use_bulk = 0;
     }
-    if (type == DT_F32) cross_attention_decode_kernel<float><<<grid, 128, 0, st>>>((const float*)q, (const float*)xkv, s, d, T, (float*)out);
+    if (type == DT_F32) OH_CUDA_CHECK(launch_k(cross_attention_decode_kernel<float>, grid, 128, 0, st, (const float*)q, (const float*)xkv, s, d, T, (float*)out));
     else if (use_bulk && type == DT_F16)
-        cross_attention_decode_bulk_kernel<__half><<<grid, XA_THREADS, XA_SMEM_BYTES, st>>>((const __half*)q, (const __half*)xkv, s, d, T, (__half*)out);
+        OH_CUDA_CHECK(launch_k(cross_attention_decode_bulk_kernel<__half>, grid, XA_THREADS, XA_SMEM_BYTES, st, (const __half*)q, (const __half*)xkv, s, d, T, (__half*)out));
     else if (use_bulk)
-        cross_attention_decode_bulk_kernel<__nv_bfloat16><<<grid, XA_THREADS, XA_SMEM_BYTES, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)xkv, s, d, T,
-                                                                                                    (__nv_bfloat16*)out);
+        OH_CUDA_CHECK(launch_k(cross_attention_decode_bulk_kernel<__nv_bfloat16>, grid, XA_THREADS, XA_SMEM_BYTES, st, (const __nv_bfloat16*)q, (const __nv_bfloat16*)xkv, s, d, T, (__nv_bfloat16*)out));
     else if (type == DT_F16)
-        attention_decode_online_kernel<__half, false><<<grid, 128, 0, st>>>((const __half*)q, d, (const __half*)xkv, (const __half*)xkv, nullptr, nullptr, s, d, T,
-                                                                             (__half*)out);
+        OH_CUDA_CHECK(launch_k(attention_decode_online_kernel<__half, false>, grid, 128, 0, st, (const __half*)q, d, (const __half*)xkv, (const __half*)xkv, nullptr, nullptr, s, d, T, (__half*)out));
     else
-        attention_decode_online_kernel<__nv_bfloat16, false><<<grid, 128, 0, st>>>((const __nv_bfloat16*)q, d, (const __nv_bfloat16*)xkv, (const __nv_bfloat16*)xkv,
-                                                                                    nullptr, nullptr, s, d, T, (__nv_bfloat16*)out);
+        OH_CUDA_CHECK(launch_k(attention_decode_online_kernel<__nv_bfloat16, false>, grid, 128, 0, st, (const __nv_bfloat16*)q, d, (const __nv_bfloat16*)xkv, (const __nv_bfloat16*)xkv, nullptr, nullptr, s, d, T, (__nv_bfloat16*)out));
     OH_COUNT_LAUNCH();
     OH_CUDA_CHECK(cudaGetLastError());
     return OH_OK;
@@ -954,7 +967,7 @@ int launch_cross_attention_decode(const void* q, const void* xkv, int type, cons
 int launch_logits_step(const float* logits, int ld, const DecodeSeqState& s, const DecodeRules* r, int rows, float* dump_logprobs, float* dump_probs,
                        cudaStream_t st) {
     ProfScope ps(PC_LOGITS, (double)rows * ld * 4.0 * 2, st);
-    logits_step_kernel<<<rows, K9_THREADS, 0, st>>>(logits, ld, s, r, dump_logprobs, dump_probs);
+    OH_CUDA_CHECK(launch_k(logits_step_kernel, rows, K9_THREADS, 0, st, logits, ld, s, r, dump_logprobs, dump_probs));
     OH_COUNT_LAUNCH();
     OH_CUDA_CHECK(cudaGetLastError());
     return OH_OK;

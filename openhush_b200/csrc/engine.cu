@@ -17,6 +17,7 @@
 namespace oh {
 
 thread_local long long g_launch_count = 0;
+thread_local int g_pdl = 0;
 thread_local Profiler* g_prof = nullptr;
 unsigned g_skip_mask = 0;  // OH_SKIP_CATS: timing experiments only (kernel categories that are not launched)
 static thread_local std::string g_error;
@@ -100,6 +101,7 @@ int state_alloc(oh_state* st) {
     if (const char* s = getenv("OH_GEMM")) st->gemm_mode = strcmp(s, "simt") == 0 ? 1 : 0;
     if (const char* s = getenv("OH_ATTN")) st->attn_mode = strcmp(s, "simple") == 0 ? 1 : 0;
     if (const char* s = getenv("OH_GRAPHS")) st->use_graphs = atoi(s) != 0;
+    if (const char* s = getenv("OH_PDL")) st->use_pdl = atoi(s) != 0;
     if (const char* s = getenv("OH_GELU")) st->gelu_lut_f32 = strcmp(s, "lut") == 0;
     if (const char* s = getenv("OH_SKIP_CATS")) g_skip_mask = (unsigned)strtoul(s, nullptr, 0);
     if (const char* s = getenv("OH_SKINNY")) st->skinny_mode = atoi(s) == 0 ? 1 : 0;  // OH_SKINNY=0: decode mat-muls through the persistent tcgen05 kernel
@@ -411,6 +413,11 @@ static int decode_step_launch(oh_state* st, int rows, bool with_k9, bool dump) {
     cudaStream_t s = st->stream;
     float* x = (float*)st->dx.p;
     int rc;
+    struct PdlScope {  // kernels launched below may start while their predecessor drains (common.cuh)
+        const bool on;
+        explicit PdlScope(bool enable) : on(enable) { g_pdl += on ? 1 : 0; }
+        ~PdlScope() { g_pdl -= on ? 1 : 0; }
+    } pdl_scope(st->use_pdl && g_prof == nullptr);
     if ((rc = launch_embed(m.tok_emb.w, m.compute_type == OH_COMPUTE_BF16 ? DT_BF16 : DT_F16, m.dec_pos, st->seq, rows, d, x, s))) return rc;
     for (int l = 0; l < hp.n_text_layer; ++l) {
         const DecLayer& D = m.dec[l];

@@ -84,6 +84,7 @@ struct oh_state {
     int gemm_mode = 0;             // 0 auto (tcgen05 when 16-bit), 1 force SIMT
     int attn_mode = 0;             // 0 auto, 1 force the simple kernel
     int skinny_mode = 2;           // decode mat-muls: 2 cluster split-K tcgen05 kernel (default), 0 register-streaming mma.sync kernel, 1 persistent tcgen05 kernel
+    bool use_pdl = true;           // OH_PDL=0: decode-step kernels are launched fully serialised
     bool gelu_lut_f32 = false;     // OH_GELU=lut: f32 mode evaluates GELU through ggml's f16 table instead of f32 tanh
     oh::Profiler* prof = nullptr;
     bool profiling = false;

@@ -46,6 +46,8 @@ template <typename TA, typename TW, typename TC>
 __global__ void __launch_bounds__(THREADS) gemm_simt_kernel(GemmArgs g) {
     __shared__ float As[BK][BM + 4];
     __shared__ float Ws[BK][BN + 4];
+    pdl_wait();  // programmatic dependent launch (see common.cuh)
+    pdl_launch_dependents();
     const int M = g.batch * g.rows;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int tid = threadIdx.x;
@@ -137,9 +139,9 @@ __global__ void __launch_bounds__(THREADS) gemm_simt_kernel(GemmArgs g) {
 template <typename TA, typename TW>
 int dispatch_c(const GemmArgs& g, dim3 grid, cudaStream_t st) {
     switch (g.c_type) {
-        case DT_F32: gemm_simt_kernel<TA, TW, float><<<grid, THREADS, 0, st>>>(g); break;
-        case DT_F16: gemm_simt_kernel<TA, TW, __half><<<grid, THREADS, 0, st>>>(g); break;
-        default: gemm_simt_kernel<TA, TW, __nv_bfloat16><<<grid, THREADS, 0, st>>>(g); break;
+        case DT_F32: OH_CUDA_CHECK(launch_k(gemm_simt_kernel<TA, TW, float>, grid, THREADS, 0, st, g)); break;
+        case DT_F16: OH_CUDA_CHECK(launch_k(gemm_simt_kernel<TA, TW, __half>, grid, THREADS, 0, st, g)); break;
+        default: OH_CUDA_CHECK(launch_k(gemm_simt_kernel<TA, TW, __nv_bfloat16>, grid, THREADS, 0, st, g)); break;
     }
     return OH_OK;
 }

@@ -78,6 +78,8 @@ __device__ __forceinline__ float sk_gelu(float v, int gelu, int round_type, cons
 template <typename T, int MT>
 __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const SkParams p) {
     extern __shared__ __align__(128) uint8_t sk_smem[];
+    pdl_wait();  // programmatic dependent launch (see common.cuh)
+    pdl_launch_dependents();
     cg::cluster_group cluster = cg::this_cluster();
     const int cs = (int)cluster.num_blocks();
     const int crank = (int)cluster.block_rank();
@@ -193,13 +195,15 @@ int launch_mt(const SkParams& p, int cs, cudaStream_t st) {
     cfg.blockDim = dim3(SK_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = cs;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = g_pdl > 0 ? 2 : 1;
     OH_SKIP_IF(PC_GEMM_DEC);
     ProfScope ps(PC_GEMM_DEC, 2.0 * p.M * (double)p.N * p.K, st);
     OH_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_skinny_kernel<T, MT>, p));

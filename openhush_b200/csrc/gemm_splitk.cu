@@ -100,9 +100,19 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 
     if (warp == 0) {
         if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int i = 0; i < n_kb; ++i) {
+            // programmatic dependent launch: the weights do not depend on the preceding kernel, so the first ring of W
+            // boxes is requested before pdl_wait(); the activations follow once the predecessor has completed
+            const int n_pre = min(n_kb, SPK_STAGES);
+            for (int i = 0; i < n_pre; ++i) {
+                mbar_arrive_expect_tx(full_bar(i), SPK_STAGE_BYTES);
+                tma_load_2d(&map_w, smem_base + i * SPK_STAGE_BYTES + SPK_A_BYTES, full_bar(i), (kb0 + i) * SPK_K, n_blk * SPK_N);
+            }
+            pdl_wait();
+            pdl_launch_dependents();
+            for (int i = 0; i < n_pre; ++i) tma_load_2d(&map_a, smem_base + i * SPK_STAGE_BYTES, full_bar(i), (kb0 + i) * SPK_K, m_blk * SPK_M);
+            int stage = n_pre == SPK_STAGES ? 0 : n_pre;
+            uint32_t phase = n_pre == SPK_STAGES ? 1 : 0;
+            for (int i = n_pre; i < n_kb; ++i) {
                 mbar_wait(empty_bar(stage), phase ^ 1);
                 const uint32_t sa = smem_base + stage * SPK_STAGE_BYTES, sb = sa + SPK_A_BYTES;
                 mbar_arrive_expect_tx(full_bar(stage), SPK_STAGE_BYTES);
@@ -160,6 +170,8 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         }
     }
     tc_fence_before();
+    pdl_wait();  // every thread orders itself after the preceding kernel before it reads the residual / writes C
+    pdl_launch_dependents();
     cluster.sync();  // every partial tile is complete and visible cluster-wide
     if (warp == 1) {
         tc_fence_after();
@@ -300,13 +312,15 @@ int launch_gemm_splitk(const GemmArgs& g, cudaStream_t st) {
     cfg.blockDim = dim3(SPK_THREADS);
     cfg.dynamicSmemBytes = SPK_SMEM_BYTES;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = cs;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = g_pdl > 0 ? 2 : 1;
     OH_SKIP_IF(PC_GEMM_DEC);
     ProfScope ps(PC_GEMM_DEC, 2.0 * M * (double)g.N * g.K, st);
     OH_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_splitk_kernel, ma, mw, p));

@@ -101,6 +101,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_wait();  // programmatic dependent launch: barrier / TMEM set-up above overlaps the preceding kernel (see common.cuh)
+    pdl_launch_dependents();
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -395,7 +397,7 @@ int launch_t(const GemmArgs& g, cudaStream_t st) {
     p.c_hsplit = g.c_hsplit; p.c_hstride = g.c_hstride;
     const int grid = std::min(p.num_tiles, g_num_sms);
     ProfScope ps(g.batch * g.rows <= 512 ? PC_GEMM_DEC : PC_GEMM_ENC, 2.0 * g.batch * (double)g.rows * g.N * g.K, st);
-    gemm_tc_kernel<BLOCK_N><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(ma[0], ma[1], ma[2], mw, p);
+    OH_CUDA_CHECK(launch_k(gemm_tc_kernel<BLOCK_N>, grid, TC_THREADS, Cfg::SMEM_BYTES, st, ma[0], ma[1], ma[2], mw, p));
     OH_COUNT_LAUNCH();
     OH_CUDA_CHECK(cudaGetLastError());
     return OH_OK;

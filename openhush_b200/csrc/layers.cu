@@ -14,6 +14,8 @@ constexpr int LN_MAX_PER_LANE = 40;  // d <= 1280
 template <typename T>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int rows, int d, const float* __restrict__ w,
                                                         const float* __restrict__ b, T* __restrict__ y) {
+    pdl_wait();  // programmatic dependent launch (see common.cuh)
+    pdl_launch_dependents();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -77,9 +79,9 @@ int launch_layernorm(const float* x, int rows, int d, const float* w, const floa
     OH_SKIP_IF(PC_LN);
     ProfScope ps(PC_LN, (double)rows * d * (4.0 + (y_type == DT_F32 ? 4 : 2)), st);
     dim3 grid((rows + warps - 1) / warps);
-    if (y_type == DT_F32) layernorm_kernel<float><<<grid, warps * 32, 0, st>>>(x, rows, d, w, b, (float*)y);
-    else if (y_type == DT_F16) layernorm_kernel<__half><<<grid, warps * 32, 0, st>>>(x, rows, d, w, b, (__half*)y);
-    else layernorm_kernel<__nv_bfloat16><<<grid, warps * 32, 0, st>>>(x, rows, d, w, b, (__nv_bfloat16*)y);
+    if (y_type == DT_F32) OH_CUDA_CHECK(launch_k(layernorm_kernel<float>, grid, warps * 32, 0, st, x, rows, d, w, b, (float*)y));
+    else if (y_type == DT_F16) OH_CUDA_CHECK(launch_k(layernorm_kernel<__half>, grid, warps * 32, 0, st, x, rows, d, w, b, (__half*)y));
+    else OH_CUDA_CHECK(launch_k(layernorm_kernel<__nv_bfloat16>, grid, warps * 32, 0, st, x, rows, d, w, b, (__nv_bfloat16*)y));
     OH_COUNT_LAUNCH();
     OH_CUDA_CHECK(cudaGetLastError());
     return OH_OK;
