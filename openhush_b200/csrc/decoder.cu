@@ -386,6 +386,30 @@ __global__ void __launch_bounds__(128) attention_decode_online_kernel(const T* _
     }
 }
 
+// eight 16-bit elements (one 16-byte load) -> f32
+template <typename T>
+__device__ __forceinline__ void raw8_to_f32(const uint4& u, float (&v)[8]);
+template <>
+__device__ __forceinline__ void raw8_to_f32<__half>(const uint4& u, float (&v)[8]) {
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(h[i]);
+        v[2 * i] = f.x;
+        v[2 * i + 1] = f.y;
+    }
+}
+template <>
+__device__ __forceinline__ void raw8_to_f32<__nv_bfloat16>(const uint4& u, float (&v)[8]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(h[i]);
+        v[2 * i] = f.x;
+        v[2 * i + 1] = f.y;
+    }
+}
+
 // ------------------------------------------------- K7+K8a (16-bit modes): self attention, one warp per (row, head)
 // The self cache is short (<= 448 keys, typically ~100) and L2-resident, so this kernel is latency-bound: one warp
 // per (row, head) with no block-level barrier, 4 groups of 8 lanes x 4 keys per sweep (8 independent 16-byte loads
@@ -422,24 +446,33 @@ __global__ void __launch_bounds__(128) self_attention_decode_warp_kernel(const T
     for (int i = 0; i < 8; ++i) o[i] = 0.0f;
     const T* Kb = K + sub * 8;
     const T* Vb = V + sub * 8;
-    for (int base = 0; base < n_kv; base += 16) {  // warp-uniform trip count
-        Vec8<T> kv[4], vv[4];
+    // 16 keys per sweep (4 per group); the next sweep's K/V rows are requested before the current one is consumed, so a
+    // lane keeps up to 16 16-byte loads in flight (the kernel is bound by memory latency, not by arithmetic)
+    uint4 kc[4], vc[4];
+    auto load16 = [&](int base, uint4 (&kr)[4], uint4 (&vr)[4]) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int j = base + grp + 4 * u;
-            if (j < n_kv) {
-                kv[u].load_cg(Kb + (size_t)j * kHeadDim);
-                vv[u].load_cg(Vb + (size_t)j * kHeadDim);
+            if (j < n_kv) {  // the cache is written by this kernel: coherent (L2) loads, not the read-only path
+                kr[u] = __ldcg(reinterpret_cast<const uint4*>(Kb + (size_t)j * kHeadDim));
+                vr[u] = __ldcg(reinterpret_cast<const uint4*>(Vb + (size_t)j * kHeadDim));
             }
         }
+    };
+    load16(0, kc, vc);
+    for (int base = 0; base < n_kv; base += 16) {  // warp-uniform trip count
+        uint4 kn[4], vn[4];
+        if (base + 16 < n_kv) load16(base + 16, kn, vn);
         float sc4[4], mx = -INFINITY;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int j = base + grp + 4 * u;
             float acc = 0.0f;
             if (j < n_kv) {
+                float kf[8];
+                raw8_to_f32<T>(kc[u], kf);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) acc = fmaf(qv[i], kv[u].v[i], acc);
+                for (int i = 0; i < 8; ++i) acc = fmaf(qv[i], kf[i], acc);
             }
             acc += __shfl_xor_sync(0xffffffffu, acc, 1);
             acc += __shfl_xor_sync(0xffffffffu, acc, 2);
@@ -460,10 +493,17 @@ __global__ void __launch_bounds__(128) self_attention_decode_warp_kernel(const T
                     const float p = exp2f(sc4[u] - m_new);
                     l_run += p;
                     const float pr = Cvt<T>::to_f32(Cvt<T>::from_f32(p));
+                    float vf[8];
+                    raw8_to_f32<T>(vc[u], vf);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) o[i] = fmaf(pr, vv[u].v[i], o[i]);
+                    for (int i = 0; i < 8; ++i) o[i] = fmaf(pr, vf[i], o[i]);
                 }
             }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            kc[u] = kn[u];
+            vc[u] = vn[u];
         }
     }
     // merge the 4 groups (lanes sub, sub+8, sub+16, sub+24 hold the same channels)
