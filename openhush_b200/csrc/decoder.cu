@@ -1006,6 +1006,7 @@ int launch_cross_attention_decode(const void* q, const void* xkv, int type, cons
 
 int launch_logits_step(const float* logits, int ld, const DecodeSeqState& s, const DecodeRules* r, int rows, float* dump_logprobs, float* dump_probs,
                        cudaStream_t st) {
+    OH_SKIP_IF(PC_LOGITS);
     ProfScope ps(PC_LOGITS, (double)rows * ld * 4.0 * 2, st);
     OH_CUDA_CHECK(launch_k(logits_step_kernel, rows, K9_THREADS, 0, st, logits, ld, s, r, dump_logprobs, dump_probs));
     OH_COUNT_LAUNCH();

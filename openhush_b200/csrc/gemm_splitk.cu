@@ -82,6 +82,8 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     const int n_kb = kb_base + (crank < kb_rem ? 1 : 0);
 
     if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
         for (int s = 0; s < SPK_STAGES; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
@@ -184,20 +186,31 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 #pragma unroll
     for (int c = 0; c < 8; ++c) remote[c] = cluster.map_shared_rank(Ps, c < cs ? c : 0);
     const int m_lim = min(p.M - m_blk * SPK_M, SPK_M);
+    // phase 1: sum the CS partials of this CTA's rows (rank order) and park the sums in its own copy of those rows —
+    // peers only ever read the rows THEY own, so the in-place update races with nobody
     for (int idx = threadIdx.x; idx < rows_per * (SPK_N / 4); idx += SPK_THREADS) {
         const int rl = crank * rows_per + idx / (SPK_N / 4), c4 = (idx % (SPK_N / 4)) * 4;
-        const int n = n_blk * SPK_N + c4;
-        if (rl >= m_lim || n >= p.N) continue;
+        if (rl >= m_lim || n_blk * SPK_N + c4 >= p.N) continue;
         float4 part[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c)
             if (c < cs) part[c] = *reinterpret_cast<const float4*>(remote[c] + (size_t)rl * SPK_PS + c4);
-        float f[4] = {part[0].x, part[0].y, part[0].z, part[0].w};
+        float4 f = part[0];
 #pragma unroll
         for (int c = 1; c < 8; ++c)
             if (c < cs) {
-                f[0] += part[c].x; f[1] += part[c].y; f[2] += part[c].z; f[3] += part[c].w;
+                f.x += part[c].x; f.y += part[c].y; f.z += part[c].z; f.w += part[c].w;
             }
+        *reinterpret_cast<float4*>(Ps + (size_t)rl * SPK_PS + c4) = f;  // same thread reads it back in phase 2
+    }
+    cluster.barrier_arrive();  // this CTA no longer reads remote shared memory; the matching wait is the last statement
+    // phase 2: epilogue from local shared memory (overlaps the cluster barrier)
+    for (int idx = threadIdx.x; idx < rows_per * (SPK_N / 4); idx += SPK_THREADS) {
+        const int rl = crank * rows_per + idx / (SPK_N / 4), c4 = (idx % (SPK_N / 4)) * 4;
+        const int n = n_blk * SPK_N + c4;
+        if (rl >= m_lim || n >= p.N) continue;
+        const float4 f4 = *reinterpret_cast<const float4*>(Ps + (size_t)rl * SPK_PS + c4);
+        float f[4] = {f4.x, f4.y, f4.z, f4.w};
         const int r = m_blk * SPK_M + rl;
         const bool full = n + 4 <= p.N;
         if (full) {
@@ -234,7 +247,7 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             }
         }
     }
-    cluster.sync();  // nobody leaves while a peer may still read its partial tile
+    cluster.barrier_wait();  // nobody leaves while a peer may still read its partial tile
 }
 
 PFN_cuTensorMapEncodeTiled_v12000 g_spk_encode = nullptr;

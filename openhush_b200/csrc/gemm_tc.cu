@@ -396,6 +396,7 @@ int launch_t(const GemmArgs& g, cudaStream_t st) {
     p.R = g.R; p.r_bstride = g.r_bstride; p.ldr = g.ldr; p.gelu = g.gelu; p.round_type = g.round_type; p.lut = g.lut;
     p.c_hsplit = g.c_hsplit; p.c_hstride = g.c_hstride;
     const int grid = std::min(p.num_tiles, g_num_sms);
+    OH_SKIP_IF(g.N > 40000 ? PC_LOGITS : (g.batch * g.rows <= 512 ? PC_GEMM_DEC : PC_GEMM_ENC));  // timing experiments only
     ProfScope ps(g.batch * g.rows <= 512 ? PC_GEMM_DEC : PC_GEMM_ENC, 2.0 * g.batch * (double)g.rows * g.N * g.K, st);
     OH_CUDA_CHECK(launch_k(gemm_tc_kernel<BLOCK_N>, grid, TC_THREADS, Cfg::SMEM_BYTES, st, ma[0], ma[1], ma[2], mw, p));
     OH_COUNT_LAUNCH();

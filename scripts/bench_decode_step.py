@@ -21,8 +21,8 @@ ctx = lib.Context(path, compute_type=COMPUTE_F16, max_batch=rows)
 stream = torch.cuda.Stream()
 torch.cuda.set_stream(stream)
 mel = None
-CATS = {"gemm_decoder": 3, "layernorm": 4, "self_attention": 6, "cross_attention": 7, "embed": 8}
-variants = [("all kernels", 0)] + [("without " + k, 1 << v) for k, v in CATS.items()] + [("without all five", sum(1 << v for v in CATS.values()))]
+CATS = {"gemm_decoder": 3, "layernorm": 4, "self_attention": 6, "cross_attention": 7, "embed": 8, "logits": 9}
+variants = [("all kernels", 0)] + [("without " + k, 1 << v) for k, v in CATS.items()] + [("without all six", sum(1 << v for v in CATS.values()))]
 if len(sys.argv) > 4 and sys.argv[4] == "quick":
     variants = [v for v in variants if v[0] in ("all kernels", "without gemm_decoder", "without self_attention")]
 base = None
