@@ -983,18 +983,23 @@ int launch_cross_attention_decode(const void* q, const void* xkv, int type, cons
     OH_SKIP_IF(PC_CROSS_ATTN);
     ProfScope ps(PC_CROSS_ATTN, (double)rows * T * 2.0 * d * (type == DT_F32 ? 4 : 2), st);
     static int use_bulk = -1;
+    static int xa_smem = XA_SMEM_BYTES;
     if (use_bulk < 0) {
         const char* e = getenv("OH_XATTN");
         use_bulk = (e && strcmp(e, "online") == 0) ? 0 : 1;
-        if (cudaFuncSetAttribute(cross_attention_decode_bulk_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, XA_SMEM_BYTES) != cudaSuccess ||
-            cudaFuncSetAttribute(cross_attention_decode_bulk_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, XA_SMEM_BYTES) != cudaSuccess)
+        // OH_XATTN_OCC=1: one CTA per SM (shared memory padded past half an SM) so that the other row group's kernels
+        // always find room next to it; the 6-stage ring of a single CTA per SM still covers the HBM latency
+        const char* o = getenv("OH_XATTN_OCC");
+        if (o && atoi(o) == 1) xa_smem = 116 * 1024;
+        if (cudaFuncSetAttribute(cross_attention_decode_bulk_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, xa_smem) != cudaSuccess ||
+            cudaFuncSetAttribute(cross_attention_decode_bulk_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, xa_smem) != cudaSuccess)
             use_bulk = 0;
     }
     if (type == DT_F32) OH_CUDA_CHECK(launch_k(cross_attention_decode_kernel<float>, grid, 128, 0, st, (const float*)q, (const float*)xkv, s, d, T, (float*)out));
     else if (use_bulk && type == DT_F16)
-        OH_CUDA_CHECK(launch_k(cross_attention_decode_bulk_kernel<__half>, grid, XA_THREADS, XA_SMEM_BYTES, st, (const __half*)q, (const __half*)xkv, s, d, T, (__half*)out));
+        OH_CUDA_CHECK(launch_k(cross_attention_decode_bulk_kernel<__half>, grid, XA_THREADS, xa_smem, st, (const __half*)q, (const __half*)xkv, s, d, T, (__half*)out));
     else if (use_bulk)
-        OH_CUDA_CHECK(launch_k(cross_attention_decode_bulk_kernel<__nv_bfloat16>, grid, XA_THREADS, XA_SMEM_BYTES, st, (const __nv_bfloat16*)q, (const __nv_bfloat16*)xkv, s, d, T, (__nv_bfloat16*)out));
+        OH_CUDA_CHECK(launch_k(cross_attention_decode_bulk_kernel<__nv_bfloat16>, grid, XA_THREADS, xa_smem, st, (const __nv_bfloat16*)q, (const __nv_bfloat16*)xkv, s, d, T, (__nv_bfloat16*)out));
     else if (type == DT_F16)
         OH_CUDA_CHECK(launch_k(attention_decode_online_kernel<__half, false>, grid, 128, 0, st, (const __half*)q, d, (const __half*)xkv, (const __half*)xkv, nullptr, nullptr, s, d, T, (__half*)out));
     else

@@ -55,6 +55,9 @@ struct DevBuf {
 struct oh_state {
     oh_context* ctx = nullptr;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t stream2 = nullptr;  // second row group of the interleaved decode step
+    cudaEvent_t ev_dual[3] = {nullptr, nullptr, nullptr};
+    int dual_min_rows = 1 << 30;     // OH_DUAL=n: batches of >= n rows decode as two interleaved row groups (measured slower on B200: off)
     int max_batch = 1;   // KV-cache slots
     int enc_chunk = 1;   // windows per encoder pass
     int esz = 2;         // bytes per activation element
