@@ -1,5 +1,7 @@
 """BASELINE.json configs as GPU parity cases (the bench line is config 3; the others are checked here).
 
+  config 0  whisper tiny.en and tiny (multilingual), one 30 s clip, greedy; reference defaults (temperature fallback on)
+            and temperature_inc=0 — f32 mode, token ids and segment times exact against the oracle
   config 1  whisper base, batched log-mel + encoder forward, batch 32 x 30 s
   config 2  whisper small, batched greedy decode with KV cache (batch reduced to keep the oracle affordable)
   config 3  whisper large-v3 at full size: size-independent properties (batch == single, determinism, rule invariants)
@@ -15,6 +17,32 @@ pytestmark = pytest.mark.gpu
 
 def _flat(segs):
     return [t for s in segs for t in s["tokens"]], [x for s in segs for x in (s["t0"], s["t1"])]
+
+
+@pytest.mark.parametrize("arch", ["tiny.en", "tiny"])
+def test_config0_tiny_greedy_f32_token_exact(arch):
+    path = synth.model_path(arch)
+    om = O.OracleModel(path)
+    ost = O.OracleState(om, gelu=O.GELU_TANH, act_round=O.ACT_NONE)
+    ctx = lib.Context(path, compute_type=COMPUTE_F32, max_batch=1)
+    st = lib.State(ctx)
+    assert ctx.n_vocab == (51864 if arch == "tiny.en" else 51865)
+    clip = synth.audio(1)
+    ref_mel, _ = ost.pcm_to_mel(clip)
+    assert np.abs(st.pcm_to_mel([clip])[0] - ref_mel).max() < 1e-4
+    for inc in (0.0, 0.2):  # 0.2 = the reference's defaults: fallback ladder, host-side mt19937 sampling
+        p = default_full_params()
+        p.temperature_inc = inc
+        assert st.full(clip, p) == 0
+        assert ost.full(clip, p) == 0
+        got, ref = st.segments(0), ost.segments()
+        assert len(ref) > 0
+        assert _flat(got) == _flat(ref), (arch, inc)
+        assert [s["text"] for s in got] == [s["text"] for s in ref]
+    st.close()
+    ctx.close()
+    ost.close()
+    om.close()
 
 
 def test_config1_base_mel_encoder_batch32():
