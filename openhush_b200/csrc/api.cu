@@ -11,6 +11,7 @@ const std::string& get_error();
 }
 using namespace oh;
 
+static float g_attn_selftest_err = -1.0f;
 static float g_selftest_err = -1.0f;
 
 static int select_device(oh_context* ctx) { return cudaSetDevice(ctx->params.gpu_device) == cudaSuccess ? OH_OK : OH_ERR_CUDA; }
@@ -83,6 +84,11 @@ OH_API oh_context* oh_init_from_file(const char* path_model, oh_context_params p
                 float e3 = -1.0f;
                 selftest_rc = gemm_splitk_selftest(nullptr, &e3);
                 if (selftest_rc == OH_OK) selftest_err = std::max(selftest_err, e3);
+            }
+            if (selftest_rc == OH_OK) {  // attention compares two different summation orders with 16-bit P: own (looser) bound inside
+                float e4 = -1.0f;
+                selftest_rc = encoder_attention_tc_selftest(nullptr, &e4);
+                g_attn_selftest_err = e4;
             }
             g_selftest_err = selftest_err;
         }

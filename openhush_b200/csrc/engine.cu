@@ -109,7 +109,7 @@ int state_alloc(oh_state* st) {
     if (const char* s = getenv("OH_ENC_CHUNK")) chunk = std::max(1, std::min(st->max_batch, atoi(s)));
     st->enc_chunk = chunk;
     if (const char* s = getenv("OH_GEMM")) st->gemm_mode = strcmp(s, "simt") == 0 ? 1 : 0;
-    if (const char* s = getenv("OH_ATTN")) st->attn_mode = strcmp(s, "simple") == 0 ? 1 : 0;
+    if (const char* s = getenv("OH_ATTN")) st->attn_mode = strcmp(s, "simple") == 0 ? 1 : (strcmp(s, "flash") == 0 ? 2 : 0);  // flash: the mma.sync kernel
     if (const char* s = getenv("OH_GRAPHS")) st->use_graphs = atoi(s) != 0;
     if (const char* s = getenv("OH_PDL")) st->use_pdl = atoi(s) != 0;
     if (const char* s = getenv("OH_DUAL")) st->dual_min_rows = atoi(s) > 0 ? atoi(s) : (1 << 30);  // OH_DUAL=0: never interleave row groups
@@ -373,8 +373,12 @@ int run_encoder(oh_state* st, int nw, int slot0, float* d_enc_f32_out, const int
         g.W = L.qkv.w; g.N = 3 * d; g.K = d; g.bias = L.qkv.b;
         g.C = st->qkv.p; g.c_type = act; g.ldc = 3 * d;
         if ((rc = gemm(st, g))) return rc;
-        if (act != DT_F32 && st->attn_mode == 0) rc = launch_encoder_attention_mma(st->qkv.p, st->h.p, act, nw, T, d, s);
-        else rc = launch_encoder_attention_simple(st->qkv.p, st->h.p, act, nw, T, d, s);
+        if (act != DT_F32 && st->attn_mode != 1) {
+            rc = st->attn_mode == 0 ? launch_encoder_attention_tc(st->qkv.p, st->h.p, act, nw, T, d, s) : OH_ERR_UNSUPPORTED;
+            if (rc == OH_ERR_UNSUPPORTED) rc = launch_encoder_attention_mma(st->qkv.p, st->h.p, act, nw, T, d, s);
+        } else {
+            rc = launch_encoder_attention_simple(st->qkv.p, st->h.p, act, nw, T, d, s);
+        }
         if (rc) return rc;
         GemmArgs o;
         o.A = st->h.p; o.a_type = act; o.lda = d; o.rows = M;

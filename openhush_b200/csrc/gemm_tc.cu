@@ -411,6 +411,11 @@ bool gemm_tc_available() {
     return g_tc_state == 1;
 }
 
+bool tc_encode_tiled(CUtensorMap* map, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box) {
+    return gemm_tc_available() && encode_map(map, dt, rank, base, dims, strides_bytes, box);
+}
+
 int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
     if (!gemm_tc_available()) return OH_ERR_UNSUPPORTED;
     if (g.a_type == DT_F32 || g.a_type != g.w_type) return OH_ERR_UNSUPPORTED;

@@ -89,6 +89,10 @@ int launch_layernorm(const float* x, int rows, int d, const float* w, const floa
 // qkv: [B*T][3d] (q|k|v per token) of type t; out: [B*T][d] of type t.  Non-causal, softmax(q k^T / 8) v per head.
 int launch_encoder_attention_simple(const void* qkv, void* out, int type, int B, int T, int d, cudaStream_t st);
 int launch_encoder_attention_mma(const void* qkv, void* out, int type, int B, int T, int d, cudaStream_t st);
+// tcgen05 / TMEM / TMA flash attention (attention_tc.cu); 16-bit modes, returns OH_ERR_UNSUPPORTED otherwise
+int launch_encoder_attention_tc(const void* qkv, void* out, int type, int B, int T, int d, cudaStream_t st);
+bool encoder_attention_tc_available();
+int encoder_attention_tc_selftest(cudaStream_t st, float* max_rel_err);
 
 // ---- K7/K8/K9: decoder step (decoder.cu) ----------------------------------------------------------------
 constexpr int kMaxPrompt = 232;   // [prev] + 224 past tokens + sot/lang/task/notimestamps, rounded up

@@ -7,6 +7,11 @@
 #include "kernels.h"
 
 namespace oh {
+
+// 128-byte-swizzled tiled tensor map through the driver entry point resolved by gemm_tc.cu (rank 2 or 3; 16-bit elements)
+bool tc_encode_tiled(CUtensorMap* map, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box);
+
 namespace tcx {
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------
