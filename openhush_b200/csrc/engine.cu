@@ -916,8 +916,9 @@ int run_full(oh_state* st, const oh_full_params& p, const float* const* pcm, con
     const int nslots = std::min(batch, st->max_batch);  // more items than slots: items queue for a free slot
     const int n_max = hp.n_text_ctx / 2 - 4;
     const bool lockstep = getenv("OH_SCHED") && strcmp(getenv("OH_SCHED"), "lockstep") == 0;
-    const int CHECK = 8;
-    const int admit_threshold = lockstep ? nslots : std::max(1, std::min(8, nslots / 8));
+    // host look-in period (steps) and the number of waiting windows that triggers an encoder pass while rows are decoding
+    const int CHECK = getenv("OH_CHECK") ? std::max(1, atoi(getenv("OH_CHECK"))) : 8;
+    const int admit_threshold = lockstep ? nslots : (getenv("OH_ADMIT") ? std::max(1, atoi(getenv("OH_ADMIT"))) : std::max(1, std::min(8, nslots / 8)));
     std::vector<SlotInfo> slots(nslots);
     std::vector<int> free_slots;
     for (int i = nslots - 1; i >= 0; --i) free_slots.push_back(i);  // pop_back yields ascending slot ids
