@@ -316,7 +316,8 @@ def main():
                         peak_source=pk["src"], share_of_step=top["total_ms"] / tot_ms, avg_launch_ms=src["total_ms"] / src["launches"],
                         launches=src["launches"], measured_on="decode steps with every row active (stage API), CUDA events on the launching stream")
         kernels = {r["name"]: dict(ms=round(r["total_ms"], 3), launches=r["launches"], share=round(r["total_ms"] / tot_ms, 4),
-                                   rate=(round(r["work"] / (r["total_ms"] / 1e3) / 1e12, 2) if r["name"].startswith("gemm") or r["name"] == "attention_encoder"
+                                   rate=(None if not r["work"] else
+                                         round(r["work"] / (r["total_ms"] / 1e3) / 1e12, 2) if r["name"].startswith("gemm") or r["name"] == "attention_encoder"
                                          else round(r["work"] / (r["total_ms"] / 1e3) / 1e9, 1)),
                                    rate_unit=("TFLOP/s" if r["name"].startswith("gemm") or r["name"] == "attention_encoder" else "GB/s"))
                    for r in rep_sorted}
