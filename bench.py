@@ -222,7 +222,7 @@ def main():
     torch.cuda.synchronize()
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches = tokens = windows = dsteps = 0
+    launches = tokens = windows = dsteps = psteps = rsteps = 0
     e0.record(stream)
     for s in range(W, W + K):
         step_device(s)
@@ -231,6 +231,8 @@ def main():
         tokens += t.n_tokens
         windows += t.n_windows
         dsteps += t.n_decode_steps
+        psteps += t.n_prompt_steps
+        rsteps += t.n_row_steps
     e1.record(stream)
     barrier()
     torch.cuda.synchronize()
@@ -332,6 +334,7 @@ def main():
                     clocks=clocks,
                     e2e=dict(value=e2e_val, unit="audio-s/s", h2d_bytes_per_step=h2d // K, d2h_bytes_per_step=d2h // K, ms_per_step=e2e_ms / K),
                     gpu_launches=launches, roofline=roof, tokens_per_s=tokens / (ms / 1000.0), windows=windows, decode_steps=dsteps,
+                    row_steps=dict(total=rsteps, sampling=tokens, prompt_feed=psteps, idle=rsteps - tokens - psteps),
                     last_step_ms=last, kernels=kernels,
                     cross_attention_decode_gbs=(xattn["work"] / (xattn["total_ms"] / 1e3) / 1e9 if xattn else None))
         if not args.no_cpu_baseline and world == 1:

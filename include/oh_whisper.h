@@ -209,6 +209,8 @@ typedef struct oh_timings {
     int n_windows, n_decode_steps, n_tokens, n_fallbacks;
     long long n_kernel_launches;
     long long h2d_bytes, d2h_bytes; /* host<->device traffic of the call (PCM in, decoder state / token records out) */
+    long long n_prompt_steps;       /* row-steps spent feeding prompt tokens (one per step), not sampling */
+    long long n_row_steps;          /* decode steps x resident rows */
 } oh_timings;
 OH_API oh_timings oh_get_timings(oh_state* state);
 

@@ -1030,6 +1030,7 @@ int run_full(oh_state* st, const oh_full_params& p, const float* const* pcm, con
                 hs.completed[r] = 0;
                 hs.seek[r] = it.seek;
                 hs.seek_end[r] = it.seek_end;
+                st->timings.n_prompt_steps += pl - 1;
             }
             OH_CUDA_CHECK(cudaMemcpyAsync(st->seq_dev.p, hb, scalar_words * 4, cudaMemcpyHostToDevice, s));
             st->timings.h2d_bytes += (long long)scalar_words * 4;
@@ -1118,6 +1119,7 @@ int run_full(oh_state* st, const oh_full_params& p, const float* const* pcm, con
         for (int step = 0; step < CHECK; ++step) {
             if ((rc = run_decode_step_graph(st, nslots))) return rc == OH_ERR_CUDA ? rc : OH_ERR_DECODE;
             st->timings.n_decode_steps++;
+            st->timings.n_row_steps += nslots;
         }
         OH_CUDA_CHECK(cudaMemcpyAsync(hb, st->seq_dev.p, scalar_words * 4, cudaMemcpyDeviceToHost, s));
         OH_CUDA_CHECK(cudaStreamSynchronize(s));
