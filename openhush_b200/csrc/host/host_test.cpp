@@ -5,6 +5,7 @@
 #include <cstring>
 
 #include "engine.hpp"
+#include "tracker.hpp"
 
 using namespace openhush;
 #define CHECK(c)                                                          \
@@ -42,6 +43,41 @@ int main(int argc, char** argv) {
         job.sequence_id = 9;
         JobResult jr = process_job(nullptr, job);
         CHECK(jr.text.empty() && jr.sequence_id == 9 && std::fabs(jr.duration_secs - 1.0f) < 1e-6f);
+    }
+    {  // the reference's tracker unit tests (queue/mod.rs:324-466), same inputs and expected values
+        auto res = [](uint64_t seq, uint32_t chunk, const char* text, bool fin) { return JobResult{text, seq, chunk, fin, 1.0f}; };
+        TranscriptionTracker t;
+        t.add_pending(0, 0);
+        t.add_pending(0, 1);
+        t.add_result(res(0, 1, "world", true));
+        auto ready = t.take_ready();
+        CHECK(ready.size() == 1 && ready[0].text == "world");
+        t.add_result(res(0, 0, "hello", false));
+        ready = t.take_ready();
+        CHECK(ready.size() == 1 && ready[0].text == "hello");
+        TranscriptionTracker o = TranscriptionTracker::new_ordered();
+        o.add_pending(0, 0);
+        o.add_pending(1, 0);
+        o.add_result(res(1, 0, "second", true));
+        CHECK(o.take_ready().empty());
+        o.add_result(res(0, 0, "first", true));
+        ready = o.take_ready();
+        CHECK(ready.size() == 2 && ready[0].text == "first" && ready[1].text == "second");
+        TranscriptionTracker d;
+        d.add_result(res(0, 0, "hello world this is a test", false));
+        CHECK(d.take_ready()[0].text == "hello world this is a test");
+        d.add_result(res(0, 1, "is a test and more words", true));
+        CHECK(d.take_ready()[0].text == "and more words");
+        TranscriptionTracker b;
+        for (uint32_t c = 0; c < 3; ++c) CHECK(b.add_pending_with_config(0, c, 3, 2, BackpressureStrategy::DropNewest));
+        CHECK(!b.add_pending_with_config(0, 3, 3, 2, BackpressureStrategy::DropNewest) && b.pending_count() == 3);
+        TranscriptionTracker b2;
+        for (uint32_t c = 0; c < 3; ++c) CHECK(b2.add_pending_with_config(0, c, 3, 2, BackpressureStrategy::DropOldest));
+        CHECK(b2.add_pending_with_config(0, 3, 3, 2, BackpressureStrategy::DropOldest) && b2.pending_count() == 3);
+        CHECK(!b2.is_pending(0, 0) && b2.is_pending(0, 3));
+        TranscriptionTracker b3;
+        for (uint32_t c = 0; c < 4; ++c) CHECK(b3.add_pending_with_config(0, c, 3, 2, BackpressureStrategy::Warn));
+        CHECK(b3.pending_count() == 4 && b3.stats().waiting_count == 0 && !b3.is_empty());
     }
     if (argc >= 2) {
         auto r = WhisperEngine::create(argv[1], "en", false, argc >= 4 ? atoi(argv[3]) != 0 : true);

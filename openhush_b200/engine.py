@@ -283,6 +283,7 @@ class JobResult:  # queue::TranscriptionResult, queue/mod.rs:31-43
     chunk_id: int
     is_final: bool
     duration_secs: float
+    segments: list = field(default_factory=list)  # additive: (t0, t1, text) in 10 ms units, chunk-relative
 
 
 class TranscriptionWorker:
@@ -302,13 +303,14 @@ class TranscriptionWorker:
 
     def process_job(self, job: TranscriptionJob) -> JobResult:
         dur = job.buffer.duration_secs()
-        text = ""
+        text, segs = "", []
         if self.engine is not None:
             try:
-                text = self.engine.transcribe(job.buffer).text
+                res = self.engine.transcribe(job.buffer)
+                text, segs = res.text, res.segments
             except WhisperError:
-                text = ""
-        return JobResult(text, job.sequence_id, job.chunk_id, job.is_final, dur)
+                text, segs = "", []
+        return JobResult(text, job.sequence_id, job.chunk_id, job.is_final, dur, segs)
 
 
 def shard_jobs(n_jobs: int, rank: int, world: int):

@@ -1,0 +1,122 @@
+"""The step after the hot path: ordering, streaming merge and word-overlap dedup of results.
+The first nine tests restate the reference's own unit tests (/root/reference/src/queue/mod.rs:324-466) against the
+host mirror, with the same inputs and expected values; the rest cover what the mirror adds (timed segments)."""
+from openhush_b200.engine import JobResult
+from openhush_b200.tracker import BackpressureStrategy, TranscriptionTracker, merge_timed_segments
+
+
+def result(seq, chunk, text, is_final):  # queue/mod.rs:313-322
+    return JobResult(text, seq, chunk, is_final, 1.0)
+
+
+def test_streaming_mode_outputs_immediately():
+    tracker = TranscriptionTracker.new()
+    tracker.add_pending(0, 0)
+    tracker.add_pending(0, 1)
+    tracker.add_result(result(0, 1, "world", True))  # out of order
+    ready = tracker.take_ready()
+    assert len(ready) == 1 and ready[0].text == "world"
+    tracker.add_result(result(0, 0, "hello", False))
+    ready = tracker.take_ready()
+    assert len(ready) == 1 and ready[0].text == "hello"
+
+
+def test_ordered_mode_waits():
+    tracker = TranscriptionTracker.new_ordered()
+    tracker.add_pending(0, 0)
+    tracker.add_pending(1, 0)
+    tracker.add_result(result(1, 0, "second", True))
+    assert tracker.take_ready() == []
+    tracker.add_result(result(0, 0, "first", True))
+    ready = tracker.take_ready()
+    assert [r.text for r in ready] == ["first", "second"]
+
+
+def test_deduplication():
+    tracker = TranscriptionTracker.new()
+    tracker.add_pending(0, 0)
+    tracker.add_result(result(0, 0, "hello world this is a test", False))
+    assert tracker.take_ready()[0].text == "hello world this is a test"
+    tracker.add_pending(0, 1)
+    tracker.add_result(result(0, 1, "is a test and more words", True))
+    assert tracker.take_ready()[0].text == "and more words"
+
+
+def test_empty_tracker():
+    tracker = TranscriptionTracker.new()
+    assert tracker.is_empty() and tracker.pending_count() == 0 and tracker.waiting_count() == 0
+
+
+def test_pending_count():
+    tracker = TranscriptionTracker.new()
+    tracker.add_pending(0, 0)
+    tracker.add_pending(0, 1)
+    assert tracker.pending_count() == 2
+    tracker.add_result(result(0, 0, "test", False))
+    assert tracker.pending_count() == 1 and tracker.waiting_count() == 1
+
+
+def test_backpressure_drop_newest():
+    tracker = TranscriptionTracker.new()
+    for c in range(3):
+        assert tracker.add_pending_with_config(0, c, 3, 2, BackpressureStrategy.DROP_NEWEST)
+    assert not tracker.add_pending_with_config(0, 3, 3, 2, BackpressureStrategy.DROP_NEWEST)
+    assert tracker.pending_count() == 3
+
+
+def test_backpressure_drop_oldest():
+    tracker = TranscriptionTracker.new()
+    for c in range(3):
+        assert tracker.add_pending_with_config(0, c, 3, 2, BackpressureStrategy.DROP_OLDEST)
+    assert tracker.add_pending_with_config(0, 3, 3, 2, BackpressureStrategy.DROP_OLDEST)
+    assert tracker.pending_count() == 3
+    assert (0, 0) not in tracker.pending and (0, 3) in tracker.pending
+
+
+def test_backpressure_warn_accepts():
+    tracker = TranscriptionTracker.new()
+    for c in range(4):
+        assert tracker.add_pending_with_config(0, c, 3, 2, BackpressureStrategy.WARN)
+    assert tracker.pending_count() == 4
+
+
+def test_queue_stats():
+    tracker = TranscriptionTracker.new()
+    tracker.add_pending(0, 0)
+    tracker.add_pending(0, 1)
+    tracker.add_result(result(0, 0, "test", False))
+    stats = tracker.stats()
+    assert stats.pending_count == 1 and stats.waiting_count == 1
+
+
+# ---- beyond the reference's tests ---------------------------------------------------------------------------
+def test_dedup_details():
+    tracker = TranscriptionTracker.new()
+    tracker.add_result(result(0, 0, "short", False))          # <= 10 bytes: the remembered tail is not updated
+    assert tracker.take_ready()[0].text == "short" and tracker.last_text_suffix == ""
+    long = "x" * 40 + " the quick brown fox jumps"
+    tracker.add_result(result(0, 1, long, False))
+    tracker.take_ready()
+    assert tracker.last_text_suffix == long[-50:]                # last 50 bytes
+    tracker.add_result(result(0, 2, "fox jumps over", False))    # at most the first 10 words are candidates
+    assert tracker.take_ready()[0].text == "over"
+    tracker.reset_dedup()
+    tracker.add_result(result(0, 3, "fox jumps again", True))
+    assert tracker.take_ready()[0].text == "fox jumps again"
+    # multi-byte text: the 50-byte cut never lands inside a character
+    tracker.add_result(result(1, 0, "é" * 40, True))
+    tracker.take_ready()
+    assert tracker.last_text_suffix == "é" * 25
+    # streaming hand-out is sorted by (sequence_id, chunk_id) whatever the completion order
+    tracker.reset_dedup()
+    for seq, chunk in [(2, 1), (1, 5), (2, 0)]:
+        tracker.add_result(result(seq, chunk, f"{seq}.{chunk}", False))
+    assert [(r.sequence_id, r.chunk_id) for r in tracker.take_ready()] == [(1, 5), (2, 0), (2, 1)]
+
+
+def test_merge_timed_segments():
+    a = JobResult("a b", 7, 0, False, 30.0, [(0, 250, "a"), (250, 2900, " b")])
+    b = JobResult("c", 7, 1, True, 12.5, [(10, 400, "c")])
+    assert merge_timed_segments([b, a]) == [(0, 250, "a"), (250, 2900, " b"), (3010, 3400, "c")]
+    # overlapping capture: chunk 1 starts 0.5 s before chunk 0 ends
+    assert merge_timed_segments([a, b], chunk_offsets_cs={0: 0, 1: 2950})[-1] == (2960, 3350, "c")
