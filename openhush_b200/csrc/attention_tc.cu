@@ -50,7 +50,6 @@ struct AtParams {
     int T, d, n_kb;
     uint32_t idesc_qk, idesc_pv;
     void* out;
-    int out_is_bf16;
 };
 
 template <typename T>
@@ -64,10 +63,6 @@ template <>
 __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
-}
-template <typename T>
-__device__ __forceinline__ float round_act(float v) {
-    return Cvt<T>::to_f32(Cvt<T>::from_f32(v));
 }
 __device__ __forceinline__ float ex2_approx(float x) {  // arguments are <= 0 here; flush-to-zero for very negative ones is what we want
     float y;
@@ -356,7 +351,6 @@ int launch_encoder_attention_tc(const void* qkv, void* out, int type, int B, int
     p.idesc_qk = base | ((uint32_t)(AT_BK >> 3) << 17);
     p.idesc_pv = base | ((uint32_t)(AT_HD >> 3) << 17) | (1u << 16);  // bit 16: B operand is MN-major
     p.out = out;
-    p.out_is_bf16 = type == DT_BF16;
     dim3 grid((Tn + AT_BQ - 1) / AT_BQ, d / AT_HD, B);
     ProfScope ps(PC_ATTN_ENC, 4.0 * B * (double)Tn * Tn * d, st);
     if (type == DT_F16) OH_CUDA_CHECK(launch_k(encoder_attention_tc_kernel<__half>, grid, AT_THREADS, AT_SMEM_BYTES, st, map_q, map_kv, p));

@@ -8,8 +8,10 @@
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (M128 N64 K16, f32 accumulator in TMEM)
 //   warps 2..5  tcgen05.ld the 128 x 64 partial tile into shared memory (aliases the drained ring)
 //   cluster.sync
-//   all warps   CTA r reduces rows [r*128/CS, +128/CS) over the CS partial tiles in rank order (deterministic; no
-//               partial sum touches HBM), then bias / GELU / residual / type conversion and 16-byte coalesced stores
+//   all warps   CTA r sums rows [r*128/CS, +128/CS) of the CS partial tiles in rank order (deterministic; no partial
+//               sum touches HBM) into its own copy, arrives on the cluster barrier, then runs the epilogue from local
+//               shared memory (bias / GELU / residual / type conversion, 16-byte coalesced stores) and only then
+//               waits on the barrier, so the barrier latency hides under the stores
 //
 // The K-split depends on (N, K) only, never on M, and tensor-core rows are independent of each other, so a row's
 // result does not depend on which other rows share the batch.
