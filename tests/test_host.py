@@ -174,3 +174,24 @@ def test_cpp_host_mirror_cpu(micro_path):
     if not torch.cuda.is_available():
         r = subprocess.run([exe, micro_path, "32000", "1"], capture_output=True, text=True, timeout=60)
         assert "LOAD_FAILED Failed to load model:" in r.stdout and "no CPU fallback" in r.stdout
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the restated reference path on the host cores) on the micro model: one JSON line with
+    the keys the driver reads; under torchrun only rank 0 prints."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, OH_REF_BUDGET_S="30")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--arch", "micro", "--steps", "2", "--warmup", "1"],
+                         capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "audio_seconds_per_second" and line["unit"] == "audio-s/s"
+    assert line["higher_is_better"] is True and line["value"] > 0 and line["steps"] >= 1
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    out1 = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--arch", "micro", "--gpus", "2"],
+                          capture_output=True, text=True, env=dict(env, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"), timeout=600)
+    assert out1.returncode == 0 and out1.stdout.strip() == ""
