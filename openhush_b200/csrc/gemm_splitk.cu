@@ -4,7 +4,8 @@
 // Here a thread-block CLUSTER of CS CTAs shares one 128 x 64 output tile and splits K, so a CTA ingests only
 // X[:, K/CS] and W[64][K/CS]; the CS partial tiles meet in distributed shared memory:
 //
-//   warp 0      TMA producer: k-blocks (64 wide) of this CTA's K-range, A box [128][64] + W box [64][64], 4-stage ring
+//   warp 0      TMA producer: k-blocks (64 wide) of this CTA's K-range, A box(es) [128][64] + W box [64][64], 4-stage ring
+//               (M > 128: two A boxes per stage share the W box, 2-stage ring — 256 rows cost one pass over W)
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (M128 N64 K16, f32 accumulator in TMEM)
 //   warps 2..5  tcgen05.ld the 128 x 64 partial tile into shared memory (aliases the drained ring)
 //   cluster.sync
@@ -40,12 +41,19 @@ using namespace tcx;
 
 constexpr int SPK_M = 128, SPK_N = 64, SPK_K = 64, SPK_UMMA_K = 16;
 constexpr int SPK_THREADS = 192;
-constexpr int SPK_STAGES = 4;
-constexpr int SPK_A_BYTES = SPK_M * SPK_K * 2, SPK_B_BYTES = SPK_N * SPK_K * 2, SPK_STAGE_BYTES = SPK_A_BYTES + SPK_B_BYTES;
+constexpr int SPK_A_BYTES = SPK_M * SPK_K * 2, SPK_B_BYTES = SPK_N * SPK_K * 2;
 constexpr int SPK_PS = SPK_N + 4;  // row stride (floats) of the partial tile: 16-byte aligned, spreads rows over banks
-constexpr int SPK_TMEM_COLS = 64;
-constexpr int SPK_SMEM_BYTES = SPK_STAGES * SPK_STAGE_BYTES + 1024 /*align slack*/ + 128 /*barriers*/;
-static_assert(SPK_M * SPK_PS * 4 <= SPK_STAGES * SPK_STAGE_BYTES, "partial tile must fit in the drained ring");
+// MT = 128-row tiles of X per CTA (1 for M <= 128, 2 for M <= 256): both tiles share every W box, so 256 rows cost one
+// pass over the weights and one cluster per output column block, not two
+template <int MT>
+struct SpkCfg {
+    static constexpr int STAGES = MT == 1 ? 4 : 2;  // 96 KB / 80 KB of ring: two CTAs per SM either way
+    static constexpr int STAGE_BYTES = MT * SPK_A_BYTES + SPK_B_BYTES;
+    static constexpr int TMEM_COLS = 64 * MT;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 128 /*barriers*/;
+    static constexpr int ROWS = MT * SPK_M;
+    static_assert(ROWS * SPK_PS * 4 <= STAGES * STAGE_BYTES, "partial tile must fit in the drained ring");
+};
 
 struct SpkParams {
     int M, N, K, num_kb;
@@ -59,8 +67,12 @@ struct SpkParams {
     const uint16_t* lut;
 };
 
+template <int MT>
 __global__ void __launch_bounds__(SPK_THREADS, 2)
 gemm_splitk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const SpkParams p) {
+    constexpr int SPK_STAGES = SpkCfg<MT>::STAGES, SPK_STAGE_BYTES = SpkCfg<MT>::STAGE_BYTES, SPK_TMEM_COLS = SpkCfg<MT>::TMEM_COLS,
+                  SPK_ROWS = SpkCfg<MT>::ROWS;
+    constexpr int SPK_W_OFF = MT * SPK_A_BYTES;  // stage layout: A tile 0 [, A tile 1], W
     extern __shared__ uint8_t spk_smem_raw[];
     cg::cluster_group cluster = cg::this_cluster();
     const int cs = (int)cluster.num_blocks();
@@ -74,7 +86,7 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     const uint32_t tfull_bar = bar_base + 8u * (2 * SPK_STAGES);
     const uint32_t tmem_slot = bar_base + 8u * (2 * SPK_STAGES + 1);
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
-    float* Ps = reinterpret_cast<float*>(smem_gen);  // partial tile [128][SPK_PS], valid once the MMAs have drained the ring
+    float* Ps = reinterpret_cast<float*>(smem_gen);  // partial tile [128*MT][SPK_PS], valid once the MMAs have drained the ring
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -109,20 +121,24 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             const int n_pre = min(n_kb, SPK_STAGES);
             for (int i = 0; i < n_pre; ++i) {
                 mbar_arrive_expect_tx(full_bar(i), SPK_STAGE_BYTES);
-                tma_load_2d(&map_w, smem_base + i * SPK_STAGE_BYTES + SPK_A_BYTES, full_bar(i), (kb0 + i) * SPK_K, n_blk * SPK_N);
+                tma_load_2d(&map_w, smem_base + i * SPK_STAGE_BYTES + SPK_W_OFF, full_bar(i), (kb0 + i) * SPK_K, n_blk * SPK_N);
             }
             pdl_wait();
             pdl_launch_dependents();
-            for (int i = 0; i < n_pre; ++i) tma_load_2d(&map_a, smem_base + i * SPK_STAGE_BYTES, full_bar(i), (kb0 + i) * SPK_K, m_blk * SPK_M);
+            for (int i = 0; i < n_pre; ++i)
+#pragma unroll
+                for (int t = 0; t < MT; ++t)
+                    tma_load_2d(&map_a, smem_base + i * SPK_STAGE_BYTES + t * SPK_A_BYTES, full_bar(i), (kb0 + i) * SPK_K, m_blk * SPK_ROWS + t * SPK_M);
             int stage = n_pre == SPK_STAGES ? 0 : n_pre;
             uint32_t phase = n_pre == SPK_STAGES ? 1 : 0;
             for (int i = n_pre; i < n_kb; ++i) {
                 mbar_wait(empty_bar(stage), phase ^ 1);
-                const uint32_t sa = smem_base + stage * SPK_STAGE_BYTES, sb = sa + SPK_A_BYTES;
+                const uint32_t sa = smem_base + stage * SPK_STAGE_BYTES, sb = sa + SPK_W_OFF;
                 mbar_arrive_expect_tx(full_bar(stage), SPK_STAGE_BYTES);
                 const int kc = (kb0 + i) * SPK_K;
                 tma_load_2d(&map_w, sb, full_bar(stage), kc, n_blk * SPK_N);
-                tma_load_2d(&map_a, sa, full_bar(stage), kc, m_blk * SPK_M);
+#pragma unroll
+                for (int t = 0; t < MT; ++t) tma_load_2d(&map_a, sa + t * SPK_A_BYTES, full_bar(stage), kc, m_blk * SPK_ROWS + t * SPK_M);
                 if (++stage == SPK_STAGES) {
                     stage = 0;
                     phase ^= 1;
@@ -137,10 +153,15 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             for (int i = 0; i < n_kb; ++i) {
                 mbar_wait(full_bar(stage), phase);
                 tc_fence_after();
-                const uint32_t sa = smem_base + stage * SPK_STAGE_BYTES, sb = sa + SPK_A_BYTES;
-                const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sb);
+                const uint32_t sa = smem_base + stage * SPK_STAGE_BYTES, sb = sa + SPK_W_OFF;
+                const uint64_t db = make_smem_desc(sb);
 #pragma unroll
-                for (int k = 0; k < SPK_K / SPK_UMMA_K; ++k) tc_mma_f16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (i | k) != 0 ? 1u : 0u);
+                for (int t = 0; t < MT; ++t) {
+                    const uint64_t da = make_smem_desc(sa + t * SPK_A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < SPK_K / SPK_UMMA_K; ++k)
+                        tc_mma_f16(tmem_base + (uint32_t)(t * SPK_N), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (i | k) != 0 ? 1u : 0u);
+                }
                 tc_commit(empty_bar(stage));
                 if (++stage == SPK_STAGES) {
                     stage = 0;
@@ -154,23 +175,28 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         // partial tile TMEM -> shared memory; thread = one accumulator row
         const int lane_grp = warp & 3;  // TMEM lanes [32*lane_grp, +32) are the only ones this warp may read
         const int row = lane_grp * 32 + lane;
-        float* prow = Ps + (size_t)row * SPK_PS;
         if (n_kb > 0) {
             mbar_wait(tfull_bar, 0);
             tc_fence_after();
+        }
 #pragma unroll
-            for (int c0 = 0; c0 < SPK_N; c0 += 32) {
-                uint32_t v[32];
-                tc_ld_32x32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)c0, v);
-                tc_wait_ld();
+        for (int t = 0; t < MT; ++t) {
+            float* prow = Ps + (size_t)(t * SPK_M + row) * SPK_PS;
+            if (n_kb > 0) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4*>(prow + c0 + j) =
-                        make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                for (int c0 = 0; c0 < SPK_N; c0 += 32) {
+                    uint32_t v[32];
+                    tc_ld_32x32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(t * SPK_N + c0), v);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(prow + c0 + j) =
+                            make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                }
+            } else {  // K-range empty (more ranks than k-blocks): contributes zeros
+#pragma unroll
+                for (int j = 0; j < SPK_N; j += 4) *reinterpret_cast<float4*>(prow + j) = make_float4(0.f, 0.f, 0.f, 0.f);
             }
-        } else {  // K-range empty (more ranks than k-blocks): contributes zeros
-#pragma unroll
-            for (int j = 0; j < SPK_N; j += 4) *reinterpret_cast<float4*>(prow + j) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
     tc_fence_before();
@@ -183,11 +209,11 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     }
 
     // ---- fixed-order reduction of this CTA's rows across the cluster + epilogue
-    const int rows_per = SPK_M / cs;
+    const int rows_per = SPK_ROWS / cs;
     const float* remote[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) remote[c] = cluster.map_shared_rank(Ps, c < cs ? c : 0);
-    const int m_lim = min(p.M - m_blk * SPK_M, SPK_M);
+    const int m_lim = min(p.M - m_blk * SPK_ROWS, SPK_ROWS);
     // phase 1: sum the CS partials of this CTA's rows (rank order) and park the sums in its own copy of those rows —
     // peers only ever read the rows THEY own, so the in-place update races with nobody
     for (int idx = threadIdx.x; idx < rows_per * (SPK_N / 4); idx += SPK_THREADS) {
@@ -213,7 +239,7 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         if (rl >= m_lim || n >= p.N) continue;
         const float4 f4 = *reinterpret_cast<const float4*>(Ps + (size_t)rl * SPK_PS + c4);
         float f[4] = {f4.x, f4.y, f4.z, f4.w};
-        const int r = m_blk * SPK_M + rl;
+        const int r = m_blk * SPK_ROWS + rl;
         const bool full = n + 4 <= p.N;
         if (full) {
             if (p.bias) {
@@ -271,7 +297,10 @@ void spk_init_once() {
         g_spk_state = -1;
         return;
     }
-    g_spk_state = cudaFuncSetAttribute(gemm_splitk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SPK_SMEM_BYTES) == cudaSuccess ? 1 : -1;
+    g_spk_state = cudaFuncSetAttribute(gemm_splitk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SpkCfg<1>::SMEM_BYTES) == cudaSuccess &&
+                          cudaFuncSetAttribute(gemm_splitk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SpkCfg<2>::SMEM_BYTES) == cudaSuccess
+                      ? 1
+                      : -1;
 }
 
 bool spk_encode_map(CUtensorMap* map, CUtensorMapDataType dt, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems, uint32_t box_outer) {
@@ -295,7 +324,7 @@ int gemm_splitk_cluster_size(int N, int K) {
     }
     const int n_tiles = (N + SPK_N - 1) / SPK_N, num_kb = (K + SPK_K - 1) / SPK_K;
     int cs = 1;
-    while (cs * 2 <= cap && cs * 2 <= num_kb && n_tiles * cs * 2 <= 296) cs *= 2;
+    while (cs * 2 <= cap && cs * 2 <= num_kb && n_tiles * cs * 2 <= 296) cs *= 2;  // 296 = 2 resident CTAs x 148 SMs (MT = 1)
     return cs;
 }
 
@@ -323,9 +352,10 @@ int launch_gemm_splitk(const GemmArgs& g, cudaStream_t st) {
     p.gelu = g.gelu; p.round_type = g.round_type; p.lut = g.lut;
     const int cs = gemm_splitk_cluster_size(g.N, g.K);
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(n_tiles * cs, (M + SPK_M - 1) / SPK_M);
+    const int mt = M > SPK_M ? 2 : 1;
+    cfg.gridDim = dim3(n_tiles * cs, (M + mt * SPK_M - 1) / (mt * SPK_M));
     cfg.blockDim = dim3(SPK_THREADS);
-    cfg.dynamicSmemBytes = SPK_SMEM_BYTES;
+    cfg.dynamicSmemBytes = mt == 2 ? SpkCfg<2>::SMEM_BYTES : SpkCfg<1>::SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -338,7 +368,8 @@ int launch_gemm_splitk(const GemmArgs& g, cudaStream_t st) {
     cfg.numAttrs = g_pdl > 0 ? 2 : 1;
     OH_SKIP_IF(PC_GEMM_DEC);
     ProfScope ps(PC_GEMM_DEC, 2.0 * M * (double)g.N * g.K, st);
-    OH_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_splitk_kernel, ma, mw, p));
+    if (mt == 2) OH_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_splitk_kernel<2>, ma, mw, p));
+    else OH_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_splitk_kernel<1>, ma, mw, p));
     OH_COUNT_LAUNCH();
     return OH_OK;
 }
@@ -348,8 +379,8 @@ int gemm_splitk_selftest(cudaStream_t st, float* max_rel_err) {
     struct Case {
         int M, N, K, c_type, gelu;
     };
-    const Case cases[6] = {{64, 1280, 1280, DT_F32, 0}, {100, 3840, 1280, DT_F16, 0}, {37, 5120, 1280, DT_F16, 1},
-                           {128, 1280, 5120, DT_F32, 0}, {200, 1300, 264, DT_F32, 0}, {3, 384, 384, DT_F16, 1}};
+    const Case cases[7] = {{64, 1280, 1280, DT_F32, 0}, {100, 3840, 1280, DT_F16, 0}, {37, 5120, 1280, DT_F16, 1}, {128, 1280, 5120, DT_F32, 0},
+                           {200, 1300, 264, DT_F32, 0}, {3, 384, 384, DT_F16, 1}, {256, 1280, 5120, DT_F16, 1}};  // M > 128: two row tiles per CTA
     float worst = 0.0f;
     for (const Case& c : cases) {
         std::vector<__half> hA((size_t)c.M * c.K), hW((size_t)c.N * c.K);
