@@ -837,6 +837,408 @@ static int decode_pass(oh_state* st, const oh_full_params& p, bool no_timestamps
     return OH_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ beam search
+// BASELINE config 4 / A.7 "Beam".  The reference never selects it (/root/reference/src/engine/whisper.rs:243 hard-codes
+// Greedy) and the pinned upstream's candidate sampler cannot be verified offline, so this follows SURVEY.md A.5/A.7
+// as written — per live decoder the top beam_size ids of the filtered distribution, candidates ranked by
+// sum_logprobs_all, assigned to the decoders in order skipping repeats, KV cache inherited from the proposing decoder
+// — and mirrors the oracle (oracle/orc_full.cpp) decision for decision.  It is a host-driven lock-step loop over
+// beam_size decoder rows (the K9 kernel runs in "dump" mode: rules + log-softmax on the device, the distributions come
+// back to the host); items and windows are processed one after the other.  Correctness path, not a throughput path.
+namespace {
+
+struct BeamDec {
+    std::vector<TokenData> tokens;
+    int seek_delta = 100 * 30, result_len = 0, slot = 0;
+    bool has_ts = false, failed = false, completed = false;
+    double sum_logprobs_all = 0.0;
+    std::vector<float> probs, logprobs;
+};
+struct BeamCand {
+    int decoder_idx, seek_delta, result_len;
+    bool has_ts;
+    std::vector<TokenData> tokens;
+    double sum_logprobs_all;
+};
+
+// the k most probable ids, best first (ties: lower id); tid / pt / ptsum as for every sampled token (A.7)
+std::vector<TokenData> topk_on_host(const Vocab& vc, const float* probs, const float* logprobs, int k) {
+    TokenData base;
+    {
+        double sum_ts = 0.0, max_ts = 0.0;
+        for (int i = vc.token_beg; i < vc.n_vocab; ++i) {
+            sum_ts += probs[i];
+            if (max_ts < probs[i]) {
+                max_ts = probs[i];
+                base.tid = i;
+            }
+        }
+        base.pt = (float)(max_ts / (sum_ts + 1e-10));
+        base.ptsum = (float)sum_ts;
+    }
+    std::vector<int> ids(vc.n_vocab);
+    for (int i = 0; i < vc.n_vocab; ++i) ids[i] = i;
+    k = std::min(k, vc.n_vocab);
+    std::partial_sort(ids.begin(), ids.begin() + k, ids.end(), [&](int a, int b) {
+        if (logprobs[a] != logprobs[b]) return logprobs[a] > logprobs[b];
+        return a < b;
+    });
+    std::vector<TokenData> out;
+    for (int c = 0; c < k; ++c) {
+        TokenData r = base;
+        r.id = ids[c];
+        r.p = probs[r.id];
+        r.plog = logprobs[r.id];
+        if (r.id >= vc.token_beg) {
+            r.tid = r.id;
+            r.pt = r.p;
+        }
+        out.push_back(r);
+    }
+    return out;
+}
+
+int copy_self_kv(oh_state* st, int src_slot, int dst_slot) {
+    const HParams& hp = st->ctx->model->hp;
+    const size_t per_slot = (size_t)hp.n_text_ctx * hp.n_text_state * st->esz;
+    for (int l = 0; l < hp.n_text_layer; ++l) {
+        const size_t base = (size_t)l * st->max_batch * per_slot;
+        OH_CUDA_CHECK(cudaMemcpyAsync((char*)st->kself.p + base + dst_slot * per_slot, (char*)st->kself.p + base + src_slot * per_slot, per_slot,
+                                      cudaMemcpyDeviceToDevice, st->stream));
+        OH_CUDA_CHECK(cudaMemcpyAsync((char*)st->vself.p + base + dst_slot * per_slot, (char*)st->vself.p + base + src_slot * per_slot, per_slot,
+                                      cudaMemcpyDeviceToDevice, st->stream));
+    }
+    return OH_OK;
+}
+int copy_cross_kv(oh_state* st, int src_slot, int dst_slot) {
+    const HParams& hp = st->ctx->model->hp;
+    const size_t per_slot = (size_t)hp.n_audio_ctx * 2 * hp.n_text_state * st->esz;
+    for (int l = 0; l < hp.n_text_layer; ++l) {
+        const size_t base = (size_t)l * st->max_batch * per_slot;
+        OH_CUDA_CHECK(cudaMemcpyAsync((char*)st->xkv.p + base + dst_slot * per_slot, (char*)st->xkv.p + base + src_slot * per_slot, per_slot,
+                                      cudaMemcpyDeviceToDevice, st->stream));
+    }
+    return OH_OK;
+}
+
+// one window, temperature 0, nb decoders on rows / slots 0..nb-1 (cross K/V of the window already in every slot)
+int beam_pass(oh_state* st, const oh_full_params& p, bool no_timestamps, const Item& it, const std::vector<int>& prompt, int nb, PassResult& best) {
+    const Model& m = *st->ctx->model;
+    const Vocab& vc = m.vocab;
+    const int n_max = m.hp.n_text_ctx / 2 - 4;
+    const int pl = (int)prompt.size();
+    if (pl > kMaxPrompt || pl < 1) {
+        set_error("prompt too long");
+        return OH_ERR_DECODE;
+    }
+    SeqLayout lay(st->max_batch);
+    int32_t* hb = (int32_t*)st->pinned;
+    DecodeSeqState hs = seq_view(hb, lay);
+    memset(hb, 0, lay.total_words * 4);
+    for (int r = 0; r < nb; ++r) {
+        hs.slot[r] = r;
+        hs.prompt_len[r] = pl;
+        for (int i = 0; i < pl; ++i) hs.prompt[(size_t)r * kMaxPrompt + i] = prompt[i];
+        hs.seek_delta[r] = 100 * 30;
+        hs.seek[r] = it.seek;
+        hs.seek_end[r] = it.seek_end;
+    }
+    hs.active[0] = 1;
+    hs.cur_token[0] = prompt[0];
+    DecodeRules R;
+    R.n_vocab = vc.n_vocab; R.eot = vc.token_eot; R.sot = vc.token_sot; R.translate = vc.token_translate; R.transcribe = vc.token_transcribe;
+    R.solm = vc.token_solm; R.prev = vc.token_prev; R.nosp = vc.token_nosp; R.tok_not = vc.token_not; R.beg = vc.token_beg;
+    R.blank = vc.token_blank; R.n_lang = vc.num_languages();
+    R.no_timestamps = no_timestamps; R.suppress_blank = p.suppress_blank; R.single_segment = p.single_segment; R.max_tokens = p.max_tokens;
+    R.n_max = n_max;
+    R.tid0_initial = p.max_initial_ts > 0.0f ? (int)std::round(p.max_initial_ts / (30.0f / (float)m.hp.n_audio_ctx)) : -1;
+    R.temperature = 0.0f;
+    cudaStream_t s = st->stream;
+    OH_CUDA_CHECK(cudaMemcpyAsync(st->seq_dev.p, hb, lay.total_words * 4, cudaMemcpyHostToDevice, s));
+    OH_CUDA_CHECK(cudaMemcpyAsync(st->rules_dev.p, &R, sizeof R, cudaMemcpyHostToDevice, s));
+    OH_CUDA_CHECK(cudaStreamSynchronize(s));
+    const size_t ld = st->ld_logits;
+    int rc;
+    auto upload_rows = [&]() -> int {  // scalars, prompts and sampled-token ids (the kernel reads the last two ids of a row)
+        OH_CUDA_CHECK(cudaMemcpyAsync(st->seq_dev.p, hb, lay.tok_off[1] * 4, cudaMemcpyHostToDevice, s));
+        st->timings.h2d_bytes += (long long)lay.tok_off[1] * 4;
+        return OH_OK;
+    };
+    // the prompt through decoder 0 (A.5: "decode(prompt) -> process_logits(decoder0, is_initial)")
+    // (the kernel advances pos / cur_token through the prompt on the device by itself; the pinned host mirror must not be
+    // touched while an asynchronous upload of it could still be in flight, so nothing is uploaded in this phase)
+    for (int i = 0; i < pl; ++i) {
+        if ((rc = decode_step_all(st, nb, true, true))) return rc;
+        st->timings.n_decode_steps++;
+    }
+    hs.pos[0] = pl - 1;
+    hs.cur_token[0] = prompt[pl - 1];
+    std::vector<BeamDec> dec(nb);
+    dec[0].probs.resize(ld);
+    dec[0].logprobs.resize(ld);
+    OH_CUDA_CHECK(cudaMemcpyAsync(dec[0].probs.data(), st->dump_p.p, ld * 4, cudaMemcpyDeviceToHost, s));
+    OH_CUDA_CHECK(cudaMemcpyAsync(dec[0].logprobs.data(), st->dump_lp.p, ld * 4, cudaMemcpyDeviceToHost, s));
+    st->timings.d2h_bytes += (long long)ld * 8;
+    for (int j = 1; j < nb; ++j)  // "copy logits/probs/kv to the other decoders"
+        if ((rc = copy_self_kv(st, 0, j))) return rc;
+    OH_CUDA_CHECK(cudaStreamSynchronize(s));
+    for (int j = 0; j < nb; ++j) {
+        dec[j].slot = j;
+        if (j > 0) {
+            dec[j].probs = dec[0].probs;
+            dec[j].logprobs = dec[0].logprobs;
+        }
+    }
+
+    for (int i = 0; i < n_max; ++i) {
+        // ---- candidates of every live decoder, ranked
+        std::vector<BeamCand> cands;
+        for (int j = 0; j < nb; ++j) {
+            BeamDec& d = dec[j];
+            if (d.completed || d.failed) continue;
+            for (const TokenData& tok : topk_on_host(vc, d.probs.data(), d.logprobs.data(), nb)) {
+                BeamCand c{j, d.seek_delta, d.result_len, d.has_ts, d.tokens, d.sum_logprobs_all + tok.plog};
+                c.tokens.push_back(tok);
+                cands.push_back(std::move(c));
+            }
+        }
+        std::stable_sort(cands.begin(), cands.end(), [](const BeamCand& a, const BeamCand& b) {
+            if (a.sum_logprobs_all != b.sum_logprobs_all) return a.sum_logprobs_all > b.sum_logprobs_all;
+            return a.decoder_idx < b.decoder_idx;
+        });
+        auto same_tokens = [](const BeamCand& a, const BeamCand& b) {
+            if (a.tokens.size() != b.tokens.size()) return false;
+            for (size_t q = 0; q < a.tokens.size(); ++q)
+                if (a.tokens[q].id != b.tokens[q].id) return false;
+            return true;
+        };
+        std::vector<int> take(nb, -1);
+        size_t cur_c = 0;
+        for (int j = 0; j < nb; ++j) {
+            if (dec[j].completed || dec[j].failed) continue;
+            if (cur_c >= cands.size()) cur_c = 0;
+            const size_t pick = cur_c++;
+            while (cur_c < cands.size() && i > 0 && same_tokens(cands[cur_c], cands[pick])) ++cur_c;
+            take[j] = (int)pick;
+        }
+        // ---- KV caches follow the candidates: a cache moves with its slot index; only a cache that two decoders inherit
+        // (or that its owner keeps while another decoder inherits it) is copied, into the slot of a decoder that nobody follows
+        std::vector<int> old_slot(nb), new_slot(nb, -1);
+        std::vector<char> claimed(st->max_batch, 0);
+        for (int j = 0; j < nb; ++j) old_slot[j] = dec[j].slot;
+        for (int j = 0; j < nb; ++j)
+            if (take[j] >= 0 && cands[take[j]].decoder_idx == j) {
+                new_slot[j] = old_slot[j];
+                claimed[old_slot[j]] = 1;
+            }
+        for (int j = 0; j < nb; ++j)
+            if (take[j] >= 0 && new_slot[j] < 0) {
+                const int src = old_slot[cands[take[j]].decoder_idx];
+                if (!claimed[src]) {
+                    new_slot[j] = src;
+                    claimed[src] = 1;
+                }
+            }
+        for (int j = 0; j < nb; ++j)
+            if (take[j] >= 0 && new_slot[j] < 0) {
+                int f = -1;
+                for (int q = 0; q < nb; ++q)
+                    if (!claimed[old_slot[q]]) {
+                        f = old_slot[q];
+                        break;
+                    }
+                if (f < 0) {
+                    set_error("beam search: no free KV slot");
+                    return OH_ERR_DECODE;
+                }
+                if ((rc = copy_self_kv(st, old_slot[cands[take[j]].decoder_idx], f))) return rc;
+                new_slot[j] = f;
+                claimed[f] = 1;
+            }
+        {   // decoders that are finished keep distinct (unused) slots
+            int q = 0;
+            for (int j = 0; j < nb; ++j)
+                if (new_slot[j] < 0) {
+                    while (claimed[old_slot[q]]) ++q;
+                    new_slot[j] = old_slot[q];
+                    claimed[old_slot[q]] = 1;
+                }
+        }
+        for (int j = 0; j < nb; ++j) {
+            dec[j].slot = new_slot[j];
+            if (take[j] < 0) continue;
+            const BeamCand& c = cands[take[j]];
+            dec[j].tokens = c.tokens;
+            dec[j].seek_delta = c.seek_delta;
+            dec[j].has_ts = c.has_ts;
+            dec[j].result_len = c.result_len;
+            dec[j].sum_logprobs_all = c.sum_logprobs_all;
+        }
+        // ---- A.5 bookkeeping for the token each live decoder ended up with
+        bool all_done = true;
+        for (int j = 0; j < nb; ++j) {
+            BeamDec& d = dec[j];
+            if (d.completed || d.failed) continue;
+            SeqFlags f{d.has_ts ? 1 : 0, d.seek_delta, d.result_len, 0, 0};
+            apply_token_rules(f, d.tokens.back().id, i, it.seek, it.seek_end, vc.token_beg, vc.token_eot, p.max_tokens, no_timestamps, p.single_segment,
+                              n_max);
+            d.has_ts = f.has_ts != 0;
+            d.seek_delta = f.seek_delta;
+            d.result_len = f.result_len;
+            d.failed = f.failed != 0;
+            d.completed = f.completed != 0;
+            if (!d.completed && !d.failed) all_done = false;
+        }
+        if (all_done || i + 1 == n_max) break;
+        // ---- one token per live decoder
+        for (int j = 0; j < nb; ++j) {
+            const BeamDec& d = dec[j];
+            const bool live = !d.completed && !d.failed;
+            hs.active[j] = live ? 1 : 0;
+            hs.slot[j] = d.slot;
+            if (!live) continue;
+            hs.pos[j] = pl + i;
+            hs.cur_token[j] = d.tokens.back().id;
+            hs.n_gen[j] = (int)d.tokens.size();
+            hs.has_ts[j] = d.has_ts ? 1 : 0;
+            hs.seek_delta[j] = d.seek_delta;
+            hs.result_len[j] = d.result_len;
+            for (size_t q = 0; q < d.tokens.size(); ++q) hs.tok_id[(size_t)j * kMaxGen + q] = d.tokens[q].id;
+        }
+        if ((rc = upload_rows())) return rc;
+        if ((rc = decode_step_all(st, nb, true, true))) return rc;
+        st->timings.n_decode_steps++;
+        for (int j = 0; j < nb; ++j) {
+            BeamDec& d = dec[j];
+            if (d.completed || d.failed) continue;
+            d.probs.resize(ld);
+            d.logprobs.resize(ld);
+            OH_CUDA_CHECK(cudaMemcpyAsync(d.probs.data(), (float*)st->dump_p.p + (size_t)j * ld, ld * 4, cudaMemcpyDeviceToHost, s));
+            OH_CUDA_CHECK(cudaMemcpyAsync(d.logprobs.data(), (float*)st->dump_lp.p + (size_t)j * ld, ld * 4, cudaMemcpyDeviceToHost, s));
+            st->timings.d2h_bytes += (long long)ld * 8;
+        }
+        OH_CUDA_CHECK(cudaStreamSynchronize(s));
+    }
+    // ---- rank the decoders (A.5 / A.8): first best score among the ones that did not fail
+    double best_score = -INFINITY;
+    int best_id = 0;
+    std::vector<PassResult> res(nb);
+    for (int j = 0; j < nb; ++j) {
+        PassResult& r = res[j];
+        const BeamDec& d = dec[j];
+        r.tokens = d.tokens;
+        r.result_len = d.result_len;
+        r.seek_delta = d.seek_delta;
+        r.has_ts = d.has_ts;
+        r.failed = d.failed;
+        r.completed = d.completed;
+        if (r.failed) continue;
+        r.tokens.resize(std::min<size_t>(r.tokens.size(), (size_t)r.result_len));
+        sequence_score(p, r);
+        if (r.result_len > 32 && r.entropy < p.entropy_thold) {
+            r.failed = true;
+            continue;
+        }
+        if (best_score < r.score) {
+            best_score = r.score;
+            best_id = j;
+        }
+    }
+    best = res[best_id];
+    for (const BeamDec& d : dec) st->timings.n_tokens += (int)d.tokens.size();
+    return OH_OK;
+}
+
+}  // namespace
+
+// full() for strategy = BEAM_SEARCH: items one after the other, windows in order (A.5), beam_size decoder rows
+static int run_full_beam(oh_state* st, const oh_full_params& p, int batch, const std::vector<float>& temperatures, const std::vector<int>& prompt_init,
+                         bool no_timestamps, const ClipMeta& cm, std::chrono::steady_clock::time_point t_begin, long long launches0) {
+    using clk = std::chrono::steady_clock;
+    const Model& m = *st->ctx->model;
+    const Vocab& vc = m.vocab;
+    const HParams& hp = m.hp;
+    const int nb = std::max(1, p.beam_size);
+    if (nb > st->max_batch) {
+        set_error("beam search needs oh_context_params.max_batch >= beam_size (one KV-cache slot per beam)");
+        return OH_ERR_INVALID;
+    }
+    cudaStream_t s = st->stream;
+    int rc;
+    auto build_prompt = [&](const Item& it, float t_cur, std::vector<int>& prompt) {
+        prompt.clear();
+        if (!it.prompt_past.empty() && t_cur < 0.5f && p.n_max_text_ctx > 0) {
+            const int n_take = std::min(std::min(p.n_max_text_ctx, hp.n_text_ctx / 2), (int)it.prompt_past.size());
+            prompt.push_back(vc.token_prev);
+            prompt.insert(prompt.end(), it.prompt_past.end() - n_take, it.prompt_past.end());
+        }
+        prompt.insert(prompt.end(), prompt_init.begin(), prompt_init.end());
+    };
+    for (int i = 0; i < batch; ++i) {
+        Item& it = st->items[i];
+        while (!it.done) {
+            if (it.seek + 100 >= it.seek_end) {
+                it.done = true;
+                break;
+            }
+            // ---- encode the window into slot 0, then give every beam its own copy of the cross K/V
+            auto t0 = clk::now();
+            const int slot0 = 0;
+            OH_CUDA_CHECK(cudaMemcpyAsync(cm.clip_of_slot, &i, 4, cudaMemcpyHostToDevice, s));
+            OH_CUDA_CHECK(cudaMemcpyAsync(cm.seek_of_slot, &it.seek, 4, cudaMemcpyHostToDevice, s));
+            WindowGatherArgs wa;
+            wa.raw = (const float*)st->mel_raw.p;
+            wa.ld = st->mel_ld;
+            wa.n_mel = hp.n_mels;
+            wa.max_key = cm.max_key;
+            wa.n_active = cm.n_active;
+            wa.n_len = cm.n_len;
+            wa.clip_of_slot = cm.clip_of_slot;
+            wa.seek_of_slot = cm.seek_of_slot;
+            if ((rc = launch_window_gather(wa, 1, st->xin.p, st->ctx->act_type, s))) return rc == OH_ERR_CUDA ? rc : OH_ERR_ENCODE;
+            if ((rc = run_encoder(st, 1, 0, nullptr, &slot0))) return rc == OH_ERR_CUDA ? rc : OH_ERR_ENCODE;
+            for (int j = 1; j < nb; ++j)
+                if ((rc = copy_cross_kv(st, 0, j))) return rc;
+            OH_CUDA_CHECK(cudaStreamSynchronize(s));  // &i / &it.seek were read by the copies above
+            st->timings.n_windows++;
+            st->timings.encode_ms += std::chrono::duration<float, std::milli>(clk::now() - t0).count();
+            if (it.seek > 0 && it.seek + 500 >= it.seek_end) it.prompt_past.clear();  // short tail: drop the prompt (upstream behaviour)
+
+            auto t1 = clk::now();
+            PassResult best;
+            std::vector<int> prompt;
+            for (size_t ti = 0; ti < temperatures.size(); ++ti) {
+                const float t_cur = temperatures[ti];
+                build_prompt(it, t_cur, prompt);
+                if (t_cur <= 0.0f) {
+                    if ((rc = beam_pass(st, p, no_timestamps, it, prompt, nb, best))) return rc == OH_ERR_CUDA ? rc : OH_ERR_DECODE;
+                } else {
+                    // A.5: BEAM at t > 0 runs best_of decoders with sampling; best_of defaults to -1 for this strategy -> one decoder
+                    std::vector<PassRow> rows = {PassRow{i, 0, prompt}};
+                    std::vector<PassResult> res;
+                    if ((rc = decode_pass(st, p, no_timestamps, rows, t_cur, res))) return rc == OH_ERR_CUDA ? rc : OH_ERR_DECODE;
+                    best = res[0];
+                    if (!best.failed) {
+                        best.tokens.resize(std::min<size_t>(best.tokens.size(), (size_t)best.result_len));
+                        sequence_score(p, best);
+                        if (best.result_len > 32 && best.entropy < p.entropy_thold) best.failed = true;
+                    }
+                }
+                if (ti + 1 != temperatures.size() && (best.failed || best.avg_logprobs < p.logprob_thold)) {
+                    st->timings.n_fallbacks++;
+                    continue;
+                }
+                break;
+            }
+            emit_segments(m, p, it, best, prompt, (int)prompt_init.size());
+            st->timings.decode_ms += std::chrono::duration<float, std::milli>(clk::now() - t1).count();
+        }
+    }
+    st->timings.total_ms = std::chrono::duration<float, std::milli>(clk::now() - t_begin).count();
+    st->timings.n_kernel_launches = g_launch_count - launches0;
+    return OH_OK;
+}
+
 int run_full(oh_state* st, const oh_full_params& p, const float* const* pcm, const int* n, int batch, bool pcm_on_device) {
     using clk = std::chrono::steady_clock;
     const Model& m = *st->ctx->model;
@@ -846,8 +1248,8 @@ int run_full(oh_state* st, const oh_full_params& p, const float* const* pcm, con
         set_error("empty batch");
         return OH_ERR_INVALID;
     }
-    if (p.strategy != OH_SAMPLING_GREEDY) {
-        set_error("beam search is not implemented yet");
+    if (p.strategy != OH_SAMPLING_GREEDY && p.strategy != OH_SAMPLING_BEAM_SEARCH) {
+        set_error("unknown sampling strategy");
         return OH_ERR_UNSUPPORTED;
     }
     if (p.suppress_non_speech_tokens || p.offset_ms != 0 || p.duration_ms != 0) {
@@ -899,6 +1301,7 @@ int run_full(oh_state* st, const oh_full_params& p, const float* const* pcm, con
     }
 
     ClipMeta cm = clip_meta_view(st->clip_meta.p, std::max<size_t>(batch, st->max_batch));
+    if (p.strategy == OH_SAMPLING_BEAM_SEARCH) return run_full_beam(st, p, batch, temperatures, prompt_init, no_timestamps, cm, t_begin, launches0);
 
     // ------------------------------------------------------------------------------------------------------------
     // Scheduler.  Every KV-cache slot is one decoder row.  Windows are admitted to free slots (encoder pass over the

@@ -202,6 +202,7 @@ struct State {
 
 void process_logits(const Model& m, const FullParams& p, Decoder& dec, float temperature, bool is_initial);
 TokenData sample_token(const Model& m, Decoder& dec, bool best);
+std::vector<TokenData> sample_token_topk(const Model& m, Decoder& dec, int k);
 int full(State& st, const FullParams& p, const float* pcm, int n);
 int lang_id_from_code(const char* code);
 

@@ -131,6 +131,51 @@ TokenData sample_token(const Model& m, Decoder& dec, bool best) {
     return r;
 }
 
+// A.7, beam search: the k most probable ids of the filtered distribution, best first (ties: lower id first — a
+// deterministic order, the same one the product uses).  tid / pt / ptsum as in sample_token.
+// UNVERIFIED OFFLINE (SURVEY.md A.7 "I believe"): upstream versions differ in whether this takes the top-k or draws k
+// samples; the reference never selects beam search (/root/reference/src/engine/whisper.rs:243), so nothing pins it.
+std::vector<TokenData> sample_token_topk(const Model& m, Decoder& dec, int k) {
+    const Vocab& vc = m.vocab;
+    const int n_logits = vc.n_vocab;
+    const auto& probs = dec.probs;
+    const auto& logprobs = dec.logprobs;
+    TokenData base;
+    {
+        double sum_ts = 0.0, max_ts = 0.0;
+        for (int i = vc.token_beg; i < n_logits; ++i) {
+            if (probs[i] == -INFINITY) continue;
+            sum_ts += probs[i];
+            if (max_ts < probs[i]) {
+                max_ts = probs[i];
+                base.tid = i;
+            }
+        }
+        base.pt = (float)(max_ts / (sum_ts + 1e-10));
+        base.ptsum = (float)sum_ts;
+    }
+    std::vector<int> ids(n_logits);
+    for (int i = 0; i < n_logits; ++i) ids[i] = i;
+    k = std::min(k, n_logits);
+    std::partial_sort(ids.begin(), ids.begin() + k, ids.end(), [&](int a, int b) {
+        if (logprobs[a] != logprobs[b]) return logprobs[a] > logprobs[b];
+        return a < b;
+    });
+    std::vector<TokenData> out;
+    for (int c = 0; c < k; ++c) {
+        TokenData r = base;
+        r.id = ids[c];
+        r.p = probs[r.id];
+        r.plog = logprobs[r.id];
+        if (r.id >= vc.token_beg) {
+            r.tid = r.id;
+            r.pt = r.p;
+        }
+        out.push_back(r);
+    }
+    return out;
+}
+
 // A.8
 static void sequence_score(const FullParams& p, Decoder& d) {
     const int n = d.result_len;
@@ -168,7 +213,8 @@ int full(State& st, const FullParams& p, const float* pcm, int n) {
     st.window_temps.clear();
     st.window_tokens.clear();
     if (n <= 200) return -1;  // cannot reflect-pad: "failed to compute log mel spectrogram"
-    if (p.strategy != 0) return -101;  // beam search: see orc_beam (not restated yet)
+    if (p.strategy != 0 && p.strategy != 1) return -101;
+    const bool beam = p.strategy == 1;
 
     log_mel_spectrogram(m, pcm, n, st.mel, st.opt.n_threads);
 
@@ -202,7 +248,7 @@ int full(State& st, const FullParams& p, const float* pcm, int n) {
     FullParams pp = p;
     pp.no_timestamps = no_timestamps;
 
-    const int n_decoders = std::max(1, p.best_of);
+    const int n_decoders = std::max(1, beam ? std::max(p.beam_size, p.best_of) : p.best_of);
     if ((int)st.decoders.size() < n_decoders) st.decoders.resize(n_decoders);
 
     int seek = seek_start;
@@ -232,9 +278,10 @@ int full(State& st, const FullParams& p, const float* pcm, int n) {
         for (int it = 0; it < (int)temperatures.size(); ++it) {
             const float t_cur = temperatures[it];
             t_accepted = t_cur;
-            int n_decoders_cur = 1;
+            int n_decoders_cur = beam ? p.beam_size : 1;  // A.5: GREEDY t==0 ? 1 : best_of | BEAM t==0 ? beam_size : best_of
             if (t_cur > 0.0f) n_decoders_cur = p.best_of;
             n_decoders_cur = std::max(1, n_decoders_cur);
+            const bool beam_step = beam && t_cur <= 0.0f;
 
             for (int j = 0; j < n_decoders_cur; ++j) {
                 Decoder& d = st.decoders[j];
@@ -275,12 +322,74 @@ int full(State& st, const FullParams& p, const float* pcm, int n) {
 
             const int n_max = m.hp.n_text_ctx / 2 - 4;
             for (int i = 0; i < n_max; ++i) {
-                for (int j = 0; j < n_decoders_cur; ++j) {
-                    Decoder& d = st.decoders[j];
-                    if (d.completed || d.failed) continue;
-                    TokenData tok = sample_token(m, d, t_cur < 1e-6f);
-                    d.tokens.push_back(tok);
-                    d.sum_logprobs_all += tok.plog;
+                if (!beam_step) {
+                    for (int j = 0; j < n_decoders_cur; ++j) {
+                        Decoder& d = st.decoders[j];
+                        if (d.completed || d.failed) continue;
+                        TokenData tok = sample_token(m, d, t_cur < 1e-6f);
+                        d.tokens.push_back(tok);
+                        d.sum_logprobs_all += tok.plog;
+                    }
+                } else {
+                    // A.7 beam: every live decoder proposes its top beam_size continuations; all candidates are ranked by
+                    // sum_logprobs_all (ties: proposing decoder, then rank inside its proposal) and handed to the live
+                    // decoders in order, skipping a candidate whose token sequence equals the previous pick (i > 0);
+                    // a decoder that takes a candidate of another decoder also takes that decoder's KV cache
+                    struct Cand {
+                        int decoder_idx, seek_delta;
+                        bool has_ts;
+                        int result_len;
+                        std::vector<TokenData> tokens;
+                        double sum_logprobs_all;
+                    };
+                    std::vector<Cand> cands;
+                    for (int j = 0; j < n_decoders_cur; ++j) {
+                        Decoder& d = st.decoders[j];
+                        if (d.completed || d.failed) continue;
+                        for (const TokenData& tok : sample_token_topk(m, d, p.beam_size)) {
+                            Cand c{j, d.seek_delta, d.has_ts, d.result_len, d.tokens, d.sum_logprobs_all + tok.plog};
+                            c.tokens.push_back(tok);
+                            cands.push_back(std::move(c));
+                        }
+                    }
+                    std::stable_sort(cands.begin(), cands.end(), [](const Cand& a, const Cand& b) {
+                        if (a.sum_logprobs_all != b.sum_logprobs_all) return a.sum_logprobs_all > b.sum_logprobs_all;
+                        return a.decoder_idx < b.decoder_idx;
+                    });
+                    auto same_tokens = [](const Cand& a, const Cand& b) {
+                        if (a.tokens.size() != b.tokens.size()) return false;
+                        for (size_t q = 0; q < a.tokens.size(); ++q)
+                            if (a.tokens[q].id != b.tokens[q].id) return false;
+                        return true;
+                    };
+                    std::vector<KVCache> kv_src(n_decoders_cur);
+                    std::vector<char> kv_saved(n_decoders_cur, 0);
+                    std::vector<int> take(n_decoders_cur, -1);
+                    size_t cur_c = 0;
+                    for (int j = 0; j < n_decoders_cur; ++j) {
+                        Decoder& d = st.decoders[j];
+                        if (d.completed || d.failed) continue;
+                        if (cur_c >= cands.size()) cur_c = 0;
+                        const size_t pick = cur_c++;
+                        while (cur_c < cands.size() && i > 0 && same_tokens(cands[cur_c], cands[pick])) ++cur_c;
+                        take[j] = (int)pick;
+                    }
+                    for (int j = 0; j < n_decoders_cur; ++j)  // caches that another decoder is about to inherit: keep a copy
+                        if (take[j] >= 0 && cands[take[j]].decoder_idx != j && !kv_saved[cands[take[j]].decoder_idx]) {
+                            kv_src[cands[take[j]].decoder_idx] = st.decoders[cands[take[j]].decoder_idx].kv;
+                            kv_saved[cands[take[j]].decoder_idx] = 1;
+                        }
+                    for (int j = 0; j < n_decoders_cur; ++j) {
+                        if (take[j] < 0) continue;
+                        Decoder& d = st.decoders[j];
+                        const Cand& c = cands[take[j]];
+                        if (c.decoder_idx != j) d.kv = kv_src[c.decoder_idx];
+                        d.tokens = c.tokens;
+                        d.seek_delta = c.seek_delta;
+                        d.has_ts = c.has_ts;
+                        d.result_len = c.result_len;
+                        d.sum_logprobs_all = c.sum_logprobs_all;
+                    }
                 }
                 for (int j = 0; j < n_decoders_cur; ++j) {
                     Decoder& d = st.decoders[j];

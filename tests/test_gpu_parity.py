@@ -192,9 +192,41 @@ def test_full_edge_cases(st32):
     assert st32.full(np.zeros(32000, np.float32), p) == 0                           # the engine's benchmark() input (whisper.rs:343-353)
     assert st32.full_batch([synth.audio(3, 17600), synth.audio(2, 100), synth.audio(4, 20000)], p) == 0
     assert st32.segments(1) == []
-    q = default_full_params()
-    q.strategy = 1
-    assert st32.full(synth.audio(1, 32000), q) == -101                               # beam search: not implemented yet
+    q = default_full_params(1)
+    q.beam_size = 9                                                                  # more beams than KV slots (max_batch 8)
+    assert st32.full(synth.audio(1, 32000), q) != 0
+
+
+def test_beam_search_matches_oracle(st32, micro_oracle):
+    """BASELINE config 4's decode policy (A.5 / A.7 beam; the reference itself never selects it): f32 mode, token ids and
+    segment times identical to the oracle's beam search, with and without the temperature ladder (fresh states on both
+    sides so that the t > 0 draws see the same mt19937 stream); one beam == greedy."""
+    ctx = st32.ctx
+    n_fb = 0
+    for seed, n in ((1, 480000), (3, 123456)):
+        clip = synth.audio(seed, n)
+        for inc in (0.0, 0.2):
+            stf, of = lib.State(ctx), O.OracleState(micro_oracle, gelu=O.GELU_TANH, act_round=O.ACT_NONE)
+            p = default_full_params(1)
+            p.temperature_inc = inc
+            assert stf.full(clip, p) == 0
+            assert of.full(clip, p) == 0
+            assert len(of.segments()) > 0
+            assert _flat(stf.segments(0)) == _flat(of.segments()), (seed, inc)
+            assert stf.timings().n_fallbacks == of.stats()["n_fallbacks"]
+            n_fb += of.stats()["n_fallbacks"]
+            stf.close()
+            of.close()
+    g = default_full_params()
+    g.temperature_inc = 0.0
+    b1 = default_full_params(1)
+    b1.temperature_inc = 0.0
+    b1.beam_size = 1
+    clip = synth.audio(2)
+    assert st32.full(clip, g) == 0
+    greedy = _flat(st32.segments(0))
+    assert st32.full(clip, b1) == 0
+    assert _flat(st32.segments(0)) == greedy
 
 
 # ---------------------------------------------------------------------------------------------- 16-bit tensor-core modes

@@ -223,3 +223,28 @@ def test_full_segments_are_well_formed(micro_oracle, clip1):
     assert stats["n_encode"] == len(stats["seeks"]) >= 1 and stats["seeks"][0] == 0
     assert all(b > a for a, b in zip(stats["seeks"], stats["seeks"][1:]))
     st.close()
+
+
+def test_beam_search_restatement(micro_oracle, clip1):
+    """A.5 / A.7 beam: one beam is greedy decoding; five beams are deterministic, well-formed, and never score below the
+    greedy sequence they contain as a candidate at step 0 (unpinned by the reference, which never selects beam search)."""
+    ost = O.OracleState(micro_oracle, gelu=O.GELU_TANH, act_round=O.ACT_NONE)
+    g = default_full_params()
+    g.temperature_inc = 0.0
+    assert ost.full(clip1, g) == 0
+    greedy = [(s["t0"], s["t1"], s["tokens"]) for s in ost.segments()]
+    b = default_full_params(1)
+    b.temperature_inc = 0.0
+    b.beam_size = 1
+    assert ost.full(clip1, b) == 0
+    assert [(s["t0"], s["t1"], s["tokens"]) for s in ost.segments()] == greedy
+    b.beam_size = 5
+    assert ost.full(clip1, b) == 0
+    first = [(s["t0"], s["t1"], s["tokens"]) for s in ost.segments()]
+    assert ost.full(clip1, b) == 0
+    assert [(s["t0"], s["t1"], s["tokens"]) for s in ost.segments()] == first and len(first) > 0
+    last = -1
+    for t0, t1, toks in first:
+        assert t0 >= 0 and t1 >= last
+        last = t1
+    ost.close()
