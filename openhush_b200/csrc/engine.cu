@@ -842,7 +842,7 @@ static int decode_pass(oh_state* st, const oh_full_params& p, bool no_timestamps
 // Greedy) and the pinned upstream's candidate sampler cannot be verified offline, so this follows SURVEY.md A.5/A.7
 // as written — per live decoder the top beam_size ids of the filtered distribution, candidates ranked by
 // sum_logprobs_all, assigned to the decoders in order skipping repeats, KV cache inherited from the proposing decoder
-// — and mirrors the oracle (oracle/orc_full.cpp) decision for decision.  It is a host-driven lock-step loop over
+// — decision for decision the same procedure the test oracle restates.  It is a host-driven lock-step loop over
 // beam_size decoder rows (the K9 kernel runs in "dump" mode: rules + log-softmax on the device, the distributions come
 // back to the host); items and windows are processed one after the other.  Correctness path, not a throughput path.
 namespace {
