@@ -227,6 +227,17 @@ def test_beam_search_matches_oracle(st32, micro_oracle):
     greedy = _flat(st32.segments(0))
     assert st32.full(clip, b1) == 0
     assert _flat(st32.segments(0)) == greedy
+    # the committed beam vectors (tests/golden/oracle_micro_beam.npz), through one batched call
+    gb = np.load(os.path.join(GOLD, "oracle_micro_beam.npz"))
+    pb = default_full_params(1)
+    pb.temperature_inc = 0.0
+    pb.beam_size = int(gb["beam_size"])
+    clips = [synth.audio(int(s), int(n)) for s, n in zip(gb["seeds"], gb["n_samples"])]
+    assert st32.full_batch(clips, pb) == 0
+    for k in range(len(clips)):
+        toks, times = _flat(st32.segments(k))
+        assert toks == list(gb["tokens"][gb["tok_off"][k]:gb["tok_off"][k + 1]]), k
+        assert times == list(gb["times"][2 * gb["seg_off"][k]:2 * gb["seg_off"][k + 1]]), k
 
 
 # ---------------------------------------------------------------------------------------------- 16-bit tensor-core modes

@@ -248,3 +248,18 @@ def test_beam_search_restatement(micro_oracle, clip1):
         assert t0 >= 0 and t1 >= last
         last = t1
     ost.close()
+
+
+def test_beam_golden(micro_oracle):
+    """The frozen beam-search outputs (tests/golden/make_oracle_beam_golden.py): later edits of the oracle cannot drift."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "oracle_micro_beam.npz"))
+    ost = O.OracleState(micro_oracle, gelu=O.GELU_TANH, act_round=O.ACT_NONE)
+    p = default_full_params(1)
+    p.temperature_inc = 0.0
+    p.beam_size = int(g["beam_size"])
+    for k, (seed, n) in enumerate(zip(g["seeds"], g["n_samples"])):
+        assert ost.full(synth.audio(int(seed), int(n)), p) == 0
+        segs = ost.segments()
+        assert [t for s in segs for t in s["tokens"]] == list(g["tokens"][g["tok_off"][k]:g["tok_off"][k + 1]]), k
+        assert [x for s in segs for x in (s["t0"], s["t1"])] == list(g["times"][2 * g["seg_off"][k]:2 * g["seg_off"][k + 1]]), k
+    ost.close()
