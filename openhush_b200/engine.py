@@ -336,3 +336,54 @@ def merge_records(per_rank_records, world: int):
                 k += n_tok
             out[item * world + r] = segs
     return out
+
+
+class WorkerPool:
+    """One worker per GPU over ONE shared job queue (the documented-but-unimplemented multi-GPU design of the
+    reference: `config.gpu.devices`, /root/reference/src/config.rs:921-929, workers as in queue/worker.rs:255-267).
+    Jobs are independent transcribe() calls, so a worker that finishes early simply pulls the next job (dynamic load
+    balance: decode length is data-dependent); results carry (sequence_id, chunk_id) and go to one result queue, where a
+    TranscriptionTracker restores the order.  Nothing is exchanged between GPUs.
+
+    `engines`: one engine per device (anything with .transcribe(AudioBuffer)); None entries model a worker whose engine
+    failed to load — it still answers every job with an empty text, like the reference's worker."""
+
+    def __init__(self, engines):
+        import queue
+        import threading
+        self.jobs: "queue.Queue" = queue.Queue()
+        self.results: "queue.Queue" = queue.Queue()
+        self.workers = [TranscriptionWorker(e) for e in engines]
+        self.jobs_done = [0] * len(engines)
+        self._threads = [threading.Thread(target=self._run, args=(i,), daemon=True) for i in range(len(engines))]
+        for t in self._threads:
+            t.start()
+
+    def _run(self, i: int):
+        while True:
+            job = self.jobs.get()
+            if job is None:  # WorkerCommand::Shutdown
+                return
+            self.results.put(self.workers[i].process_job(job))
+            self.jobs_done[i] += 1
+
+    def submit(self, job: TranscriptionJob):
+        self.jobs.put(job)
+
+    def drain(self, n: int, tracker=None, timeout: float = 600.0):
+        """Collects n results; with a tracker they come back in its hand-out order (streaming or ordered)."""
+        out = []
+        for _ in range(n):
+            r = self.results.get(timeout=timeout)
+            if tracker is None:
+                out.append(r)
+            else:
+                tracker.add_result(r)
+                out.extend(tracker.take_ready())
+        return out
+
+    def shutdown(self):
+        for _ in self._threads:
+            self.jobs.put(None)
+        for t in self._threads:
+            t.join()

@@ -120,3 +120,34 @@ def test_merge_timed_segments():
     assert merge_timed_segments([b, a]) == [(0, 250, "a"), (250, 2900, " b"), (3010, 3400, "c")]
     # overlapping capture: chunk 1 starts 0.5 s before chunk 0 ends
     assert merge_timed_segments([a, b], chunk_offsets_cs={0: 0, 1: 2950})[-1] == (2960, 3350, "c")
+
+
+def test_worker_pool_shared_queue_and_ordered_handout():
+    """one worker per GPU pulling from one job queue; the tracker restores the order.  Engines are stubs
+    here (the GPU engines are exercised by the -m gpu tests); one worker has no engine and still answers."""
+    import time
+
+    import numpy as np
+
+    from openhush_b200.engine import AudioBuffer, TranscriptionJob, TranscriptionResult, WorkerPool
+
+    class StubEngine:
+        def __init__(self, delay):
+            self.delay = delay
+
+        def transcribe(self, audio):
+            time.sleep(self.delay)
+            return TranscriptionResult(f"n={len(audio.samples)}", "en", 1, [(0, 10, "x")])
+
+    pool = WorkerPool([StubEngine(0.02), StubEngine(0.001), None])
+    tracker = TranscriptionTracker.new_ordered()
+    n = 24
+    for seq in range(n):
+        tracker.add_pending_with_config(seq, 0, 0, 0, BackpressureStrategy.WARN)
+        pool.submit(TranscriptionJob(AudioBuffer(np.zeros(16000 + seq, np.float32), 16000), seq))
+    got = pool.drain(n, tracker)
+    pool.shutdown()
+    assert [r.sequence_id for r in got] == list(range(n))               # ordered hand-out despite out-of-order completion
+    assert sum(pool.jobs_done) == n                                      # every job was taken exactly once
+    assert all(r.text == "" or r.text == f"n={16000 + r.sequence_id}" for r in got)   # an engine-less worker answers with empty text
+    assert all(r.segments == [(0, 10, "x")] for r in got if r.text)
