@@ -139,6 +139,64 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def ncu_traffic(kernel_substr: str):
+    """DRAM bytes per launch of `kernel_substr` from the newest committed `ncu --set full` extract under profiles/ that has
+    it (dram__bytes_read.sum + dram__bytes_write.sum, Mbyte columns), with the launch's grid size; (None, None, None) if absent."""
+    import csv
+    import glob
+    best = (None, None, None)
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full_*.csv"))):
+        try:
+            with open(path, newline="") as f:
+                rows = list(csv.reader(f))
+            hdr = rows[0]
+            i_name, i_grid = hdr.index("Kernel Name"), hdr.index("launch__grid_size")
+            i_rd, i_wr = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+            for r in rows[2:]:
+                if len(r) > max(i_rd, i_wr) and kernel_substr in r[i_name]:
+                    best = ((float(r[i_rd]) + float(r[i_wr])) * 1e6, int(float(r[i_grid])), os.path.relpath(path, ROOT))
+        except (OSError, ValueError, IndexError):
+            continue
+    return best
+
+
+def set_knobs():
+    """Every OH_* environment knob that is set (they select kernels / scheduler variants; the defaults are the product)."""
+    knobs = {k: v for k, v in os.environ.items() if k.startswith("OH_") and k not in ("OH_MODEL_CACHE", "OH_REF_BUDGET_S")}
+    if "OH_SKIP_CATS" in knobs:
+        raise SystemExit("bench.py: OH_SKIP_CATS is set — that switch skips kernels (diagnostic builds only); refusing to report a number")
+    return knobs
+
+
+def parity_check(st, ctx, om, ost, clip, p):
+    """One window of the benchmarked configuration against the oracle (ggml-faithful mode: f16 activations at mat-muls,
+    f16 GELU table): the free-running token sequences, and teacher-forced agreement of every greedy pick along the oracle's
+    own sequence (SURVEY.md A.6/A.7 applied to the product's logits).  The oracle's full() must already have run on `clip`."""
+    toks = ost.window_tokens(0)
+    assert st.full(clip, p) == 0
+    ours = [t for s in st.segments(0) for t in s["tokens"]]
+    ref = [t for s in ost.segments() for t in s["tokens"]]
+    same_prefix = 0
+    for a, b in zip(ours, ref):
+        if a != b:
+            break
+        same_prefix += 1
+    mel, _ = ost.pcm_to_mel(clip)
+    st.encode(np.ascontiguousarray(mel[None, :, :3000]))
+    prompt = [om.sot, om.sot + 1, om.transcribe] if om.n_vocab >= 51865 else [om.sot]
+    agree, has_ts, seek_delta = 0, False, 3000
+    logits = st.decode(np.array([prompt], np.int32), 0)[0]
+    for i, t in enumerate(toks):
+        r = om.process_logits(logits, tokens_cur=toks[:i], has_ts=has_ts, seek_delta=seek_delta)
+        agree += int(r["id"] == t)
+        if t > om.beg:
+            has_ts, seek_delta = True, 2 * (t - om.beg)
+        if i + 1 < len(toks):
+            logits = st.decode(np.array([[t]], np.int32), len(prompt) + i)[0]
+    return dict(agree=agree, n=len(toks), free_run_identical=(ours == ref), free_run_common_prefix=same_prefix, free_run_len=len(ref),
+                oracle_mode="gelu=f16-table, activations rounded to f16 at mat-muls (ggml-faithful)", window="window 0 of the recording")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -147,9 +205,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--arch", default="large-v3")
     ap.add_argument("--batch", type=int, default=512, help="30 s windows (independent transcription jobs) per GPU per step")
-    ap.add_argument("--slots", type=int, default=128, help="decoder rows / KV-cache slots resident per GPU (oh_context_params.max_batch)")
+    ap.add_argument("--slots", type=int, default=256, help="decoder rows resident per GPU (oh_context_params.max_batch)")
     ap.add_argument("--compute", default="f16", choices=["f16", "bf16", "f32"])
+    ap.add_argument("--strategy", default="greedy", choices=["greedy", "beam"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the strong-scaling and single-call latency legs")
+    ap.add_argument("--blocking", action="store_true", help="one blocking oh_full_batch per step (rows drain between steps) instead of the stream API")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -166,6 +227,7 @@ def main():
     from openhush_b200 import COMPUTE_BF16, COMPUTE_F16, COMPUTE_F32, default_full_params, lib, synth
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    knobs = set_knobs()
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -185,15 +247,15 @@ def main():
     S = min(args.slots, B)
     ctx = lib.Context(path, compute_type=ctype, gpu_device=local_rank, max_batch=S)
     st = lib.State(ctx)
-    stream = torch.cuda.Stream()  # a real (non-default) stream: the library launches on it and the timing events are recorded on it
+    stream = torch.cuda.Stream()  # a real (non-default) stream: the library's decode stream, and the one the timing events are recorded on
     torch.cuda.set_stream(stream)
     st.set_stream(stream.cuda_stream)
-    p = default_full_params()
+    beam = args.strategy == "beam"
+    p = default_full_params(1 if beam else 0)
     p.temperature_inc = 0.0  # no temperature fallback in throughput runs (both arms)
 
     # windows of this rank: window set q holds recording windows [(q*world + rank)*B, +B).  Every warm-up step uses set 0 and
     # timed step k uses set k+1 (never a set the library has seen before), which keeps the pinned host copy at (K+1) sets
-    # (3.9 GB per rank at the defaults) instead of W+K
     n_sets = K + 1
     host = torch.empty((n_sets * B, N_SAMPLES), dtype=torch.float32, pin_memory=True)
     hv = host.numpy()
@@ -208,61 +270,83 @@ def main():
     def set_of(s):  # step index (0..W+K-1) -> window set
         return 0 if s < W else s - W + 1
 
-    def step_device(s):
-        base = dev.data_ptr() + set_of(s) * B * N_SAMPLES * 4
-        rc = st.full_batch_ptrs([base + i * N_SAMPLES * 4 for i in range(B)], ns, p, on_device=True)
-        assert rc == 0, (rc, st.lib.oh_last_error())
+    def ptrs(base_ptr, s):
+        base = base_ptr + set_of(s) * B * N_SAMPLES * 4
+        return [base + i * N_SAMPLES * 4 for i in range(B)]
 
-    def step_host(s):
-        base = host.data_ptr() + set_of(s) * B * N_SAMPLES * 4
-        rc = st.full_batch_ptrs([base + i * N_SAMPLES * 4 for i in range(B)], ns, p, on_device=False)
-        assert rc == 0, (rc, st.lib.oh_last_error())
-        return st.pack_records()  # the step's result: segment records (token ids, t0/t1) read back to the host
+    # One step = B windows submitted as one ticket.  With the stream API the next step's ticket is submitted before this
+    # step's is waited for, so the decoder rows stay full across steps (continuous batching); every window of all K steps
+    # completes inside the timed region, the final drain included.
+    def run_steps(first, last, on_device, collect=None):
+        base_ptr = dev.data_ptr() if on_device else host.data_ptr()
+        if args.blocking or beam:
+            for s in range(first, last):
+                rc = st.full_batch_ptrs(ptrs(base_ptr, s), ns, p, on_device=on_device)
+                assert rc == 0, (rc, st.lib.oh_last_error())
+                if collect:
+                    collect(s)
+            return
+        ticket = st.stream_submit(ptrs(base_ptr, first), ns, p, on_device=on_device)
+        for s in range(first, last):
+            nxt = st.stream_submit(ptrs(base_ptr, s + 1), ns, p, on_device=on_device) if s + 1 < last else None
+            rc = st.stream_wait(ticket)
+            assert rc == 0, (rc, st.lib.oh_last_error())
+            if collect:
+                collect(s)
+            ticket = nxt
 
     # ---------------- kernel-only value: inputs resident in HBM ----------------
-    for s in range(W):
-        step_device(s)
+    run_steps(0, W, True)
     sampler = ClockSampler(local_rank)
     barrier()
     torch.cuda.synchronize()
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches = tokens = windows = dsteps = psteps = rsteps = 0
-    e0.record(stream)
-    for s in range(W, W + K):
-        step_device(s)
+    cnt = dict(launches=0, tokens=0, windows=0, dsteps=0, psteps=0, rsteps=0, asteps=0)
+    last = {}
+
+    def collect_counters(s):
         t = st.timings()
-        launches += t.n_kernel_launches
-        tokens += t.n_tokens
-        windows += t.n_windows
-        dsteps += t.n_decode_steps
-        psteps += t.n_prompt_steps
-        rsteps += t.n_row_steps
+        cnt["launches"] += t.n_kernel_launches
+        cnt["tokens"] += t.n_tokens
+        cnt["windows"] += t.n_windows
+        cnt["dsteps"] += t.n_decode_steps
+        cnt["psteps"] += t.n_prompt_steps
+        cnt["rsteps"] += t.n_row_steps
+        cnt["asteps"] += t.n_armed_row_steps
+        last.update(mel_ms=t.mel_ms, encode_issue_ms=t.encode_ms, decode_ms=t.decode_ms, total_ms=t.total_ms)
+
+    e0.record(stream)
+    run_steps(W, W + K, True, collect_counters)
     e1.record(stream)
     barrier()
     torch.cuda.synchronize()
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
-    last = dict(mel_ms=t.mel_ms, encode_ms=t.encode_ms, decode_ms=t.decode_ms, total_ms=t.total_ms)
 
-    # ---------------- end to end: host PCM through the C ABI ----------------
-    step_host(0)
+    # ---------------- end to end: host PCM through the C ABI, records read back ----------------
+    recs = {}
+
+    def collect_e2e(s):
+        tt = st.timings()
+        recs["h2d"] = recs.get("h2d", 0) + tt.h2d_bytes
+        recs["d2h"] = recs.get("d2h", 0) + tt.d2h_bytes
+        recs["rec"] = st.pack_records()  # the step's result: segment records (token ids, t0/t1) read back to the host
+
+    run_steps(0, 1, False)
     barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    h2d = d2h = 0
-    for s in range(W, W + K):
-        rec = step_host(s)
-        tt = st.timings()
-        h2d += tt.h2d_bytes
-        d2h += tt.d2h_bytes
+    run_steps(W, W + K, False, collect_e2e)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
+    h2d, d2h, rec = recs["h2d"], recs["d2h"], recs["rec"]
 
     # ---------------- per-kernel profile of one step (events around every launch; graphs bypassed) ----------------
     st.profile(True)
-    step_device(W)
+    rc = st.full_batch_ptrs(ptrs(dev.data_ptr(), W), ns, p, on_device=True)
+    assert rc == 0
     rep = st.profile_report()
     st.profile(False)
     # exact-bytes measurement of the decode attention: a stage decode step with every row active
@@ -273,22 +357,69 @@ def main():
     rep_dec = st.profile_report()
     st.profile(False)
 
+    # ---------------- extras: config 3 as stated (strong scaling over a fixed 1200-window recording), single-call latency --------
+    extras = {}
+    if not args.no_extras and not beam:
+        n_rec = 1200  # 10 h of audio
+        def strong_leg(n_ranks, r):
+            mine = list(range(r, n_rec, n_ranks))
+            buf = torch.empty((len(mine), N_SAMPLES), dtype=torch.float32, pin_memory=True)
+            bv = buf.numpy()
+            for i, w in enumerate(mine):
+                gen.ohgen_audio(100000 + w + 1, N_SAMPLES, bv[i].ctypes.data)
+            dbuf = buf.cuda()
+            pp = [dbuf.data_ptr() + i * N_SAMPLES * 4 for i in range(len(mine))]
+            barrier()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            rc = st.full_batch_ptrs(pp, [N_SAMPLES] * len(mine), p, on_device=True)
+            assert rc == 0, (rc, st.lib.oh_last_error())
+            b.record(stream)
+            torch.cuda.synchronize()
+            return a.elapsed_time(b)
+        t_n = strong_leg(world, rank)
+        t_1 = strong_leg(1, 0) if world > 1 else t_n  # the same recording on one GPU (every rank runs it, the max is taken)
+        extras["strong_ms"] = (t_n, t_1)
+        # single-call latency: the reference's actual usage, one clip per transcribe() on a max_batch = 1 context
+        if rank == 0:
+            ctx1 = lib.Context(path, compute_type=ctype, gpu_device=local_rank, max_batch=1)
+            st1 = lib.State(ctx1)
+            clip = hv[0]
+            for _ in range(2):
+                assert st1.full(clip, p) == 0
+            lat = []
+            for _ in range(5):
+                t0 = time.perf_counter()
+                assert st1.full(clip, p) == 0
+                lat.append(time.perf_counter() - t0)
+            n_tok1 = sum(len(sg["tokens"]) for sg in st1.segments(0))
+            extras["latency_b1"] = dict(ms=1000.0 * statistics.median(lat), rtf=statistics.median(lat) / WINDOW_S, tokens=n_tok1,
+                                        what="one 30 s clip through oh_full (host PCM in, segments out), max_batch = 1, median of 5")
+            st1.close()
+            ctx1.close()
+        barrier()
+
     # ---------------- reduce over ranks ----------------
     if world > 1:
-        tms = torch.tensor([ms, e2e_s * 1000.0], device="cuda", dtype=torch.float64)
+        tms = torch.tensor([ms, e2e_s * 1000.0] + list(extras.get("strong_ms", (0.0, 0.0))), device="cuda", dtype=torch.float64)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        cnt = torch.tensor([launches, tokens, windows, h2d, d2h], device="cuda", dtype=torch.float64)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        c = torch.tensor([cnt[k] for k in ("launches", "tokens", "windows", "dsteps", "psteps", "rsteps", "asteps")] + [h2d, d2h],
+                         device="cuda", dtype=torch.float64)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
         ms, e2e_ms = float(tms[0]), float(tms[1])
-        launches, tokens, windows = int(cnt[0]), int(cnt[1]), int(cnt[2])
-        h2d, d2h = int(cnt[3]) // world, int(cnt[4]) // world
+        if "strong_ms" in extras:
+            extras["strong_ms"] = (float(tms[2]), float(tms[3]))
+        for i, k in enumerate(("launches", "tokens", "windows", "dsteps", "psteps", "rsteps", "asteps")):
+            cnt[k] = int(c[i])
+        h2d, d2h = int(c[7]) // world, int(c[8]) // world
         # the path's only collective: gather of the fixed-size segment records (off the math path)
-        recs = torch.from_numpy(rec.astype(np.int64)).cuda()
-        n = torch.tensor([recs.numel()], device="cuda")
+        recs_t = torch.from_numpy(rec.astype(np.int64)).cuda()
+        n = torch.tensor([recs_t.numel()], device="cuda")
         sizes = [torch.zeros_like(n) for _ in range(world)]
         dist.all_gather(sizes, n)
         pad = torch.zeros(int(max(int(x) for x in sizes)), dtype=torch.int64, device="cuda")
-        pad[:recs.numel()] = recs
+        pad[:recs_t.numel()] = recs_t
         allrec = [torch.zeros_like(pad) for _ in range(world)]
         dist.all_gather(allrec, pad)
     else:
@@ -306,9 +437,6 @@ def main():
         # launches are long enough to be timed (>= 50 us) — the ncu launch list in profiles/ has the same ordering
         timed = [r for r in rep_sorted if r["total_ms"] / r["launches"] >= 0.05]
         top = (timed or rep_sorted)[0]
-        # DRAM traffic per decoder row and launch of the cross-attention kernel from the committed `ncu --set full` capture
-        # (profiles/r01_ncu_full_decode_kernels.csv: 983.39 MB read + 4.70 MB written for 128 rows; algorithmic 983.04 MB)
-        XATTN_TRAFFIC_PER_ROW = (983.390208e6 + 4.695296e6) / 128
         if top["name"] in ("gemm_encoder", "gemm_decoder", "attention_encoder"):
             achieved = top["work"] / (top["total_ms"] / 1e3) / 1e12
             roof = dict(kernel=top["name"], bound="tensor", achieved=achieved, peak=pk["tf_sustained"], unit="TFLOP/s", frac=achieved / pk["tf_sustained"],
@@ -317,9 +445,14 @@ def main():
         else:
             src = next((r for r in rep_dec if r["name"] == top["name"]), top)
             achieved = src["work"] / (src["total_ms"] / 1e3) / 1e9
-            traffic = XATTN_TRAFFIC_PER_ROW * S if (top["name"] == "cross_attention_decode" and args.arch == "large-v3" and args.compute != "f32") else None
+            traffic = traffic_src = None
+            if top["name"] == "cross_attention_decode" and args.arch == "large-v3" and args.compute != "f32":
+                # DRAM bytes of one launch from the committed `ncu --set full` extract, scaled from its row count to this run's
+                t_bytes, t_grid, traffic_src = ncu_traffic("cross_attention_decode_bulk_kernel")
+                if t_bytes:
+                    traffic = t_bytes / (t_grid / 20.0) * S  # grid = 20 heads x rows
             roof = dict(kernel=top["name"], bound="hbm", achieved=achieved, peak=pk["hbm"], unit="GB/s", frac=achieved / pk["hbm"], traffic=traffic,
-                        algorithmic_bytes_per_launch=src["work"] / src["launches"],
+                        traffic_source=traffic_src, algorithmic_bytes_per_launch=src["work"] / src["launches"],
                         peak_source=pk["src"], share_of_step=top["total_ms"] / tot_ms, avg_launch_ms=src["total_ms"] / src["launches"],
                         launches=src["launches"], measured_on="decode steps with every row active (stage API), CUDA events on the launching stream")
         kernels = {r["name"]: dict(ms=round(r["total_ms"], 3), launches=r["launches"], share=round(r["total_ms"] / tot_ms, 4),
@@ -329,19 +462,32 @@ def main():
                                    rate_unit=("TFLOP/s" if r["name"].startswith("gemm") or r["name"] == "attention_encoder" else "GB/s"))
                    for r in rep_sorted}
         xattn = next((r for r in rep_dec if r["name"] == "cross_attention_decode"), None)
+        rs = cnt["rsteps"]
         line = dict(metric="audio_seconds_per_second", value=value, unit="audio-s/s", n_gpus=world, steps=K, warmup=W, ms_per_step=ms / K,
                     higher_is_better=True, scaling="weak", vs_baseline=None, dtype=args.compute, data="synthetic",
-                    config=dict(workload=f"whisper {args.arch} batched greedy (temperature_inc=0), independent 30 s windows of a synthetic recording, "
-                                         f"{B} windows per GPU per step over {S} resident decoder rows", arch=args.arch, windows_per_gpu_per_step=B,
-                                decoder_rows_per_gpu=S, window_seconds=WINDOW_S,
+                    config=dict(workload=f"whisper {args.arch} batched {'beam-5' if beam else 'greedy'} (temperature_inc=0), independent 30 s windows of a synthetic "
+                                         f"recording, {B} windows per GPU per step over {S} resident decoder rows"
+                                         + ("" if (args.blocking or beam) else ", steps pipelined through the stream API (continuous batching)"),
+                                arch=args.arch, windows_per_gpu_per_step=B, decoder_rows_per_gpu=S, window_seconds=WINDOW_S, strategy=args.strategy,
+                                api="oh_full_batch (blocking)" if (args.blocking or beam) else "oh_stream_submit / oh_stream_wait",
                                 weights="random-init, ggml-<arch>.bin format, seed 1234", l2="per-step inputs and weights exceed the 126 MB L2",
-                                gemm_backend=st.gemm_backend()),
+                                gemm_backend=st.gemm_backend(), knobs=knobs),
                     clocks=clocks,
                     e2e=dict(value=e2e_val, unit="audio-s/s", h2d_bytes_per_step=h2d // K, d2h_bytes_per_step=d2h // K, ms_per_step=e2e_ms / K),
-                    gpu_launches=launches, roofline=roof, tokens_per_s=tokens / (ms / 1000.0), windows=windows, decode_steps=dsteps,
-                    row_steps=dict(total=rsteps, sampling=tokens, prompt_feed=psteps, idle=rsteps - tokens - psteps),
+                    gpu_launches=cnt["launches"], roofline=roof, tokens_per_s=cnt["tokens"] / (ms / 1000.0), windows=cnt["windows"],
+                    decode_steps=cnt["dsteps"],
+                    row_steps=dict(total=rs, sampling=cnt["tokens"], prompt_feed=cnt["psteps"], idle=rs - cnt["tokens"] - cnt["psteps"],
+                                   no_window=rs - cnt["asteps"], idle_frac=round((rs - cnt["tokens"] - cnt["psteps"]) / max(rs, 1), 4)),
                     last_step_ms=last, kernels=kernels,
                     cross_attention_decode_gbs=(xattn["work"] / (xattn["total_ms"] / 1e3) / 1e9 if xattn else None))
+        if "strong_ms" in extras:
+            t_n, t_1 = extras["strong_ms"]
+            line["strong_1200"] = dict(value=WINDOW_S * 1200 / (t_n / 1e3), unit="audio-s/s", ms=t_n, n1_ms=t_1,
+                                       efficiency_vs_n1=(t_1 / (world * t_n)) if world > 1 else 1.0,
+                                       what="BASELINE config 3 as stated: one 10 h recording = 1200 windows split over the ranks (strong scaling), "
+                                            "PCM resident in HBM, one blocking call per rank, max over ranks")
+        if "latency_b1" in extras:
+            line["latency_b1"] = extras["latency_b1"]
         if not args.no_cpu_baseline and world == 1:
             from oracle import oracle as O
             om = O.OracleModel(path)
@@ -352,9 +498,11 @@ def main():
             dt = time.perf_counter() - t0
             line["cpu_baseline"] = dict(value=WINDOW_S / dt, unit="audio-s/s", cores=cores, kind="port",
                                         sample="1 window of 30 s (window 0 of the same recording), restated reference path (not ggml), OpenMP all cores")
+            if not beam:
+                # outputs of the benchmarked configuration against the oracle's, on the window the CPU leg just transcribed
+                line["parity_check"] = parity_check(st, ctx, om, ost, hv[0], p)
             # the reference never overrides whisper.cpp's default n_threads = min(4, cores): same window, 4 threads,
-            # encoder + the first 16 decoder steps only would not be the same workload, so the whole window is run when the
-            # all-core run says it fits ~60 s, otherwise the 4-thread figure is left out
+            # run when the all-core run says it fits ~90 s, otherwise the 4-thread figure is left out
             if dt * cores / 4.0 < 90.0 and cores > 4:
                 ost.set_options(O.GELU_TANH_F16LUT, O.ACT_F16, 4)
                 t0 = time.perf_counter()

@@ -136,6 +136,19 @@ OH_API int oh_full_batch(oh_context* ctx, oh_state* state, oh_full_params params
 OH_API int oh_full_batch_device(oh_context* ctx, oh_state* state, oh_full_params params, const float* const* d_samples,
                                 const int* n_samples, int batch);
 
+/* additive: continuous batching ACROSS calls (the daemon's jobs are independent, queue/mod.rs:18-27).
+ * oh_stream_submit registers `batch` jobs (PCM in host memory, or device memory with on_device != 0; borrowed until the
+ * call returns: it uploads the PCM and computes the log-mel) and returns a ticket; the jobs start to share the resident
+ * decoder rows with the jobs of earlier tickets.  oh_stream_wait(ticket) drives the scheduler until every job of that
+ * ticket is done; its results are then read with the *_item getters (until the next wait / oh_full* on the state).  Jobs of
+ * later tickets keep decoding meanwhile, so the rows never drain between calls.  oh_full_batch == submit + wait.
+ * All live tickets must share one set of oh_full_params (a different set waits for the live tickets to finish); sampled
+ * (t > 0) tokens of a streamed job draw from a generator seeded 0 per job.  One thread at a time per state. */
+OH_API int oh_stream_submit(oh_context* ctx, oh_state* state, oh_full_params params, const float* const* samples, const int* n_samples,
+                            int batch, int on_device, int* out_ticket);
+OH_API int oh_stream_wait(oh_context* ctx, oh_state* state, int ticket);
+OH_API int oh_stream_pending(oh_state* state); /* tickets submitted and not yet waited for */
+
 /* ---- results (item 0 unless *_item) ----------------------------------------------------------- */
 
 /* whisper_full_n_segments_from_state()  <- state.full_n_segments(), whisper.rs:271 */
@@ -153,6 +166,8 @@ OH_API float oh_full_get_token_p(oh_state* state, int i_segment, int i_token);
 /* whisper_full_lang_id_from_state()  <- state.full_lang_id_from_state(), whisper.rs:290 */
 OH_API int oh_full_lang_id(oh_state* state);
 
+/* per-item return code of a batched call: 0, or OH_ERR_MEL for a clip too short to reflect-pad (its item has no segments) */
+OH_API int oh_full_item_rc(oh_state* state, int item);
 OH_API int oh_full_n_segments_item(oh_state* state, int item);
 OH_API const char* oh_full_get_segment_text_item(oh_state* state, int item, int i_segment);
 OH_API int64_t oh_full_get_segment_t0_item(oh_state* state, int item, int i_segment);
@@ -205,7 +220,7 @@ OH_API int oh_encode_device(oh_context* ctx, oh_state* state, const float* d_mel
  * LAST position, [batch][n_vocab] f32, to out_logits (host). */
 OH_API int oh_decode_batch(oh_context* ctx, oh_state* state, const int* tokens, int n_tokens, int n_past, int batch, float* out_logits);
 
-/* timing / counters of the last oh_full* call on this state */
+/* timing / counters of the state's activity between the previous oh_full* / oh_stream_wait return and the last one */
 typedef struct oh_timings {
     float mel_ms, encode_ms, decode_ms, total_ms; /* CUDA-event times on the state's stream */
     int n_windows, n_decode_steps, n_tokens, n_fallbacks;
@@ -213,6 +228,7 @@ typedef struct oh_timings {
     long long h2d_bytes, d2h_bytes; /* host<->device traffic of the call (PCM in, decoder state / token records out) */
     long long n_prompt_steps;       /* row-steps spent feeding prompt tokens (one per step), not sampling */
     long long n_row_steps;          /* decode steps x resident rows */
+    long long n_armed_row_steps;    /* of those, row-steps of rows that had a window to decode (the rest: no window was ready) */
 } oh_timings;
 OH_API oh_timings oh_get_timings(oh_state* state);
 

@@ -25,7 +25,7 @@ class Timings(C.Structure):
     _fields_ = [("mel_ms", C.c_float), ("encode_ms", C.c_float), ("decode_ms", C.c_float), ("total_ms", C.c_float),
                 ("n_windows", C.c_int), ("n_decode_steps", C.c_int), ("n_tokens", C.c_int), ("n_fallbacks", C.c_int),
                 ("n_kernel_launches", C.c_longlong), ("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong),
-                ("n_prompt_steps", C.c_longlong), ("n_row_steps", C.c_longlong)]
+                ("n_prompt_steps", C.c_longlong), ("n_row_steps", C.c_longlong), ("n_armed_row_steps", C.c_longlong)]
 
 
 class KernelStat(C.Structure):

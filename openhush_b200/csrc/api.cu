@@ -62,40 +62,40 @@ OH_API oh_context* oh_init_from_file(const char* path_model, oh_context_params p
         set_error("cudaSetDevice failed");
         return nullptr;
     }
-    // the tensor-core GEMM must prove itself against the SIMT kernel once per process before it is trusted;
-    // OH_GEMM=simt is the explicit opt-out (slow path, same results contract)
+    // the tensor-core kernels must prove themselves against the SIMT / mma.sync kernels once per DEVICE before they are
+    // trusted (shared-memory opt-ins and the kernels' loaded images are per device); OH_GEMM=simt is the explicit opt-out
+    // (slow path, same results contract)
     if (params.compute_type != OH_COMPUTE_F32) {
         const char* gm = getenv("OH_GEMM");
         const bool force_simt = gm && strcmp(gm, "simt") == 0;
-        static int selftest_rc = 1;  // 1 = not run
-        static float selftest_err = -1.0f;
-        if (!force_simt && selftest_rc == 1) {
+        static PerDeviceInit selftest;
+        static float selftest_err[PerDeviceInit::kMaxDevices];
+        static int selftest_rc[PerDeviceInit::kMaxDevices];
+        const int dev = params.gpu_device;
+        if (!force_simt) {
             if (!gemm_tc_available()) {
                 set_error("tcgen05 GEMM path unavailable on this device/driver (set OH_GEMM=simt to run the SIMT kernels)");
                 return nullptr;
             }
-            selftest_rc = gemm_tc_selftest(nullptr, &selftest_err);
-            if (selftest_rc == OH_OK) {
-                float e2 = -1.0f;
-                selftest_rc = gemm_skinny_selftest(nullptr, &e2);
-                if (selftest_rc == OH_OK) selftest_err = std::max(selftest_err, e2);
-            }
-            if (selftest_rc == OH_OK) {
-                float e3 = -1.0f;
-                selftest_rc = gemm_splitk_selftest(nullptr, &e3);
-                if (selftest_rc == OH_OK) selftest_err = std::max(selftest_err, e3);
-            }
-            if (selftest_rc == OH_OK) {  // attention compares two different summation orders with 16-bit P: own (looser) bound inside
-                float e4 = -1.0f;
-                selftest_rc = encoder_attention_tc_selftest(nullptr, &e4);
+            const bool ok = selftest.ensure([&] {
+                float err = -1.0f, e2 = -1.0f, e3 = -1.0f, e4 = -1.0f;
+                int rc = gemm_tc_selftest(nullptr, &err);
+                if (rc == OH_OK) rc = gemm_skinny_selftest(nullptr, &e2);
+                if (rc == OH_OK) rc = gemm_splitk_selftest(nullptr, &e3);
+                // attention compares two different summation orders with 16-bit P: own (looser) bound inside
+                if (rc == OH_OK) rc = encoder_attention_tc_selftest(nullptr, &e4);
+                err = std::max(err, std::max(e2, e3));
+                selftest_err[dev] = err;
+                selftest_rc[dev] = rc;
                 g_attn_selftest_err = e4;
+                g_selftest_err = err;
+                return rc == OH_OK && err >= 0.0f && err < 2e-3f;
+            });
+            if (!ok) {
+                set_error("tcgen05 GEMM self-test failed on device " + std::to_string(dev) + ": rc=" + std::to_string(selftest_rc[dev]) +
+                          " rel_err=" + std::to_string(selftest_err[dev]) + " " + get_error());
+                return nullptr;
             }
-            g_selftest_err = selftest_err;
-        }
-        if (!force_simt && (selftest_rc != OH_OK || !(selftest_err >= 0.0f && selftest_err < 2e-3f))) {
-            set_error("tcgen05 GEMM self-test failed: rc=" + std::to_string(selftest_rc) + " rel_err=" + std::to_string(selftest_err) + " " +
-                      get_error());
-            return nullptr;
         }
     }
     Model* m = load_model(path_model, params.gpu_device, params.compute_type);
@@ -194,9 +194,53 @@ static int full_impl(oh_context* ctx, oh_state* st, const oh_full_params& p, con
     set_error("");
     for (int i = 0; i < batch; ++i)
         if (n[i] < 0 || (!samples[i] && n[i] > 0)) return OH_ERR_INVALID;
-    int rc = run_full(st, p, samples, n, batch, on_device);
+    int rc;
+    try {  // no exception may cross the C ABI
+        rc = run_full(st, p, samples, n, batch, on_device);
+    } catch (const std::exception& e) {
+        set_error(std::string("oh_full: ") + e.what());
+        sched_abort(st);
+        return OH_ERR_INVALID;
+    }
     if (rc == OH_OK && batch == 1 && !st->items.empty()) rc = st->items[0].rc;
     return rc;
+}
+
+OH_API int oh_stream_submit(oh_context* ctx, oh_state* st, oh_full_params params, const float* const* samples, const int* n_samples, int batch,
+                            int on_device, int* out_ticket) {
+    if (!ctx || !st || st->ctx != ctx || !samples || !n_samples || !out_ticket) return OH_ERR_INVALID;
+    if (select_device(ctx)) return OH_ERR_CUDA;
+    set_error("");
+    for (int i = 0; i < batch; ++i)
+        if (n_samples[i] < 0 || (!samples[i] && n_samples[i] > 0)) return OH_ERR_INVALID;
+    try {
+        int rc = sched_submit(st, params, samples, n_samples, batch, on_device != 0, /*persistent_rngs=*/false, out_ticket);
+        if (rc && rc != OH_ERR_INVALID && rc != OH_ERR_UNSUPPORTED) sched_abort(st);
+        return rc;
+    } catch (const std::exception& e) {
+        set_error(std::string("oh_stream_submit: ") + e.what());
+        sched_abort(st);
+        return OH_ERR_INVALID;
+    }
+}
+OH_API int oh_stream_wait(oh_context* ctx, oh_state* st, int ticket) {
+    if (!ctx || !st || st->ctx != ctx) return OH_ERR_INVALID;
+    if (select_device(ctx)) return OH_ERR_CUDA;
+    set_error("");
+    try {
+        int rc = sched_wait(st, ticket);
+        if (rc && rc != OH_ERR_INVALID) sched_abort(st);
+        return rc;
+    } catch (const std::exception& e) {
+        set_error(std::string("oh_stream_wait: ") + e.what());
+        sched_abort(st);
+        return OH_ERR_INVALID;
+    }
+}
+OH_API int oh_stream_pending(oh_state* st) { return st ? sched_pending(st) : 0; }
+OH_API int oh_full_item_rc(oh_state* st, int item) {
+    if (!st || item < 0 || item >= (int)st->items.size()) return OH_ERR_INVALID;
+    return st->items[item].rc;
 }
 
 OH_API int oh_full(oh_context* ctx, oh_state* st, oh_full_params params, const float* samples, int n_samples) {
@@ -461,7 +505,7 @@ OH_API int oh_profile_report(oh_state* st, oh_kernel_stat* out, int cap) {
     return n;
 }
 
-OH_API oh_timings oh_get_timings(oh_state* st) { return st ? st->timings : oh_timings{}; }
+OH_API oh_timings oh_get_timings(oh_state* st) { return st ? st->timings_out : oh_timings{}; }
 
 OH_API int oh_state_set_stream(oh_state* st, void* cuda_stream) {
     if (!st) return OH_ERR_INVALID;

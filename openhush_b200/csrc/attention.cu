@@ -103,10 +103,10 @@ __global__ void __launch_bounds__(256) encoder_attention_simple_kernel(const T* 
 template <typename T>
 int launch_simple_t(const void* qkv, void* out, int B, int Tn, int d, cudaStream_t st) {
     const size_t smem = (size_t)(SQ * S_LD + SQ * kHeadDim + KT * 65) * sizeof(float);
-    static bool attr = false;
-    if (!attr) {
-        OH_CUDA_CHECK(cudaFuncSetAttribute(encoder_attention_simple_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
+    static PerDeviceInit attr;  // per instantiation and per device
+    if (!attr.ensure([&] { return cudaFuncSetAttribute(encoder_attention_simple_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess; })) {
+        set_error("encoder_attention_simple: shared-memory opt-in failed");
+        return OH_ERR_CUDA;
     }
     dim3 grid((Tn + SQ - 1) / SQ, d / kHeadDim, B);
     ProfScope ps(PC_ATTN_ENC, 4.0 * B * (double)Tn * Tn * d, st);

@@ -320,19 +320,16 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __g
     }
 }
 
-int g_at_state = 0;  // 0 unknown, 1 usable, -1 unusable
+PerDeviceInit g_at_init;
 
 }  // namespace
 
 bool encoder_attention_tc_available() {
-    if (g_at_state == 0) {
-        g_at_state = gemm_tc_available() &&
-                             cudaFuncSetAttribute(encoder_attention_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES) == cudaSuccess &&
-                             cudaFuncSetAttribute(encoder_attention_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES) == cudaSuccess
-                         ? 1
-                         : -1;
-    }
-    return g_at_state == 1;
+    return g_at_init.ensure([] {
+        return gemm_tc_available() &&
+               cudaFuncSetAttribute(encoder_attention_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES) == cudaSuccess &&
+               cudaFuncSetAttribute(encoder_attention_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES) == cudaSuccess;
+    });
 }
 
 int launch_encoder_attention_tc(const void* qkv, void* out, int type, int B, int Tn, int d, cudaStream_t st) {

@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <initializer_list>
+#include <mutex>
 #include <string>
 #include <utility>
 #include <vector>
@@ -31,6 +32,7 @@ constexpr int kHop = 160;
 constexpr int kNBins = 201;
 constexpr int kChunkFrames = 3000;  // mel frames per 30 s window
 constexpr int kHeadDim = 64;        // every Whisper size
+constexpr int kMaxMelFilterWeights = 1024;  // sparse slaney bank staged in shared memory by the mel kernel (80 mel: 486, 128 mel: 522 weights)
 
 // launch counter for bench.py's gpu_launches (host side, incremented by every kernel launch wrapper)
 extern thread_local long long g_launch_count;
@@ -50,8 +52,45 @@ struct Profiler {
     std::vector<cudaEvent_t> free_events;
 };
 extern thread_local Profiler* g_prof;
-extern unsigned g_skip_mask;  // timing experiments: categories whose launches are skipped (results are then meaningless)
+extern thread_local int g_active_rows_hint;  // rows that hold a window in the step being launched (-1: all); only sizes the profiler's `work`
+// Timing experiments (scripts/bench_decode_step.py attributes a step by elimination): a DIAGNOSTIC build
+// (`make DIAG=1`, -DOH_DIAG) can skip whole kernel categories through OH_SKIP_CATS; results are then meaningless.
+// The release library has no such switch: the macro compiles to nothing.
+#ifdef OH_DIAG
+extern unsigned g_skip_mask;
 #define OH_SKIP_IF(cat) do { if (::oh::g_skip_mask & (1u << (cat))) return OH_OK; } while (0)
+#else
+#define OH_SKIP_IF(cat) do { } while (0)
+#endif
+
+// One-time set-up that CUDA scopes per DEVICE (cudaFuncSetAttribute opt-ins, device properties, self-tests): `init`
+// runs once per device ordinal, under a lock, on the calling thread's current device; later calls return what it
+// returned.  (One worker thread per GPU inside one process is the multi-GPU host design: INTEGRATION.md section 3.)
+class PerDeviceInit {
+   public:
+    static constexpr int kMaxDevices = 64;
+    template <typename F>
+    bool ensure(F&& init) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return false;
+        std::lock_guard<std::mutex> lk(mu_);
+        if (!done_[dev]) {
+            ok_[dev] = init();
+            done_[dev] = true;
+        }
+        return ok_[dev];
+    }
+    static int current_device() {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        return dev < 0 || dev >= kMaxDevices ? 0 : dev;
+    }
+
+   private:
+    std::mutex mu_;
+    bool done_[kMaxDevices] = {};
+    bool ok_[kMaxDevices] = {};
+};
 struct ProfScope {
     int idx = -1;
     cudaStream_t st;
@@ -89,6 +128,7 @@ struct ProfScope {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 #endif
+extern thread_local int g_sm_limit;  // > 0: persistent kernels launched by this thread size their grid for this many SMs (encoder on an SM partition)
 extern thread_local int g_pdl;  // > 0 while the calling thread is inside a decode step (set by decode_step_launch)
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {

@@ -7,6 +7,8 @@
 // lives in device memory (DecodeSeqState) and is advanced by the K9 kernel itself, so a greedy decode is a
 // fixed sequence of launches per token with no host round trip — which is what lets the step be replayed as
 // one CUDA graph.  Rows whose `active` flag is 0 exit immediately (no KV traffic).
+#include <algorithm>
+
 #include "../../include/oh_whisper.h"
 #include "decode_rules.h"
 #include "kernels.h"
@@ -42,10 +44,10 @@ __global__ void __launch_bounds__(128) self_attention_decode_kernel(const T* __r
     __shared__ float red[4];
     __shared__ float part[2][kHeadDim];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int pos = s.pos[b], slot = s.slot[b];
+    const int pos = s.pos[b], slot = s.sslot[b];
     const int n_kv = pos + 1;
     const T* row = qkv + (size_t)b * 3 * d;
-    // self cache of a slot: [heads][n_ctx][64] — contiguous per (slot, head), like the cross cache
+    // self cache of a cache line: [heads][n_ctx][64] — contiguous per (slot, head), like the cross cache
     T* K = kcache + ((size_t)slot * (d / kHeadDim) + h) * n_ctx * kHeadDim;
     T* V = vcache + ((size_t)slot * (d / kHeadDim) + h) * n_ctx * kHeadDim;
     if (tid < kHeadDim) {
@@ -276,7 +278,7 @@ __global__ void __launch_bounds__(128) attention_decode_online_kernel(const T* _
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int sub = lane & 7, grp = lane >> 3;
     const int gidx = warp * 4 + grp;
-    const int slot = s.slot[b];
+    const int slot = IS_SELF ? s.sslot[b] : s.slot[b];
     const int H = d / kHeadDim;
     int n_kv;
     size_t ld;
@@ -425,7 +427,7 @@ __global__ void __launch_bounds__(128) self_attention_decode_warp_kernel(const T
     const int b = wid / H, h = wid - b * H;
     if (!s.active[b]) return;
     const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
-    const int pos = s.pos[b], slot = s.slot[b];
+    const int pos = s.pos[b], slot = s.sslot[b];
     const int n_kv = pos + 1;
     const T* row = qkv + (size_t)b * 3 * d + h * kHeadDim;
     T* K = kcache + ((size_t)slot * H + h) * n_ctx * kHeadDim;
@@ -956,11 +958,10 @@ int launch_self_attention_decode(const void* qkv, void* kcache, void* vcache, in
     if (n_ctx > 448) return OH_ERR_INVALID;
     OH_SKIP_IF(PC_SELF_ATTN);
     ProfScope ps(PC_SELF_ATTN, 0.0, st);
-    static int use_warp = -1;
-    if (use_warp < 0) {
+    static const int use_warp = [] {
         const char* e = getenv("OH_SELFATTN");
-        use_warp = (e && strcmp(e, "online") == 0) ? 0 : 1;
-    }
+        return (e && strcmp(e, "online") == 0) ? 0 : 1;
+    }();
     if (type == DT_F32) OH_CUDA_CHECK(launch_k(self_attention_decode_kernel<float>, grid, 128, 0, st, (const float*)qkv, (float*)kcache, (float*)vcache, s, d, n_ctx, (float*)out));
     else if (!use_warp && type == DT_F16)
         OH_CUDA_CHECK(launch_k(attention_decode_online_kernel<__half, true>, grid, 128, 0, st, (const __half*)qkv, 3 * d, nullptr, nullptr, (__half*)kcache, (__half*)vcache, s, d, n_ctx, (__half*)out));
@@ -979,22 +980,25 @@ int launch_cross_attention_decode(const void* q, const void* xkv, int type, cons
                                   cudaStream_t st) {
     dim3 grid(d / kHeadDim, rows);
     if (T > 1504) return OH_ERR_INVALID;
-    // algorithmic bytes: every row streams its slot's K and V once (all rows assumed active)
+    // algorithmic bytes: every row that holds a window streams its slot's K and V once (rows without one exit at once)
     OH_SKIP_IF(PC_CROSS_ATTN);
-    ProfScope ps(PC_CROSS_ATTN, (double)rows * T * 2.0 * d * (type == DT_F32 ? 4 : 2), st);
-    static int use_bulk = -1;
-    static int xa_smem = XA_SMEM_BYTES;
-    if (use_bulk < 0) {
-        const char* e = getenv("OH_XATTN");
-        use_bulk = (e && strcmp(e, "online") == 0) ? 0 : 1;
-        // OH_XATTN_OCC=1: one CTA per SM (shared memory padded past half an SM) so that the other row group's kernels
-        // always find room next to it; the 6-stage ring of a single CTA per SM still covers the HBM latency
+    const int rows_work = g_active_rows_hint >= 0 ? std::min(rows, g_active_rows_hint) : rows;
+    ProfScope ps(PC_CROSS_ATTN, (double)rows_work * T * 2.0 * d * (type == DT_F32 ? 4 : 2), st);
+    // OH_XATTN_OCC=1: one CTA per SM (shared memory padded past half an SM) so that other kernels always find room next
+    // to it; the 6-stage ring of a single CTA per SM still covers the HBM latency
+    static const int xa_smem = [] {
         const char* o = getenv("OH_XATTN_OCC");
-        if (o && atoi(o) == 1) xa_smem = 116 * 1024;
-        if (cudaFuncSetAttribute(cross_attention_decode_bulk_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, xa_smem) != cudaSuccess ||
-            cudaFuncSetAttribute(cross_attention_decode_bulk_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, xa_smem) != cudaSuccess)
-            use_bulk = 0;
-    }
+        return (o && atoi(o) == 1) ? 116 * 1024 : XA_SMEM_BYTES;
+    }();
+    static const bool want_bulk = [] {
+        const char* e = getenv("OH_XATTN");
+        return !(e && strcmp(e, "online") == 0);
+    }();
+    static PerDeviceInit bulk_attr;  // the shared-memory opt-in is per device
+    const bool use_bulk = want_bulk && type != DT_F32 && bulk_attr.ensure([] {
+        return cudaFuncSetAttribute(cross_attention_decode_bulk_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, xa_smem) == cudaSuccess &&
+               cudaFuncSetAttribute(cross_attention_decode_bulk_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, xa_smem) == cudaSuccess;
+    });
     if (type == DT_F32) OH_CUDA_CHECK(launch_k(cross_attention_decode_kernel<float>, grid, 128, 0, st, (const float*)q, (const float*)xkv, s, d, T, (float*)out));
     else if (use_bulk && type == DT_F16)
         OH_CUDA_CHECK(launch_k(cross_attention_decode_bulk_kernel<__half>, grid, XA_THREADS, xa_smem, st, (const __half*)q, (const __half*)xkv, s, d, T, (__half*)out));

@@ -5,6 +5,9 @@
 // the reference; items advance window by window in lock-step rounds:
 //   gather mel window at item.seek -> encoder -> cross-KV -> greedy decode (device state machine, CUDA graph)
 //   -> host scoring / temperature fallback -> segments -> seek += seek_delta.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -18,8 +21,12 @@ namespace oh {
 
 thread_local long long g_launch_count = 0;
 thread_local int g_pdl = 0;
+thread_local int g_sm_limit = 0;
 thread_local Profiler* g_prof = nullptr;
-unsigned g_skip_mask = 0;  // OH_SKIP_CATS: timing experiments only (kernel categories that are not launched)
+thread_local int g_active_rows_hint = -1;
+#ifdef OH_DIAG
+unsigned g_skip_mask = 0;  // OH_SKIP_CATS (diagnostic build only): kernel categories that are not launched
+#endif
 static thread_local std::string g_error;
 void set_error(const std::string& msg) { g_error = msg; }
 const std::string& get_error() { return g_error; }
@@ -34,7 +41,7 @@ int ensure(DevBuf& b, size_t bytes) {
     b.bytes = bytes;
     return OH_OK;
 }
-static void release(DevBuf& b) {
+void release(DevBuf& b) {
     if (b.p) cudaFree(b.p);
     b.p = nullptr;
     b.bytes = 0;
@@ -42,29 +49,12 @@ static void release(DevBuf& b) {
 
 static inline size_t rup(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// ---- layout of the DecodeSeqState block (ints unless noted), rows = max_batch -------------------------
-namespace seqlay {
-enum { SLOT, ACTIVE, POS, CUR, PLEN, NGEN, HAS_TS, SDELTA, RLEN, FAILED, COMPLETED, SEEK, SEEKEND, N_SCALARS };
-}
-struct SeqLayout {
-    size_t rows, prompt_off, tok_off[6], counter_off, total_words;
-    explicit SeqLayout(size_t r) : rows(r) {
-        size_t o = seqlay::N_SCALARS * rows;
-        prompt_off = o;
-        o += rows * kMaxPrompt;
-        for (int i = 0; i < 6; ++i) {
-            tok_off[i] = o;
-            o += rows * kMaxGen;
-        }
-        counter_off = o;
-        total_words = o + 4;
-    }
-};
-
-static DecodeSeqState seq_view(int32_t* base, const SeqLayout& L) {
+// ---- layout of the DecodeSeqState block (ints unless noted; SeqLayout in engine.h) ------------------------------
+DecodeSeqState seq_view(int32_t* base, const SeqLayout& L) {
     DecodeSeqState s;
     using namespace seqlay;
     s.slot = base + SLOT * L.rows;
+    s.sslot = base + SSLOT * L.rows;
     s.active = base + ACTIVE * L.rows;
     s.pos = base + POS * L.rows;
     s.cur_token = base + CUR * L.rows;
@@ -90,12 +80,56 @@ static DecodeSeqState seq_view(int32_t* base, const SeqLayout& L) {
 
 // the same state block seen from row `row0` on (row groups of the interleaved decode step)
 static DecodeSeqState seq_offset(DecodeSeqState s, int row0) {
-    s.slot += row0; s.active += row0; s.pos += row0; s.cur_token += row0; s.prompt_len += row0; s.n_gen += row0; s.has_ts += row0;
+    s.slot += row0; s.sslot += row0; s.active += row0; s.pos += row0; s.cur_token += row0; s.prompt_len += row0; s.n_gen += row0; s.has_ts += row0;
     s.seek_delta += row0; s.result_len += row0; s.failed += row0; s.completed += row0; s.seek += row0; s.seek_end += row0;
     s.prompt += (size_t)row0 * kMaxPrompt;
     s.tok_id += (size_t)row0 * kMaxGen; s.tok_tid += (size_t)row0 * kMaxGen; s.tok_p += (size_t)row0 * kMaxGen;
     s.tok_plog += (size_t)row0 * kMaxGen; s.tok_pt += (size_t)row0 * kMaxGen; s.tok_ptsum += (size_t)row0 * kMaxGen;
     return s;
+}
+
+// ---- encoder stream on an SM partition (green context) --------------------------------------------------------------
+// The encoder is tensor-bound, a decode step is HBM- and latency-bound; run concurrently they hide each other, but the
+// persistent tcgen05 mat-mul holds every SM it lands on for milliseconds, and the step's short kernels would queue behind
+// it.  OH_ENC_SMS=n confines the encoder stream to n SMs (CUDA green context; the driver rounds n to its partition
+// granularity), so that the decode stream always finds the other SMs free.  Unset / 0: a plain second stream.
+namespace {
+template <typename F>
+F driver_fn(const char* name) {
+    cudaDriverEntryPointQueryResult q;
+    void* fn = nullptr;
+    if (cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+    return reinterpret_cast<F>(fn);
+}
+}  // namespace
+
+static bool create_partition_stream(oh_state* st, int want_sms) {
+    auto get_dev = driver_fn<PFN_cuDeviceGet>("cuDeviceGet");
+    auto get_res = driver_fn<PFN_cuDeviceGetDevResource>("cuDeviceGetDevResource");
+    auto split = driver_fn<PFN_cuDevSmResourceSplitByCount>("cuDevSmResourceSplitByCount");
+    auto gen = driver_fn<PFN_cuDevResourceGenerateDesc>("cuDevResourceGenerateDesc");
+    auto gcreate = driver_fn<PFN_cuGreenCtxCreate>("cuGreenCtxCreate");
+    auto gstream = driver_fn<PFN_cuGreenCtxStreamCreate>("cuGreenCtxStreamCreate");
+    if (!get_dev || !get_res || !split || !gen || !gcreate || !gstream) return false;
+    CUdevice dev;
+    if (get_dev(&dev, st->ctx->params.gpu_device) != CUDA_SUCCESS) return false;
+    CUdevResource all{}, part{}, rest{};
+    if (get_res(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return false;
+    unsigned int n_groups = 1;
+    if (split(&part, &n_groups, &all, &rest, 0, (unsigned)want_sms) != CUDA_SUCCESS || n_groups < 1) return false;
+    CUdevResourceDesc desc = nullptr;
+    if (gen(&desc, &part, 1) != CUDA_SUCCESS) return false;
+    CUgreenCtx g = nullptr;
+    if (gcreate(&g, desc, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return false;
+    CUstream cs = nullptr;
+    if (gstream(&cs, g, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) {
+        if (auto gdestroy = driver_fn<PFN_cuGreenCtxDestroy>("cuGreenCtxDestroy")) gdestroy(g);
+        return false;
+    }
+    st->green_ctx = g;
+    st->enc_stream = (cudaStream_t)cs;
+    st->enc_sms = (int)part.sm.smCount;
+    return true;
 }
 
 int state_alloc(oh_state* st) {
@@ -105,22 +139,41 @@ int state_alloc(oh_state* st) {
     st->esz = st->ctx->act_type == DT_F32 ? 4 : 2;
     const size_t e = st->esz;
     st->max_batch = std::max(1, st->ctx->params.max_batch);
-    int chunk = std::min(st->max_batch, 64);
-    if (const char* s = getenv("OH_ENC_CHUNK")) chunk = std::max(1, std::min(st->max_batch, atoi(s)));
+    int chunk = std::min(st->max_batch, 32);
+    if (const char* s = getenv("OH_ENC_CHUNK")) chunk = std::max(1, std::min(std::max(st->max_batch, 1), atoi(s)));
     st->enc_chunk = chunk;
+    // look-ahead slots: windows are encoded (on the encoder stream) before a decoder row is free for them, so a row
+    // that finishes is re-armed at the next look-in instead of waiting for an encoder pass
+    int lookahead = st->max_batch >= 16 ? std::min(st->max_batch, 3 * chunk) : 0;
+    if (const char* s = getenv("OH_LOOKAHEAD")) lookahead = std::max(0, atoi(s));
+    st->n_slots = st->max_batch + lookahead;
+    if (const char* s = getenv("OH_ASYNC_ENC")) st->async_encoder = atoi(s) != 0;
+    if (const char* s = getenv("OH_CHECK")) st->check_steps = std::max(1, atoi(s));
     if (const char* s = getenv("OH_GEMM")) st->gemm_mode = strcmp(s, "simt") == 0 ? 1 : 0;
     if (const char* s = getenv("OH_ATTN")) st->attn_mode = strcmp(s, "simple") == 0 ? 1 : (strcmp(s, "flash") == 0 ? 2 : 0);  // flash: the mma.sync kernel
     if (const char* s = getenv("OH_GRAPHS")) st->use_graphs = atoi(s) != 0;
     if (const char* s = getenv("OH_PDL")) st->use_pdl = atoi(s) != 0;
     if (const char* s = getenv("OH_DUAL")) st->dual_min_rows = atoi(s) > 0 ? atoi(s) : (1 << 30);  // OH_DUAL=0: never interleave row groups
     if (const char* s = getenv("OH_GELU")) st->gelu_lut_f32 = strcmp(s, "lut") == 0;
+#ifdef OH_DIAG
     if (const char* s = getenv("OH_SKIP_CATS")) g_skip_mask = (unsigned)strtoul(s, nullptr, 0);
+#endif
     if (const char* s = getenv("OH_SKINNY")) st->skinny_mode = atoi(s) == 0 ? 1 : 0;  // OH_SKINNY=0: decode mat-muls through the persistent tcgen05 kernel
     if (const char* s = getenv("OH_DECODE_GEMM")) st->skinny_mode = strcmp(s, "skinny") == 0 ? 0 : (strcmp(s, "tc") == 0 ? 1 : 2);
 
-    OH_CUDA_CHECK(cudaStreamCreateWithFlags(&st->own_stream, cudaStreamNonBlocking));
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // lo = numerically largest = least urgent
+    OH_CUDA_CHECK(cudaStreamCreateWithPriority(&st->own_stream, cudaStreamNonBlocking, prio_hi));
     st->stream = st->own_stream;
     OH_CUDA_CHECK(cudaStreamCreateWithFlags(&st->stream2, cudaStreamNonBlocking));
+    OH_CUDA_CHECK(cudaStreamCreateWithFlags(&st->fe_stream, cudaStreamNonBlocking));
+    int enc_sms = 0;
+    if (const char* s = getenv("OH_ENC_SMS")) enc_sms = std::max(0, atoi(s));
+    if (!(enc_sms > 0 && create_partition_stream(st, enc_sms))) {
+        st->green_ctx = nullptr;
+        st->enc_sms = 0;
+        OH_CUDA_CHECK(cudaStreamCreateWithPriority(&st->enc_stream, cudaStreamNonBlocking, prio_lo));
+    }
     for (auto& ev : st->ev) OH_CUDA_CHECK(cudaEventCreate(&ev));
     for (auto& ev : st->ev_dual) OH_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
 
@@ -132,39 +185,48 @@ int state_alloc(oh_state* st) {
     if ((rc = ensure(st->h, W * T * d * e))) return rc;
     if ((rc = ensure(st->qkv, W * T * 3 * d * e))) return rc;
     if ((rc = ensure(st->hid, W * T * 4 * d * e))) return rc;
-    const size_t S = st->max_batch;
+    st->win_desc_cap = 4 * chunk;  // ring: up to two passes in flight plus the one being filled
+    if ((rc = ensure(st->win_desc, (size_t)st->win_desc_cap * sizeof(WindowDesc)))) return rc;
+    OH_CUDA_CHECK(cudaMallocHost((void**)&st->win_desc_host, (size_t)st->win_desc_cap * sizeof(WindowDesc)));
+    const size_t R = st->max_batch, S = st->n_slots;
     if ((rc = ensure(st->xkv, (size_t)L * S * T * 2 * d * e))) return rc;
-    if ((rc = ensure(st->kself, (size_t)L * S * hp.n_text_ctx * d * e))) return rc;
-    if ((rc = ensure(st->vself, (size_t)L * S * hp.n_text_ctx * d * e))) return rc;
-    if ((rc = ensure(st->dx, S * d * 4))) return rc;
-    if ((rc = ensure(st->dh, S * d * e))) return rc;
-    if ((rc = ensure(st->dqkv, S * 3 * d * e))) return rc;
-    if ((rc = ensure(st->datt, S * d * e))) return rc;
-    if ((rc = ensure(st->dq, S * d * e))) return rc;
-    if ((rc = ensure(st->dhid, S * 4 * d * e))) return rc;
+    if ((rc = ensure(st->kself, (size_t)L * R * hp.n_text_ctx * d * e))) return rc;
+    if ((rc = ensure(st->vself, (size_t)L * R * hp.n_text_ctx * d * e))) return rc;
+    if ((rc = ensure(st->dx, R * d * 4))) return rc;
+    if ((rc = ensure(st->dh, R * d * e))) return rc;
+    if ((rc = ensure(st->dqkv, R * 3 * d * e))) return rc;
+    if ((rc = ensure(st->datt, R * d * e))) return rc;
+    if ((rc = ensure(st->dq, R * d * e))) return rc;
+    if ((rc = ensure(st->dhid, R * 4 * d * e))) return rc;
     st->ld_logits = (int)rup(V, 8);
-    if ((rc = ensure(st->logits, S * st->ld_logits * 4))) return rc;
-    SeqLayout lay(S);
+    if ((rc = ensure(st->logits, R * st->ld_logits * 4))) return rc;
+    SeqLayout lay(R);
     if ((rc = ensure(st->seq_dev, lay.total_words * 4))) return rc;
     st->seq = seq_view((int32_t*)st->seq_dev.p, lay);
     if ((rc = ensure(st->rules_dev, sizeof(DecodeRules)))) return rc;
     st->pinned_bytes = lay.total_words * 4 + 4096;
     OH_CUDA_CHECK(cudaMallocHost(&st->pinned, st->pinned_bytes));
     memset(st->pinned, 0, st->pinned_bytes);
-    st->rngs.assign(S, std::mt19937(0));
     st->items.clear();
+    Sched& sc = st->sched;
+    sc.rows.assign(R, RowInfo());
+    sc.free_slots.clear();
+    for (int i = (int)S - 1; i >= 0; --i) sc.free_slots.push_back(i);  // pop_back yields ascending slot ids
     return OH_OK;
 }
 
 void state_release(oh_state* st) {
+    sched_release(st);
     for (auto& kv : st->step_graphs) cudaGraphExecDestroy(kv.second);
     st->step_graphs.clear();
     DevBuf* all[] = {&st->pcm_stage, &st->mel_raw, &st->clip_meta, &st->xin, &st->x1, &st->x, &st->h, &st->qkv, &st->hid, &st->enc_f32,
-                     &st->xkv, &st->kself, &st->vself, &st->dx, &st->dh, &st->dqkv, &st->datt, &st->dq, &st->dhid, &st->logits,
+                     &st->win_desc, &st->xkv, &st->kself, &st->vself, &st->dx, &st->dh, &st->dqkv, &st->datt, &st->dq, &st->dhid, &st->logits,
                      &st->dump_lp, &st->dump_p, &st->seq_dev, &st->rules_dev};
     for (DevBuf* b : all) release(*b);
     if (st->pinned) cudaFreeHost(st->pinned);
     st->pinned = nullptr;
+    if (st->win_desc_host) cudaFreeHost(st->win_desc_host);
+    st->win_desc_host = nullptr;
     if (st->prof) {
         if (g_prof == st->prof) g_prof = nullptr;
         for (auto& r : st->prof->recs) {
@@ -181,6 +243,14 @@ void state_release(oh_state* st) {
     st->own_stream = nullptr;
     if (st->stream2) cudaStreamDestroy(st->stream2);
     st->stream2 = nullptr;
+    if (st->fe_stream) cudaStreamDestroy(st->fe_stream);
+    st->fe_stream = nullptr;
+    if (st->enc_stream) cudaStreamDestroy(st->enc_stream);
+    st->enc_stream = nullptr;
+    if (st->green_ctx) {
+        if (auto gdestroy = driver_fn<PFN_cuGreenCtxDestroy>("cuGreenCtxDestroy")) gdestroy((CUgreenCtx)st->green_ctx);
+        st->green_ctx = nullptr;
+    }
     for (auto& ev : st->ev_dual) {
         if (ev) cudaEventDestroy(ev);
         ev = nullptr;
@@ -188,40 +258,13 @@ void state_release(oh_state* st) {
 }
 
 // ------------------------------------------------------------------------------------------------ mel
-// clip_meta layout (device): [pcm ptrs (8 B each)] [n_samples] [n_active] [n_len] [max_key] [clip_of_slot] [seek_of_slot]
-struct ClipMeta {
-    const float** pcm;
-    int *n_samples, *n_active, *n_len, *max_key, *clip_of_slot, *seek_of_slot;
-};
-static ClipMeta clip_meta_view(void* base, size_t cap) {
-    ClipMeta c;
-    char* p = (char*)base;
-    c.pcm = (const float**)p;
-    p += cap * 8;
-    c.n_samples = (int*)p;
-    p += cap * 4;
-    c.n_active = (int*)p;
-    p += cap * 4;
-    c.n_len = (int*)p;
-    p += cap * 4;
-    c.max_key = (int*)p;
-    p += cap * 4;
-    c.clip_of_slot = (int*)p;
-    p += cap * 4;
-    c.seek_of_slot = (int*)p;
-    return c;
-}
-static size_t clip_meta_bytes(size_t cap) { return cap * (8 + 6 * 4); }
-
-int run_mel(oh_state* st, const float* const* pcm, const int* n, int batch, bool pcm_on_device) {
-    const Model& m = *st->ctx->model;
-    const int n_mel = m.hp.n_mels;
-    st->items.assign(batch, Item());
-    size_t stage_floats = 0;
-    int max_active = 0;
-    std::vector<size_t> off(batch);
+// Per-clip bookkeeping of A.3 (n_len, n_len_org, frames that see samples) and the staging layout of the clips' PCM.
+MelPlan plan_mel(std::vector<Item>& items, const int* n, int batch) {
+    MelPlan pl;
+    items.assign(batch, Item());
+    pl.pcm_off.resize(batch);
     for (int i = 0; i < batch; ++i) {
-        Item& it = st->items[i];
+        Item& it = items[i];
         it.n_samples = n[i];
         if (n[i] <= kNFFT / 2) {  // cannot reflect-pad: whisper.cpp reports "failed to compute log mel spectrogram"
             it.rc = OH_ERR_MEL;
@@ -232,49 +275,69 @@ int run_mel(oh_state* st, const float* const* pcm, const int* n, int batch, bool
             it.n_len_org = 1 + (n[i] + kNFFT / 2 - kNFFT) / kHop;
             it.n_active = std::min((n[i] + kNFFT / 2) / kHop + 1, it.n_len);
         }
-        off[i] = stage_floats;
-        stage_floats += rup((size_t)std::max(n[i], 0), 4);
-        max_active = std::max(max_active, it.n_active);
+        pl.pcm_off[i] = pl.stage_floats;
+        pl.stage_floats += rup((size_t)std::max(n[i], 0), 4);
+        pl.max_active = std::max(pl.max_active, it.n_active);
     }
-    st->mel_clips = batch;
-    st->mel_ld = (int)rup(std::max(max_active, 1), 32);
-    int rc;
-    const size_t cap = std::max<size_t>(batch, st->max_batch);
-    if ((rc = ensure(st->clip_meta, clip_meta_bytes(cap)))) return rc;
-    if ((rc = ensure(st->mel_raw, (size_t)batch * n_mel * st->mel_ld * 4))) return rc;
-    ClipMeta cm = clip_meta_view(st->clip_meta.p, cap);
+    pl.ld = (int)rup(std::max(pl.max_active, 1), 32);
+    return pl;
+}
 
+// clip_meta layout (device): [pcm ptrs (8 B each)] [n_samples] [n_active] [max_key]
+struct ClipMeta {
+    const float** pcm;
+    int *n_samples, *n_active, *max_key;
+};
+static ClipMeta clip_meta_view(void* base, size_t cap) {
+    ClipMeta c;
+    char* p = (char*)base;
+    c.pcm = (const float**)p;
+    p += cap * 8;
+    c.n_samples = (int*)p;
+    p += cap * 4;
+    c.n_active = (int*)p;
+    p += cap * 4;
+    c.max_key = (int*)p;
+    return c;
+}
+static size_t clip_meta_bytes(size_t cap) { return cap * (8 + 3 * 4); }
+
+int launch_mel(oh_state* st, const MelPlan& pl, const std::vector<Item>& items, const float* const* pcm, bool pcm_on_device, DevBuf& pcm_stage,
+               DevBuf& mel_raw, DevBuf& clip_meta, cudaStream_t stream, long long* h2d_bytes) {
+    const Model& m = *st->ctx->model;
+    const int n_mel = m.hp.n_mels, batch = (int)items.size();
+    int rc;
+    if ((rc = ensure(clip_meta, clip_meta_bytes(batch)))) return rc;
+    if ((rc = ensure(mel_raw, (size_t)batch * n_mel * pl.ld * 4))) return rc;
+    ClipMeta cm = clip_meta_view(clip_meta.p, batch);
     std::vector<const float*> ptrs(batch);
-    std::vector<int> ns(batch), na(batch), nl(batch);
+    std::vector<int> ns(batch), na(batch);
     if (!pcm_on_device) {
-        if ((rc = ensure(st->pcm_stage, std::max<size_t>(stage_floats, 4) * 4))) return rc;
+        if ((rc = ensure(pcm_stage, std::max<size_t>(pl.stage_floats, 4) * 4))) return rc;
         for (int i = 0; i < batch; ++i) {
-            ptrs[i] = (const float*)st->pcm_stage.p + off[i];
-            if (n[i] > 0)
-            {
-                OH_CUDA_CHECK(cudaMemcpyAsync((float*)st->pcm_stage.p + off[i], pcm[i], (size_t)n[i] * 4, cudaMemcpyHostToDevice, st->stream));
-                st->timings.h2d_bytes += (long long)n[i] * 4;
+            ptrs[i] = (const float*)pcm_stage.p + pl.pcm_off[i];
+            if (items[i].n_samples > 0) {
+                OH_CUDA_CHECK(cudaMemcpyAsync((float*)pcm_stage.p + pl.pcm_off[i], pcm[i], (size_t)items[i].n_samples * 4, cudaMemcpyHostToDevice, stream));
+                if (h2d_bytes) *h2d_bytes += (long long)items[i].n_samples * 4;
             }
         }
     } else {
         for (int i = 0; i < batch; ++i) ptrs[i] = pcm[i];
     }
     for (int i = 0; i < batch; ++i) {
-        ns[i] = st->items[i].n_samples;
-        na[i] = st->items[i].n_active;
-        nl[i] = st->items[i].n_len;
+        ns[i] = items[i].n_samples;
+        na[i] = items[i].n_active;
     }
-    OH_CUDA_CHECK(cudaMemcpyAsync(cm.pcm, ptrs.data(), batch * 8, cudaMemcpyHostToDevice, st->stream));
-    OH_CUDA_CHECK(cudaMemcpyAsync(cm.n_samples, ns.data(), batch * 4, cudaMemcpyHostToDevice, st->stream));
-    OH_CUDA_CHECK(cudaMemcpyAsync(cm.n_active, na.data(), batch * 4, cudaMemcpyHostToDevice, st->stream));
-    OH_CUDA_CHECK(cudaMemcpyAsync(cm.n_len, nl.data(), batch * 4, cudaMemcpyHostToDevice, st->stream));
-    // the vectors above must outlive the async copies from pageable memory: those are staged synchronously by the runtime
+    // the vectors are pageable: the runtime stages such copies before cudaMemcpyAsync returns
+    OH_CUDA_CHECK(cudaMemcpyAsync(cm.pcm, ptrs.data(), (size_t)batch * 8, cudaMemcpyHostToDevice, stream));
+    OH_CUDA_CHECK(cudaMemcpyAsync(cm.n_samples, ns.data(), (size_t)batch * 4, cudaMemcpyHostToDevice, stream));
+    OH_CUDA_CHECK(cudaMemcpyAsync(cm.n_active, na.data(), (size_t)batch * 4, cudaMemcpyHostToDevice, stream));
     MelArgs a;
     a.pcm = cm.pcm;
     a.n_samples = cm.n_samples;
     a.n_active = cm.n_active;
-    a.raw = (float*)st->mel_raw.p;
-    a.ld = st->mel_ld;
+    a.raw = (float*)mel_raw.p;
+    a.ld = pl.ld;
     a.max_key = cm.max_key;
     a.n_mel = n_mel;
     a.twiddle = st->ctx->d_twiddle;
@@ -284,10 +347,19 @@ int run_mel(oh_state* st, const float* const* pcm, const int* n, int batch, bool
     a.filt_off = m.mel.offset;
     a.filt_w = m.mel.weights;
     a.n_filt_w = m.mel.n_weights;
-    if (max_active > 0) {
-        if ((rc = launch_mel_frames(a, batch, max_active, st->stream))) return rc;
+    if (pl.max_active > 0) {
+        if ((rc = launch_mel_frames(a, batch, pl.max_active, stream))) return rc;
     }
     return OH_OK;
+}
+
+const int* clip_max_key(const DevBuf& clip_meta, int batch, int clip) { return clip_meta_view(clip_meta.p, batch).max_key + clip; }
+
+int run_mel(oh_state* st, const float* const* pcm, const int* n, int batch, bool pcm_on_device) {
+    MelPlan pl = plan_mel(st->items, n, batch);
+    st->mel_clips = batch;
+    st->mel_ld = pl.ld;
+    return launch_mel(st, pl, st->items, pcm, pcm_on_device, st->pcm_stage, st->mel_raw, st->clip_meta, st->stream, &st->timings.h2d_bytes);
 }
 
 // ------------------------------------------------------------------------------------------------ GEMM dispatch
@@ -311,12 +383,19 @@ static int gemm(oh_state* st, GemmArgs g, cudaStream_t stream = nullptr) {
 }
 
 // ------------------------------------------------------------------------------------------------ encoder
-int run_encoder(oh_state* st, int nw, int slot0, float* d_enc_f32_out, const int* slot_list) {
+int run_encoder(oh_state* st, int nw, int slot0, float* d_enc_f32_out, const int* slot_list, cudaStream_t stream) {
     const Model& m = *st->ctx->model;
     const HParams& hp = m.hp;
     const int d = hp.n_audio_state, C = hp.n_mels, T = hp.n_audio_ctx, act = st->ctx->act_type;
     const size_t e = st->esz;
-    cudaStream_t s = st->stream;
+    cudaStream_t s = stream ? stream : st->stream;
+    // on an SM partition the persistent mat-mul sizes its grid for the partition, not for the whole device
+    struct SmLimit {
+        int saved;
+        explicit SmLimit(int v) : saved(g_sm_limit) { g_sm_limit = v; }
+        ~SmLimit() { g_sm_limit = saved; }
+    } sm_limit((stream && stream == st->enc_stream && st->enc_sms > 0) ? st->enc_sms : 0);
+    auto gemm = [&](oh_state* st_, GemmArgs g_) { return oh::gemm(st_, g_, s); };
     int rc;
     char* x1 = (char*)st->x1.p;
     float* x = (float*)st->x.p;
@@ -415,7 +494,7 @@ int run_encoder(oh_state* st, int nw, int slot0, float* d_enc_f32_out, const int
             GemmArgs g;  // one "batch" per window so that the slot index separates from the row index
             g.A = (char*)st->h.p + (size_t)w0 * T * d * e; g.a_type = act; g.lda = d; g.batch = w1 - w0; g.rows = T; g.a_bstride = (long long)T * d;
             g.W = D.xkv.w; g.N = 2 * d; g.K = d; g.bias = D.xkv.b;
-            g.C = (char*)st->xkv.p + ((size_t)l * st->max_batch + first_slot) * T * 2 * d * e;
+            g.C = (char*)st->xkv.p + ((size_t)l * st->n_slots + first_slot) * T * 2 * d * e;
             g.c_type = act;
             g.c_bstride = (long long)T * 2 * d;       // one slot: [2 (k,v)][heads][T][64]
             g.c_hsplit = kHeadDim;                    // column n = (kv * heads + head) * 64 + c
@@ -476,7 +555,7 @@ static int decode_step_launch(oh_state* st, int row0, int rows, bool with_k9, bo
         q.C = dq; q.c_type = act; q.ldc = d;
         if ((rc = gemm(st, q, s))) return rc;
         if (l == 0 && after_q0) OH_CUDA_CHECK(cudaEventRecord(after_q0, s));
-        const char* xkv = (const char*)st->xkv.p + (size_t)l * st->max_batch * T * 2 * d * e;
+        const char* xkv = (const char*)st->xkv.p + (size_t)l * st->n_slots * T * 2 * d * e;
         if ((rc = launch_cross_attention_decode(dq, xkv, act, seq, rows, d, T, datt, s))) return rc;
         GemmArgs xo;
         xo.A = datt; xo.a_type = act; xo.lda = d; xo.rows = rows;
@@ -539,7 +618,7 @@ static int decode_step_all(oh_state* st, int rows, bool with_k9, bool dump) {
 
 int run_decode_step(oh_state* st, int rows, bool dump_probs) { return decode_step_all(st, rows, true, dump_probs); }
 
-static int run_decode_step_graph(oh_state* st, int rows, bool with_k9 = true) {
+int run_decode_step_graph(oh_state* st, int rows, bool with_k9) {
     if (!st->use_graphs || st->profiling) return decode_step_all(st, rows, with_k9, false);
     const int key = rows * 2 + (with_k9 ? 1 : 0);
     auto it = st->step_graphs.find(key);
@@ -571,10 +650,7 @@ static int run_decode_step_graph(oh_state* st, int rows, bool with_k9 = true) {
     return OH_OK;
 }
 
-const int* clip_max_key(oh_state* st, int batch, int clip) {
-    ClipMeta cm = clip_meta_view(st->clip_meta.p, std::max<size_t>(batch, st->max_batch));
-    return cm.max_key + clip;
-}
+const int* clip_max_key(oh_state* st, int batch, int clip) { return clip_max_key(st->clip_meta, batch, clip); }
 
 // stage API: feed tokens[batch][n_tokens] at positions n_past.. and return the logits of the last position
 int decode_tokens_stage(oh_state* st, const int* tokens, int n_tokens, int n_past, int batch, float* out_logits) {
@@ -587,6 +663,7 @@ int decode_tokens_stage(oh_state* st, const int* tokens, int n_tokens, int n_pas
     for (int i = 0; i < n_tokens; ++i) {
         for (int r = 0; r < batch; ++r) {
             hs.slot[r] = r;
+            hs.sslot[r] = r;
             hs.active[r] = 1;
             hs.pos[r] = n_past + i;
             hs.cur_token[r] = tokens[(size_t)r * n_tokens + i];
@@ -601,967 +678,6 @@ int decode_tokens_stage(oh_state* st, const int* tokens, int n_tokens, int n_pas
                                         cudaMemcpyDeviceToHost, s));
         OH_CUDA_CHECK(cudaStreamSynchronize(s));
     }
-    return OH_OK;
-}
-
-// ------------------------------------------------------------------------------------------------ full()
-namespace {
-
-struct PassRow {
-    int item, slot;
-    std::vector<int> prompt;
-};
-struct PassResult {
-    std::vector<TokenData> tokens;
-    int result_len = 0, seek_delta = 0;
-    bool has_ts = false, failed = false, completed = false;
-    double sum_logprobs = 0, avg_logprobs = 0, entropy = 0, score = 0;
-};
-
-void sequence_score(const oh_full_params& p, PassResult& r) {  // A.8
-    const int n = r.result_len;
-    double sum = 0.0;
-    for (int i = 0; i < n && i < (int)r.tokens.size(); ++i) sum += r.tokens[i].plog;
-    r.sum_logprobs = sum;
-    r.avg_logprobs = n > 0 ? sum / n : -INFINITY;
-    double penalty = n;
-    if (p.length_penalty > 0.0f) penalty = std::pow((5.0 + n) / 6.0, (double)p.length_penalty);
-    r.score = n > 0 ? sum / penalty : -INFINITY;
-    std::map<int, int> counts;
-    int cnt = 0;
-    for (int i = std::max(0, n - 32); i < n; ++i) {
-        counts[r.tokens[i].id]++;
-        cnt++;
-    }
-    double ent = 0.0;
-    for (auto& kv : counts) {
-        const double q = (double)kv.second / cnt;
-        ent -= q * std::log(q);
-    }
-    r.entropy = ent;
-}
-
-void emit_segments(const Model& m, const oh_full_params& p, Item& it, const PassResult& best, const std::vector<int>& prompt, int n_prompt_init) {
-    const Vocab& vc = m.vocab;
-    const auto& tk = best.tokens;
-    std::vector<int> new_past;
-    if (!prompt.empty() && prompt.front() == vc.token_prev) new_past.insert(new_past.end(), prompt.begin() + 1, prompt.end() - n_prompt_init);
-    for (int i = 0; i < best.result_len && i < (int)tk.size(); ++i) new_past.push_back(tk[i].id);
-    it.prompt_past.swap(new_past);
-    const int seek = it.seek;
-    if (!tk.empty()) {
-        int i0 = 0;
-        int64_t t0 = seek + 2 * (tk.front().tid - vc.token_beg);
-        std::string text;
-        for (int i = 0; i < (int)tk.size(); ++i) {
-            if (p.print_special || tk[i].id < vc.token_eot) text += vc.id_to_token[tk[i].id];
-            if (tk[i].id > vc.token_beg && !p.single_segment) {
-                const int64_t t1 = seek + 2 * (tk[i].tid - vc.token_beg);
-                if (!text.empty()) {
-                    Segment s;
-                    s.t0 = t0;
-                    s.t1 = t1;
-                    s.text = text;
-                    for (int j = i0; j <= i; ++j) s.tokens.push_back(tk[j]);
-                    it.segments.push_back(std::move(s));
-                }
-                text.clear();
-                while (i < (int)tk.size() && tk[i].id > vc.token_beg) i++;
-                i--;
-                t0 = t1;
-                i0 = i + 1;
-            }
-        }
-        if (!text.empty()) {
-            Segment s;
-            s.t0 = t0;
-            s.t1 = seek + best.seek_delta;
-            s.text = text;
-            for (int j = i0; j < (int)tk.size(); ++j) s.tokens.push_back(tk[j]);
-            it.segments.push_back(std::move(s));
-        }
-    }
-    it.seek += best.seek_delta;
-}
-
-// host side of one sampled token (A.7, t > 0): std::discrete_distribution over the row's probabilities
-TokenData sample_on_host(const Vocab& vc, const float* probs, const float* logprobs, std::mt19937& rng) {
-    TokenData r;
-    {
-        double sum_ts = 0.0, max_ts = 0.0;
-        for (int i = vc.token_beg; i < vc.n_vocab; ++i) {
-            sum_ts += probs[i];
-            if (max_ts < probs[i]) {
-                max_ts = probs[i];
-                r.tid = i;
-            }
-        }
-        r.pt = (float)(max_ts / (sum_ts + 1e-10));
-        r.ptsum = (float)sum_ts;
-    }
-    std::discrete_distribution<> dist(probs, probs + vc.n_vocab);
-    r.id = dist(rng);
-    r.p = probs[r.id];
-    r.plog = logprobs[r.id];
-    if (r.id >= vc.token_beg) {
-        r.tid = r.id;
-        r.pt = r.p;
-    }
-    return r;
-}
-
-}  // namespace
-
-static int decode_pass(oh_state* st, const oh_full_params& p, bool no_timestamps, const std::vector<PassRow>& rows_in, float temperature,
-                       std::vector<PassResult>& out) {
-    const Model& m = *st->ctx->model;
-    const Vocab& vc = m.vocab;
-    const int rows = (int)rows_in.size();
-    const int n_max = m.hp.n_text_ctx / 2 - 4;
-    SeqLayout lay(st->max_batch);
-    int32_t* hb = (int32_t*)st->pinned;
-    DecodeSeqState hs = seq_view(hb, lay);
-    memset(hb, 0, lay.total_words * 4);
-    int max_prompt = 0;
-    for (int r = 0; r < rows; ++r) {
-        const PassRow& pr = rows_in[r];
-        const Item& it = st->items[pr.item];
-        const int pl = (int)pr.prompt.size();
-        if (pl > kMaxPrompt || pl < 1) {
-            set_error("prompt too long");
-            return OH_ERR_DECODE;
-        }
-        max_prompt = std::max(max_prompt, pl);
-        hs.slot[r] = pr.slot;
-        hs.active[r] = 1;
-        hs.pos[r] = 0;
-        hs.cur_token[r] = pr.prompt[0];
-        hs.prompt_len[r] = pl;
-        for (int i = 0; i < pl; ++i) hs.prompt[(size_t)r * kMaxPrompt + i] = pr.prompt[i];
-        hs.seek_delta[r] = 100 * 30;
-        hs.seek[r] = it.seek;
-        hs.seek_end[r] = it.seek_end;
-    }
-    *hs.n_active_total = rows;
-    DecodeRules R;
-    R.n_vocab = vc.n_vocab; R.eot = vc.token_eot; R.sot = vc.token_sot; R.translate = vc.token_translate; R.transcribe = vc.token_transcribe;
-    R.solm = vc.token_solm; R.prev = vc.token_prev; R.nosp = vc.token_nosp; R.tok_not = vc.token_not; R.beg = vc.token_beg;
-    R.blank = vc.token_blank; R.n_lang = vc.num_languages();
-    R.no_timestamps = no_timestamps; R.suppress_blank = p.suppress_blank; R.single_segment = p.single_segment; R.max_tokens = p.max_tokens;
-    R.n_max = n_max;
-    R.tid0_initial = p.max_initial_ts > 0.0f ? (int)std::round(p.max_initial_ts / (30.0f / (float)m.hp.n_audio_ctx)) : -1;
-    R.temperature = temperature;
-    cudaStream_t s = st->stream;
-    OH_CUDA_CHECK(cudaMemcpyAsync(st->seq_dev.p, hb, lay.total_words * 4, cudaMemcpyHostToDevice, s));
-    OH_CUDA_CHECK(cudaMemcpyAsync(st->rules_dev.p, &R, sizeof R, cudaMemcpyHostToDevice, s));
-    st->timings.h2d_bytes += (long long)lay.total_words * 4 + (long long)sizeof R;
-    OH_CUDA_CHECK(cudaStreamSynchronize(s));  // R and hb are reused below
-
-    const int max_steps = max_prompt + n_max - 1;
-    int rc;
-    if (temperature < 1e-6f) {
-        int* counter = (int*)((char*)st->pinned + lay.total_words * 4 + 64);
-        for (int step = 0; step < max_steps; ++step) {
-            if ((rc = run_decode_step_graph(st, rows))) return rc;
-            st->timings.n_decode_steps++;
-            if ((step & 3) == 3 || step == max_steps - 1) {
-                OH_CUDA_CHECK(cudaMemcpyAsync(counter, st->seq.n_active_total, 4, cudaMemcpyDeviceToHost, s));
-                st->timings.d2h_bytes += 4;
-                OH_CUDA_CHECK(cudaStreamSynchronize(s));
-                if (*counter <= 0) break;
-            }
-        }
-        OH_CUDA_CHECK(cudaMemcpyAsync(hb, st->seq_dev.p, lay.total_words * 4, cudaMemcpyDeviceToHost, s));
-        st->timings.d2h_bytes += (long long)lay.total_words * 4;
-        OH_CUDA_CHECK(cudaStreamSynchronize(s));
-    } else {
-        // t > 0: probabilities come back to the host and are sampled with the same libstdc++ calls as upstream
-        std::vector<float> probs((size_t)rows * st->ld_logits), logprobs((size_t)rows * st->ld_logits);
-        int n_live = rows;
-        for (int step = 0; step < max_steps && n_live > 0; ++step) {
-            if ((rc = decode_step_all(st, rows, true, true))) return rc;
-            st->timings.n_decode_steps++;
-            OH_CUDA_CHECK(cudaMemcpyAsync(probs.data(), st->dump_p.p, probs.size() * 4, cudaMemcpyDeviceToHost, s));
-            OH_CUDA_CHECK(cudaMemcpyAsync(logprobs.data(), st->dump_lp.p, logprobs.size() * 4, cudaMemcpyDeviceToHost, s));
-            st->timings.d2h_bytes += (long long)probs.size() * 8;
-            OH_CUDA_CHECK(cudaStreamSynchronize(s));
-            for (int r = 0; r < rows; ++r) {
-                if (!hs.active[r]) continue;
-                const int pos = hs.pos[r];
-                if (pos + 1 < hs.prompt_len[r]) {  // mirrors the kernel's prompt feeding
-                    hs.pos[r] = pos + 1;
-                    hs.cur_token[r] = hs.prompt[(size_t)r * kMaxPrompt + pos + 1];
-                    continue;
-                }
-                TokenData t = sample_on_host(vc, probs.data() + (size_t)r * st->ld_logits, logprobs.data() + (size_t)r * st->ld_logits,
-                                             st->rngs[hs.slot[r]]);
-                const int i = hs.n_gen[r];
-                const size_t o = (size_t)r * kMaxGen + i;
-                hs.tok_id[o] = t.id; hs.tok_tid[o] = t.tid; hs.tok_p[o] = t.p; hs.tok_plog[o] = t.plog; hs.tok_pt[o] = t.pt; hs.tok_ptsum[o] = t.ptsum;
-                hs.n_gen[r] = i + 1;
-                SeqFlags f{hs.has_ts[r], hs.seek_delta[r], hs.result_len[r], 0, 0};
-                const bool live = apply_token_rules(f, t.id, i, hs.seek[r], hs.seek_end[r], vc.token_beg, vc.token_eot, p.max_tokens, no_timestamps,
-                                                    p.single_segment, n_max);
-                hs.has_ts[r] = f.has_ts; hs.seek_delta[r] = f.seek_delta; hs.result_len[r] = f.result_len;
-                hs.failed[r] = f.failed; hs.completed[r] = f.completed;
-                if (live) {
-                    hs.cur_token[r] = t.id;
-                    hs.pos[r] = pos + 1;
-                } else {
-                    hs.active[r] = 0;
-                    n_live--;
-                }
-            }
-            // scalars + token ids (the kernel reads the last two sampled ids)
-            OH_CUDA_CHECK(cudaMemcpyAsync(st->seq_dev.p, hb, (lay.tok_off[1]) * 4, cudaMemcpyHostToDevice, s));
-            st->timings.h2d_bytes += (long long)lay.tok_off[1] * 4;
-            OH_CUDA_CHECK(cudaStreamSynchronize(s));
-        }
-    }
-    out.assign(rows, PassResult());
-    for (int r = 0; r < rows; ++r) {
-        PassResult& pr = out[r];
-        const int ng = hs.n_gen[r];
-        pr.tokens.resize(ng);
-        for (int i = 0; i < ng; ++i) {
-            const size_t o = (size_t)r * kMaxGen + i;
-            pr.tokens[i] = TokenData{hs.tok_id[o], hs.tok_tid[o], hs.tok_p[o], hs.tok_plog[o], hs.tok_pt[o], hs.tok_ptsum[o]};
-        }
-        pr.result_len = hs.result_len[r];
-        pr.seek_delta = hs.seek_delta[r];
-        pr.has_ts = hs.has_ts[r];
-        pr.failed = hs.failed[r];
-        pr.completed = hs.completed[r];
-        st->timings.n_tokens += ng;
-    }
-    return OH_OK;
-}
-
-// ------------------------------------------------------------------------------------------------ beam search
-// BASELINE config 4 / A.7 "Beam".  The reference never selects it (/root/reference/src/engine/whisper.rs:243 hard-codes
-// Greedy) and the pinned upstream's candidate sampler cannot be verified offline, so this follows SURVEY.md A.5/A.7
-// as written — per live decoder the top beam_size ids of the filtered distribution, candidates ranked by
-// sum_logprobs_all, assigned to the decoders in order skipping repeats, KV cache inherited from the proposing decoder
-// — decision for decision the same procedure the test oracle restates.  It is a host-driven lock-step loop over
-// beam_size decoder rows (the K9 kernel runs in "dump" mode: rules + log-softmax on the device, the distributions come
-// back to the host); items and windows are processed one after the other.  Correctness path, not a throughput path.
-namespace {
-
-struct BeamDec {
-    std::vector<TokenData> tokens;
-    int seek_delta = 100 * 30, result_len = 0, slot = 0;
-    bool has_ts = false, failed = false, completed = false;
-    double sum_logprobs_all = 0.0;
-    std::vector<float> probs, logprobs;
-};
-struct BeamCand {
-    int decoder_idx, seek_delta, result_len;
-    bool has_ts;
-    std::vector<TokenData> tokens;
-    double sum_logprobs_all;
-};
-
-// the k most probable ids, best first (ties: lower id); tid / pt / ptsum as for every sampled token (A.7)
-std::vector<TokenData> topk_on_host(const Vocab& vc, const float* probs, const float* logprobs, int k) {
-    TokenData base;
-    {
-        double sum_ts = 0.0, max_ts = 0.0;
-        for (int i = vc.token_beg; i < vc.n_vocab; ++i) {
-            sum_ts += probs[i];
-            if (max_ts < probs[i]) {
-                max_ts = probs[i];
-                base.tid = i;
-            }
-        }
-        base.pt = (float)(max_ts / (sum_ts + 1e-10));
-        base.ptsum = (float)sum_ts;
-    }
-    std::vector<int> ids(vc.n_vocab);
-    for (int i = 0; i < vc.n_vocab; ++i) ids[i] = i;
-    k = std::min(k, vc.n_vocab);
-    std::partial_sort(ids.begin(), ids.begin() + k, ids.end(), [&](int a, int b) {
-        if (logprobs[a] != logprobs[b]) return logprobs[a] > logprobs[b];
-        return a < b;
-    });
-    std::vector<TokenData> out;
-    for (int c = 0; c < k; ++c) {
-        TokenData r = base;
-        r.id = ids[c];
-        r.p = probs[r.id];
-        r.plog = logprobs[r.id];
-        if (r.id >= vc.token_beg) {
-            r.tid = r.id;
-            r.pt = r.p;
-        }
-        out.push_back(r);
-    }
-    return out;
-}
-
-int copy_self_kv(oh_state* st, int src_slot, int dst_slot) {
-    const HParams& hp = st->ctx->model->hp;
-    const size_t per_slot = (size_t)hp.n_text_ctx * hp.n_text_state * st->esz;
-    for (int l = 0; l < hp.n_text_layer; ++l) {
-        const size_t base = (size_t)l * st->max_batch * per_slot;
-        OH_CUDA_CHECK(cudaMemcpyAsync((char*)st->kself.p + base + dst_slot * per_slot, (char*)st->kself.p + base + src_slot * per_slot, per_slot,
-                                      cudaMemcpyDeviceToDevice, st->stream));
-        OH_CUDA_CHECK(cudaMemcpyAsync((char*)st->vself.p + base + dst_slot * per_slot, (char*)st->vself.p + base + src_slot * per_slot, per_slot,
-                                      cudaMemcpyDeviceToDevice, st->stream));
-    }
-    return OH_OK;
-}
-int copy_cross_kv(oh_state* st, int src_slot, int dst_slot) {
-    const HParams& hp = st->ctx->model->hp;
-    const size_t per_slot = (size_t)hp.n_audio_ctx * 2 * hp.n_text_state * st->esz;
-    for (int l = 0; l < hp.n_text_layer; ++l) {
-        const size_t base = (size_t)l * st->max_batch * per_slot;
-        OH_CUDA_CHECK(cudaMemcpyAsync((char*)st->xkv.p + base + dst_slot * per_slot, (char*)st->xkv.p + base + src_slot * per_slot, per_slot,
-                                      cudaMemcpyDeviceToDevice, st->stream));
-    }
-    return OH_OK;
-}
-
-// one window, temperature 0, nb decoders on rows / slots 0..nb-1 (cross K/V of the window already in every slot)
-int beam_pass(oh_state* st, const oh_full_params& p, bool no_timestamps, const Item& it, const std::vector<int>& prompt, int nb, PassResult& best) {
-    const Model& m = *st->ctx->model;
-    const Vocab& vc = m.vocab;
-    const int n_max = m.hp.n_text_ctx / 2 - 4;
-    const int pl = (int)prompt.size();
-    if (pl > kMaxPrompt || pl < 1) {
-        set_error("prompt too long");
-        return OH_ERR_DECODE;
-    }
-    SeqLayout lay(st->max_batch);
-    int32_t* hb = (int32_t*)st->pinned;
-    DecodeSeqState hs = seq_view(hb, lay);
-    memset(hb, 0, lay.total_words * 4);
-    for (int r = 0; r < nb; ++r) {
-        hs.slot[r] = r;
-        hs.prompt_len[r] = pl;
-        for (int i = 0; i < pl; ++i) hs.prompt[(size_t)r * kMaxPrompt + i] = prompt[i];
-        hs.seek_delta[r] = 100 * 30;
-        hs.seek[r] = it.seek;
-        hs.seek_end[r] = it.seek_end;
-    }
-    hs.active[0] = 1;
-    hs.cur_token[0] = prompt[0];
-    DecodeRules R;
-    R.n_vocab = vc.n_vocab; R.eot = vc.token_eot; R.sot = vc.token_sot; R.translate = vc.token_translate; R.transcribe = vc.token_transcribe;
-    R.solm = vc.token_solm; R.prev = vc.token_prev; R.nosp = vc.token_nosp; R.tok_not = vc.token_not; R.beg = vc.token_beg;
-    R.blank = vc.token_blank; R.n_lang = vc.num_languages();
-    R.no_timestamps = no_timestamps; R.suppress_blank = p.suppress_blank; R.single_segment = p.single_segment; R.max_tokens = p.max_tokens;
-    R.n_max = n_max;
-    R.tid0_initial = p.max_initial_ts > 0.0f ? (int)std::round(p.max_initial_ts / (30.0f / (float)m.hp.n_audio_ctx)) : -1;
-    R.temperature = 0.0f;
-    cudaStream_t s = st->stream;
-    OH_CUDA_CHECK(cudaMemcpyAsync(st->seq_dev.p, hb, lay.total_words * 4, cudaMemcpyHostToDevice, s));
-    OH_CUDA_CHECK(cudaMemcpyAsync(st->rules_dev.p, &R, sizeof R, cudaMemcpyHostToDevice, s));
-    OH_CUDA_CHECK(cudaStreamSynchronize(s));
-    const size_t ld = st->ld_logits;
-    int rc;
-    auto upload_rows = [&]() -> int {  // scalars, prompts and sampled-token ids (the kernel reads the last two ids of a row)
-        OH_CUDA_CHECK(cudaMemcpyAsync(st->seq_dev.p, hb, lay.tok_off[1] * 4, cudaMemcpyHostToDevice, s));
-        st->timings.h2d_bytes += (long long)lay.tok_off[1] * 4;
-        return OH_OK;
-    };
-    // the prompt through decoder 0 (A.5: "decode(prompt) -> process_logits(decoder0, is_initial)")
-    // (the kernel advances pos / cur_token through the prompt on the device by itself; the pinned host mirror must not be
-    // touched while an asynchronous upload of it could still be in flight, so nothing is uploaded in this phase)
-    for (int i = 0; i < pl; ++i) {
-        if ((rc = decode_step_all(st, nb, true, true))) return rc;
-        st->timings.n_decode_steps++;
-    }
-    hs.pos[0] = pl - 1;
-    hs.cur_token[0] = prompt[pl - 1];
-    std::vector<BeamDec> dec(nb);
-    dec[0].probs.resize(ld);
-    dec[0].logprobs.resize(ld);
-    OH_CUDA_CHECK(cudaMemcpyAsync(dec[0].probs.data(), st->dump_p.p, ld * 4, cudaMemcpyDeviceToHost, s));
-    OH_CUDA_CHECK(cudaMemcpyAsync(dec[0].logprobs.data(), st->dump_lp.p, ld * 4, cudaMemcpyDeviceToHost, s));
-    st->timings.d2h_bytes += (long long)ld * 8;
-    for (int j = 1; j < nb; ++j)  // "copy logits/probs/kv to the other decoders"
-        if ((rc = copy_self_kv(st, 0, j))) return rc;
-    OH_CUDA_CHECK(cudaStreamSynchronize(s));
-    for (int j = 0; j < nb; ++j) {
-        dec[j].slot = j;
-        if (j > 0) {
-            dec[j].probs = dec[0].probs;
-            dec[j].logprobs = dec[0].logprobs;
-        }
-    }
-
-    for (int i = 0; i < n_max; ++i) {
-        // ---- candidates of every live decoder, ranked
-        std::vector<BeamCand> cands;
-        for (int j = 0; j < nb; ++j) {
-            BeamDec& d = dec[j];
-            if (d.completed || d.failed) continue;
-            for (const TokenData& tok : topk_on_host(vc, d.probs.data(), d.logprobs.data(), nb)) {
-                BeamCand c{j, d.seek_delta, d.result_len, d.has_ts, d.tokens, d.sum_logprobs_all + tok.plog};
-                c.tokens.push_back(tok);
-                cands.push_back(std::move(c));
-            }
-        }
-        std::stable_sort(cands.begin(), cands.end(), [](const BeamCand& a, const BeamCand& b) {
-            if (a.sum_logprobs_all != b.sum_logprobs_all) return a.sum_logprobs_all > b.sum_logprobs_all;
-            return a.decoder_idx < b.decoder_idx;
-        });
-        auto same_tokens = [](const BeamCand& a, const BeamCand& b) {
-            if (a.tokens.size() != b.tokens.size()) return false;
-            for (size_t q = 0; q < a.tokens.size(); ++q)
-                if (a.tokens[q].id != b.tokens[q].id) return false;
-            return true;
-        };
-        std::vector<int> take(nb, -1);
-        size_t cur_c = 0;
-        for (int j = 0; j < nb; ++j) {
-            if (dec[j].completed || dec[j].failed) continue;
-            if (cur_c >= cands.size()) cur_c = 0;
-            const size_t pick = cur_c++;
-            while (cur_c < cands.size() && i > 0 && same_tokens(cands[cur_c], cands[pick])) ++cur_c;
-            take[j] = (int)pick;
-        }
-        // ---- KV caches follow the candidates: a cache moves with its slot index; only a cache that two decoders inherit
-        // (or that its owner keeps while another decoder inherits it) is copied, into the slot of a decoder that nobody follows
-        std::vector<int> old_slot(nb), new_slot(nb, -1);
-        std::vector<char> claimed(st->max_batch, 0);
-        for (int j = 0; j < nb; ++j) old_slot[j] = dec[j].slot;
-        for (int j = 0; j < nb; ++j)
-            if (take[j] >= 0 && cands[take[j]].decoder_idx == j) {
-                new_slot[j] = old_slot[j];
-                claimed[old_slot[j]] = 1;
-            }
-        for (int j = 0; j < nb; ++j)
-            if (take[j] >= 0 && new_slot[j] < 0) {
-                const int src = old_slot[cands[take[j]].decoder_idx];
-                if (!claimed[src]) {
-                    new_slot[j] = src;
-                    claimed[src] = 1;
-                }
-            }
-        for (int j = 0; j < nb; ++j)
-            if (take[j] >= 0 && new_slot[j] < 0) {
-                int f = -1;
-                for (int q = 0; q < nb; ++q)
-                    if (!claimed[old_slot[q]]) {
-                        f = old_slot[q];
-                        break;
-                    }
-                if (f < 0) {
-                    set_error("beam search: no free KV slot");
-                    return OH_ERR_DECODE;
-                }
-                if ((rc = copy_self_kv(st, old_slot[cands[take[j]].decoder_idx], f))) return rc;
-                new_slot[j] = f;
-                claimed[f] = 1;
-            }
-        {   // decoders that are finished keep distinct (unused) slots
-            int q = 0;
-            for (int j = 0; j < nb; ++j)
-                if (new_slot[j] < 0) {
-                    while (claimed[old_slot[q]]) ++q;
-                    new_slot[j] = old_slot[q];
-                    claimed[old_slot[q]] = 1;
-                }
-        }
-        for (int j = 0; j < nb; ++j) {
-            dec[j].slot = new_slot[j];
-            if (take[j] < 0) continue;
-            const BeamCand& c = cands[take[j]];
-            dec[j].tokens = c.tokens;
-            dec[j].seek_delta = c.seek_delta;
-            dec[j].has_ts = c.has_ts;
-            dec[j].result_len = c.result_len;
-            dec[j].sum_logprobs_all = c.sum_logprobs_all;
-        }
-        // ---- A.5 bookkeeping for the token each live decoder ended up with
-        bool all_done = true;
-        for (int j = 0; j < nb; ++j) {
-            BeamDec& d = dec[j];
-            if (d.completed || d.failed) continue;
-            SeqFlags f{d.has_ts ? 1 : 0, d.seek_delta, d.result_len, 0, 0};
-            apply_token_rules(f, d.tokens.back().id, i, it.seek, it.seek_end, vc.token_beg, vc.token_eot, p.max_tokens, no_timestamps, p.single_segment,
-                              n_max);
-            d.has_ts = f.has_ts != 0;
-            d.seek_delta = f.seek_delta;
-            d.result_len = f.result_len;
-            d.failed = f.failed != 0;
-            d.completed = f.completed != 0;
-            if (!d.completed && !d.failed) all_done = false;
-        }
-        if (all_done || i + 1 == n_max) break;
-        // ---- one token per live decoder
-        for (int j = 0; j < nb; ++j) {
-            const BeamDec& d = dec[j];
-            const bool live = !d.completed && !d.failed;
-            hs.active[j] = live ? 1 : 0;
-            hs.slot[j] = d.slot;
-            if (!live) continue;
-            hs.pos[j] = pl + i;
-            hs.cur_token[j] = d.tokens.back().id;
-            hs.n_gen[j] = (int)d.tokens.size();
-            hs.has_ts[j] = d.has_ts ? 1 : 0;
-            hs.seek_delta[j] = d.seek_delta;
-            hs.result_len[j] = d.result_len;
-            for (size_t q = 0; q < d.tokens.size(); ++q) hs.tok_id[(size_t)j * kMaxGen + q] = d.tokens[q].id;
-        }
-        if ((rc = upload_rows())) return rc;
-        if ((rc = decode_step_all(st, nb, true, true))) return rc;
-        st->timings.n_decode_steps++;
-        for (int j = 0; j < nb; ++j) {
-            BeamDec& d = dec[j];
-            if (d.completed || d.failed) continue;
-            d.probs.resize(ld);
-            d.logprobs.resize(ld);
-            OH_CUDA_CHECK(cudaMemcpyAsync(d.probs.data(), (float*)st->dump_p.p + (size_t)j * ld, ld * 4, cudaMemcpyDeviceToHost, s));
-            OH_CUDA_CHECK(cudaMemcpyAsync(d.logprobs.data(), (float*)st->dump_lp.p + (size_t)j * ld, ld * 4, cudaMemcpyDeviceToHost, s));
-            st->timings.d2h_bytes += (long long)ld * 8;
-        }
-        OH_CUDA_CHECK(cudaStreamSynchronize(s));
-    }
-    // ---- rank the decoders (A.5 / A.8): first best score among the ones that did not fail
-    double best_score = -INFINITY;
-    int best_id = 0;
-    std::vector<PassResult> res(nb);
-    for (int j = 0; j < nb; ++j) {
-        PassResult& r = res[j];
-        const BeamDec& d = dec[j];
-        r.tokens = d.tokens;
-        r.result_len = d.result_len;
-        r.seek_delta = d.seek_delta;
-        r.has_ts = d.has_ts;
-        r.failed = d.failed;
-        r.completed = d.completed;
-        if (r.failed) continue;
-        r.tokens.resize(std::min<size_t>(r.tokens.size(), (size_t)r.result_len));
-        sequence_score(p, r);
-        if (r.result_len > 32 && r.entropy < p.entropy_thold) {
-            r.failed = true;
-            continue;
-        }
-        if (best_score < r.score) {
-            best_score = r.score;
-            best_id = j;
-        }
-    }
-    best = res[best_id];
-    for (const BeamDec& d : dec) st->timings.n_tokens += (int)d.tokens.size();
-    return OH_OK;
-}
-
-}  // namespace
-
-// full() for strategy = BEAM_SEARCH: items one after the other, windows in order (A.5), beam_size decoder rows
-static int run_full_beam(oh_state* st, const oh_full_params& p, int batch, const std::vector<float>& temperatures, const std::vector<int>& prompt_init,
-                         bool no_timestamps, const ClipMeta& cm, std::chrono::steady_clock::time_point t_begin, long long launches0) {
-    using clk = std::chrono::steady_clock;
-    const Model& m = *st->ctx->model;
-    const Vocab& vc = m.vocab;
-    const HParams& hp = m.hp;
-    const int nb = std::max(1, p.beam_size);
-    if (nb > st->max_batch) {
-        set_error("beam search needs oh_context_params.max_batch >= beam_size (one KV-cache slot per beam)");
-        return OH_ERR_INVALID;
-    }
-    cudaStream_t s = st->stream;
-    int rc;
-    auto build_prompt = [&](const Item& it, float t_cur, std::vector<int>& prompt) {
-        prompt.clear();
-        if (!it.prompt_past.empty() && t_cur < 0.5f && p.n_max_text_ctx > 0) {
-            const int n_take = std::min(std::min(p.n_max_text_ctx, hp.n_text_ctx / 2), (int)it.prompt_past.size());
-            prompt.push_back(vc.token_prev);
-            prompt.insert(prompt.end(), it.prompt_past.end() - n_take, it.prompt_past.end());
-        }
-        prompt.insert(prompt.end(), prompt_init.begin(), prompt_init.end());
-    };
-    for (int i = 0; i < batch; ++i) {
-        Item& it = st->items[i];
-        while (!it.done) {
-            if (it.seek + 100 >= it.seek_end) {
-                it.done = true;
-                break;
-            }
-            // ---- encode the window into slot 0, then give every beam its own copy of the cross K/V
-            auto t0 = clk::now();
-            const int slot0 = 0;
-            OH_CUDA_CHECK(cudaMemcpyAsync(cm.clip_of_slot, &i, 4, cudaMemcpyHostToDevice, s));
-            OH_CUDA_CHECK(cudaMemcpyAsync(cm.seek_of_slot, &it.seek, 4, cudaMemcpyHostToDevice, s));
-            WindowGatherArgs wa;
-            wa.raw = (const float*)st->mel_raw.p;
-            wa.ld = st->mel_ld;
-            wa.n_mel = hp.n_mels;
-            wa.max_key = cm.max_key;
-            wa.n_active = cm.n_active;
-            wa.n_len = cm.n_len;
-            wa.clip_of_slot = cm.clip_of_slot;
-            wa.seek_of_slot = cm.seek_of_slot;
-            if ((rc = launch_window_gather(wa, 1, st->xin.p, st->ctx->act_type, s))) return rc == OH_ERR_CUDA ? rc : OH_ERR_ENCODE;
-            if ((rc = run_encoder(st, 1, 0, nullptr, &slot0))) return rc == OH_ERR_CUDA ? rc : OH_ERR_ENCODE;
-            for (int j = 1; j < nb; ++j)
-                if ((rc = copy_cross_kv(st, 0, j))) return rc;
-            OH_CUDA_CHECK(cudaStreamSynchronize(s));  // &i / &it.seek were read by the copies above
-            st->timings.n_windows++;
-            st->timings.encode_ms += std::chrono::duration<float, std::milli>(clk::now() - t0).count();
-            if (it.seek > 0 && it.seek + 500 >= it.seek_end) it.prompt_past.clear();  // short tail: drop the prompt (upstream behaviour)
-
-            auto t1 = clk::now();
-            PassResult best;
-            std::vector<int> prompt;
-            for (size_t ti = 0; ti < temperatures.size(); ++ti) {
-                const float t_cur = temperatures[ti];
-                build_prompt(it, t_cur, prompt);
-                if (t_cur <= 0.0f) {
-                    if ((rc = beam_pass(st, p, no_timestamps, it, prompt, nb, best))) return rc == OH_ERR_CUDA ? rc : OH_ERR_DECODE;
-                } else {
-                    // A.5: BEAM at t > 0 runs best_of decoders with sampling; best_of defaults to -1 for this strategy -> one decoder
-                    std::vector<PassRow> rows = {PassRow{i, 0, prompt}};
-                    std::vector<PassResult> res;
-                    if ((rc = decode_pass(st, p, no_timestamps, rows, t_cur, res))) return rc == OH_ERR_CUDA ? rc : OH_ERR_DECODE;
-                    best = res[0];
-                    if (!best.failed) {
-                        best.tokens.resize(std::min<size_t>(best.tokens.size(), (size_t)best.result_len));
-                        sequence_score(p, best);
-                        if (best.result_len > 32 && best.entropy < p.entropy_thold) best.failed = true;
-                    }
-                }
-                if (ti + 1 != temperatures.size() && (best.failed || best.avg_logprobs < p.logprob_thold)) {
-                    st->timings.n_fallbacks++;
-                    continue;
-                }
-                break;
-            }
-            emit_segments(m, p, it, best, prompt, (int)prompt_init.size());
-            st->timings.decode_ms += std::chrono::duration<float, std::milli>(clk::now() - t1).count();
-        }
-    }
-    st->timings.total_ms = std::chrono::duration<float, std::milli>(clk::now() - t_begin).count();
-    st->timings.n_kernel_launches = g_launch_count - launches0;
-    return OH_OK;
-}
-
-int run_full(oh_state* st, const oh_full_params& p, const float* const* pcm, const int* n, int batch, bool pcm_on_device) {
-    using clk = std::chrono::steady_clock;
-    const Model& m = *st->ctx->model;
-    const Vocab& vc = m.vocab;
-    const HParams& hp = m.hp;
-    if (batch < 1) {
-        set_error("empty batch");
-        return OH_ERR_INVALID;
-    }
-    if (p.strategy != OH_SAMPLING_GREEDY && p.strategy != OH_SAMPLING_BEAM_SEARCH) {
-        set_error("unknown sampling strategy");
-        return OH_ERR_UNSUPPORTED;
-    }
-    if (p.suppress_non_speech_tokens || p.offset_ms != 0 || p.duration_ms != 0) {
-        set_error("unsupported oh_full_params (suppress_non_speech_tokens / offset_ms / duration_ms)");
-        return OH_ERR_UNSUPPORTED;
-    }
-    st->timings = oh_timings{};
-    const long long launches0 = g_launch_count;
-    auto t_begin = clk::now();
-    cudaStream_t s = st->stream;
-    int rc;
-
-    // the prompts of earlier calls survive only with no_context = false
-    std::vector<std::vector<int>> carried(batch);
-    if (!p.no_context)
-        for (int i = 0; i < batch && i < (int)st->items.size(); ++i) carried[i] = st->items[i].prompt_past;
-
-    if ((rc = run_mel(st, pcm, n, batch, pcm_on_device))) return rc;
-    OH_CUDA_CHECK(cudaStreamSynchronize(s));
-    auto t_mel = clk::now();
-    st->timings.mel_ms = std::chrono::duration<float, std::milli>(t_mel - t_begin).count();
-
-    std::vector<float> temperatures;
-    if (p.temperature_inc > 0.0f) {
-        for (float t = p.temperature; t < 1.0f + 1e-6f; t += p.temperature_inc) temperatures.push_back(t);
-    } else {
-        temperatures.push_back(p.temperature);
-    }
-    std::vector<int> prompt_init = {vc.token_sot};
-    bool no_timestamps = p.no_timestamps != 0;
-    int lang_id = 0;
-    if (vc.is_multilingual()) {
-        const char* lang = (p.language && strcmp(p.language, "auto") != 0 && p.language[0]) ? p.language : "en";
-        lang_id = lang_id_from_code(lang);
-        if (lang_id < 0 || lang_id >= vc.num_languages()) lang_id = 0;
-        prompt_init.push_back(vc.token_sot + 1 + lang_id);
-        prompt_init.push_back(p.translate ? vc.token_translate : vc.token_transcribe);
-    }
-    if (hp.n_text_layer == 2 && hp.n_vocab != 51866) no_timestamps = true;  // "distilled" heuristic (A.1)
-    if (no_timestamps) prompt_init.push_back(vc.token_not);
-
-    for (int i = 0; i < batch; ++i) {
-        Item& it = st->items[i];
-        it.lang_id = lang_id;
-        it.prompt_past = carried[i];
-        it.seek = 0;
-        it.seek_end = it.n_len_org;
-        if (!it.done && it.seek_end < 100) it.done = true;  // < 1 s: no segments, rc 0 (A.3 step 7)
-    }
-
-    ClipMeta cm = clip_meta_view(st->clip_meta.p, std::max<size_t>(batch, st->max_batch));
-    if (p.strategy == OH_SAMPLING_BEAM_SEARCH) return run_full_beam(st, p, batch, temperatures, prompt_init, no_timestamps, cm, t_begin, launches0);
-
-    // ------------------------------------------------------------------------------------------------------------
-    // Scheduler.  Every KV-cache slot is one decoder row.  Windows are admitted to free slots (encoder pass over the
-    // admitted windows, cross-KV straight into their slots), rows decode greedily under the device state machine, and
-    // every CHECK steps the host looks at the `active` flags: a finished row is scored, its segments are emitted, its
-    // item's seek advances, and the item's next window (A.5: windows of one call are sequentially dependent) is queued
-    // for admission while the other rows keep decoding — rows never wait for the slowest row of a "round".
-    // Rows that need a temperature fallback are parked and resolved together once the greedy rows have drained.
-    // ------------------------------------------------------------------------------------------------------------
-    struct SlotInfo {
-        int item = -1;
-        bool armed = false;
-        std::vector<int> prompt;
-    };
-    const int nslots = std::min(batch, st->max_batch);  // more items than slots: items queue for a free slot
-    const int n_max = hp.n_text_ctx / 2 - 4;
-    const bool lockstep = getenv("OH_SCHED") && strcmp(getenv("OH_SCHED"), "lockstep") == 0;
-    // host look-in period (steps) and the number of waiting windows that triggers an encoder pass while rows are decoding
-    const int CHECK = getenv("OH_CHECK") ? std::max(1, atoi(getenv("OH_CHECK"))) : 8;
-    const int admit_threshold = lockstep ? nslots : (getenv("OH_ADMIT") ? std::max(1, atoi(getenv("OH_ADMIT"))) : std::max(1, std::min(8, nslots / 8)));
-    std::vector<SlotInfo> slots(nslots);
-    std::vector<int> free_slots;
-    for (int i = nslots - 1; i >= 0; --i) free_slots.push_back(i);  // pop_back yields ascending slot ids
-    std::vector<int> need_window;                                     // items whose next window awaits admission
-    for (int i = 0; i < batch; ++i) {
-        Item& it = st->items[i];
-        if (it.done) continue;
-        if (it.seek + 100 >= it.seek_end) it.done = true;
-        else need_window.push_back(i);
-    }
-    std::vector<PassRow> parked;  // rows waiting for a temperature fallback (slot stays reserved)
-    SeqLayout lay(st->max_batch);
-    int32_t* hb = (int32_t*)st->pinned;
-    DecodeSeqState hs = seq_view(hb, lay);
-    memset(hb, 0, lay.total_words * 4);
-    OH_CUDA_CHECK(cudaMemcpyAsync(st->seq_dev.p, hb, lay.total_words * 4, cudaMemcpyHostToDevice, s));
-    st->timings.h2d_bytes += (long long)lay.total_words * 4;
-    bool rules_dirty = true;
-    int n_armed = 0;
-    const size_t scalar_words = lay.prompt_off + (size_t)lay.rows * kMaxPrompt;  // scalars + prompts
-    const size_t token_words = lay.counter_off - lay.tok_off[0];
-
-    auto build_prompt = [&](const Item& it, float t_cur, std::vector<int>& prompt) {
-        prompt.clear();
-        if (!it.prompt_past.empty() && t_cur < 0.5f && p.n_max_text_ctx > 0) {
-            const int n_take = std::min(std::min(p.n_max_text_ctx, hp.n_text_ctx / 2), (int)it.prompt_past.size());
-            prompt.push_back(vc.token_prev);
-            prompt.insert(prompt.end(), it.prompt_past.end() - n_take, it.prompt_past.end());
-        }
-        prompt.insert(prompt.end(), prompt_init.begin(), prompt_init.end());
-    };
-    // accept a finished window: segments, prompt carry-over, seek advance, next window or done
-    auto finish_window = [&](int slot, const PassResult& res) {
-        SlotInfo& si = slots[slot];
-        Item& it = st->items[si.item];
-        emit_segments(m, p, it, res, si.prompt, (int)prompt_init.size());
-        if (it.seek + 100 >= it.seek_end) it.done = true;
-        else need_window.push_back(si.item);
-        si.item = -1;
-        si.armed = false;
-        free_slots.push_back(slot);
-    };
-    // score one t=0 result; returns true if it is accepted at this temperature index
-    auto evaluate = [&](PassResult& pr, size_t ti) {
-        if (!pr.failed) {
-            pr.tokens.resize(std::min<size_t>(pr.tokens.size(), (size_t)pr.result_len));
-            sequence_score(p, pr);
-            if (pr.result_len > 32 && pr.entropy < p.entropy_thold) pr.failed = true;
-        }
-        if (ti + 1 != temperatures.size() && (pr.failed || pr.avg_logprobs < p.logprob_thold)) return false;
-        return true;
-    };
-
-    while (true) {
-        // ---- admission: encode the next windows of waiting items into free slots
-        if (!need_window.empty() && !free_slots.empty() && (n_armed == 0 || (!lockstep && (int)need_window.size() >= admit_threshold))) {
-            auto t0 = clk::now();
-            const int k = (int)std::min(need_window.size(), free_slots.size());
-            std::sort(free_slots.begin(), free_slots.end(), std::greater<int>());
-            std::vector<int> win_item(need_window.begin(), need_window.begin() + k), win_slot(k), win_seek(k);
-            need_window.erase(need_window.begin(), need_window.begin() + k);
-            for (int i = 0; i < k; ++i) {
-                win_slot[i] = free_slots.back();
-                free_slots.pop_back();
-                win_seek[i] = st->items[win_item[i]].seek;
-            }
-            OH_CUDA_CHECK(cudaMemcpyAsync(cm.clip_of_slot, win_item.data(), k * 4, cudaMemcpyHostToDevice, s));
-            OH_CUDA_CHECK(cudaMemcpyAsync(cm.seek_of_slot, win_seek.data(), k * 4, cudaMemcpyHostToDevice, s));
-            for (int c0 = 0; c0 < k; c0 += st->enc_chunk) {
-                const int nw = std::min(st->enc_chunk, k - c0);
-                WindowGatherArgs wa;
-                wa.raw = (const float*)st->mel_raw.p;
-                wa.ld = st->mel_ld;
-                wa.n_mel = hp.n_mels;
-                wa.max_key = cm.max_key;
-                wa.n_active = cm.n_active;
-                wa.n_len = cm.n_len;
-                wa.clip_of_slot = cm.clip_of_slot + c0;
-                wa.seek_of_slot = cm.seek_of_slot + c0;
-                if ((rc = launch_window_gather(wa, nw, st->xin.p, st->ctx->act_type, s))) return rc == OH_ERR_CUDA ? rc : OH_ERR_ENCODE;
-                if ((rc = run_encoder(st, nw, 0, nullptr, win_slot.data() + c0))) return rc == OH_ERR_CUDA ? rc : OH_ERR_ENCODE;
-                st->timings.n_windows += nw;
-            }
-            // arm the rows (the host mirror of the scalars is current: nothing ran since the last download)
-            for (int i = 0; i < k; ++i) {
-                const int r = win_slot[i];
-                SlotInfo& si = slots[r];
-                Item& it = st->items[win_item[i]];
-                if (it.seek > 0 && it.seek + 500 >= it.seek_end) it.prompt_past.clear();  // short tail: drop the prompt (upstream behaviour)
-                si.item = win_item[i];
-                si.armed = true;
-                build_prompt(it, temperatures[0], si.prompt);
-                const int pl = (int)si.prompt.size();
-                if (pl > kMaxPrompt) {
-                    set_error("prompt too long");
-                    return OH_ERR_DECODE;
-                }
-                hs.slot[r] = r;
-                hs.active[r] = 1;
-                hs.pos[r] = 0;
-                hs.cur_token[r] = si.prompt[0];
-                hs.prompt_len[r] = pl;
-                for (int j = 0; j < pl; ++j) hs.prompt[(size_t)r * kMaxPrompt + j] = si.prompt[j];
-                hs.n_gen[r] = 0;
-                hs.has_ts[r] = 0;
-                hs.seek_delta[r] = 100 * 30;
-                hs.result_len[r] = 0;
-                hs.failed[r] = 0;
-                hs.completed[r] = 0;
-                hs.seek[r] = it.seek;
-                hs.seek_end[r] = it.seek_end;
-                st->timings.n_prompt_steps += pl - 1;
-            }
-            OH_CUDA_CHECK(cudaMemcpyAsync(st->seq_dev.p, hb, scalar_words * 4, cudaMemcpyHostToDevice, s));
-            st->timings.h2d_bytes += (long long)scalar_words * 4;
-            n_armed += k;
-            OH_CUDA_CHECK(cudaStreamSynchronize(s));
-            st->timings.encode_ms += std::chrono::duration<float, std::milli>(clk::now() - t0).count();
-        }
-        if (n_armed == 0) {
-            if (!parked.empty()) {
-                // ---- temperature fallback for the parked rows, lock-step per temperature (A.5 ladder)
-                auto t0 = clk::now();
-                std::vector<PassRow> pending;
-                pending.swap(parked);
-                for (size_t ti = 1; ti < temperatures.size() && !pending.empty(); ++ti) {
-                    for (PassRow& pr : pending) {
-                        build_prompt(st->items[pr.item], temperatures[ti], pr.prompt);
-                        slots[pr.slot].prompt = pr.prompt;
-                    }
-                    std::vector<PassResult> res;
-                    if ((rc = decode_pass(st, p, no_timestamps, pending, temperatures[ti], res))) return rc == OH_ERR_CUDA ? rc : OH_ERR_DECODE;
-                    std::vector<PassRow> next;
-                    for (size_t r = 0; r < pending.size(); ++r) {
-                        if (evaluate(res[r], ti)) finish_window(pending[r].slot, res[r]);
-                        else {
-                            st->timings.n_fallbacks++;
-                            next.push_back(pending[r]);
-                        }
-                    }
-                    pending.swap(next);
-                }
-                rules_dirty = true;
-                memset(hb, 0, lay.total_words * 4);  // decode_pass reused the block: start the greedy rows from a clean slate
-                OH_CUDA_CHECK(cudaMemcpyAsync(st->seq_dev.p, hb, lay.total_words * 4, cudaMemcpyHostToDevice, s));
-                st->timings.decode_ms += std::chrono::duration<float, std::milli>(clk::now() - t0).count();
-                continue;
-            }
-            if (need_window.empty()) break;
-            continue;  // admission fires because nothing is armed
-        }
-        // ---- CHECK greedy steps for every slot (inactive rows exit at once)
-        auto t1 = clk::now();
-        if (rules_dirty) {
-            DecodeRules R;
-            R.n_vocab = vc.n_vocab; R.eot = vc.token_eot; R.sot = vc.token_sot; R.translate = vc.token_translate; R.transcribe = vc.token_transcribe;
-            R.solm = vc.token_solm; R.prev = vc.token_prev; R.nosp = vc.token_nosp; R.tok_not = vc.token_not; R.beg = vc.token_beg;
-            R.blank = vc.token_blank; R.n_lang = vc.num_languages();
-            R.no_timestamps = no_timestamps; R.suppress_blank = p.suppress_blank; R.single_segment = p.single_segment; R.max_tokens = p.max_tokens;
-            R.n_max = n_max;
-            R.tid0_initial = p.max_initial_ts > 0.0f ? (int)std::round(p.max_initial_ts / (30.0f / (float)hp.n_audio_ctx)) : -1;
-            R.temperature = temperatures[0];
-            OH_CUDA_CHECK(cudaMemcpyAsync(st->rules_dev.p, &R, sizeof R, cudaMemcpyHostToDevice, s));
-            OH_CUDA_CHECK(cudaStreamSynchronize(s));
-            rules_dirty = false;
-        }
-        if (temperatures[0] >= 1e-6f) {
-            // a non-zero base temperature samples on the host from the first pass on: use the lock-step path for everything
-            for (int r = 0; r < nslots; ++r)
-                if (slots[r].armed) parked.push_back(PassRow{slots[r].item, r, slots[r].prompt});
-            memset(hb, 0, scalar_words * 4);
-            n_armed = 0;
-            // run them as "fallback index 0"
-            std::vector<PassRow> pending;
-            pending.swap(parked);
-            for (size_t ti = 0; ti < temperatures.size() && !pending.empty(); ++ti) {
-                for (PassRow& pr : pending) {
-                    build_prompt(st->items[pr.item], temperatures[ti], pr.prompt);
-                    slots[pr.slot].prompt = pr.prompt;
-                }
-                std::vector<PassResult> res;
-                if ((rc = decode_pass(st, p, no_timestamps, pending, temperatures[ti], res))) return rc == OH_ERR_CUDA ? rc : OH_ERR_DECODE;
-                std::vector<PassRow> next;
-                for (size_t r = 0; r < pending.size(); ++r) {
-                    if (evaluate(res[r], ti)) finish_window(pending[r].slot, res[r]);
-                    else {
-                        st->timings.n_fallbacks++;
-                        next.push_back(pending[r]);
-                    }
-                }
-                pending.swap(next);
-            }
-            rules_dirty = true;
-            memset(hb, 0, lay.total_words * 4);
-            OH_CUDA_CHECK(cudaMemcpyAsync(st->seq_dev.p, hb, lay.total_words * 4, cudaMemcpyHostToDevice, s));
-            continue;
-        }
-        for (int step = 0; step < CHECK; ++step) {
-            if ((rc = run_decode_step_graph(st, nslots))) return rc == OH_ERR_CUDA ? rc : OH_ERR_DECODE;
-            st->timings.n_decode_steps++;
-            st->timings.n_row_steps += nslots;
-        }
-        OH_CUDA_CHECK(cudaMemcpyAsync(hb, st->seq_dev.p, scalar_words * 4, cudaMemcpyDeviceToHost, s));
-        OH_CUDA_CHECK(cudaStreamSynchronize(s));
-        st->timings.d2h_bytes += (long long)scalar_words * 4;
-        bool any_finished = false;
-        for (int r = 0; r < nslots; ++r)
-            if (slots[r].armed && !hs.active[r]) any_finished = true;
-        if (any_finished) {
-            OH_CUDA_CHECK(cudaMemcpyAsync(hb + lay.tok_off[0], (int32_t*)st->seq_dev.p + lay.tok_off[0], token_words * 4, cudaMemcpyDeviceToHost, s));
-            OH_CUDA_CHECK(cudaStreamSynchronize(s));
-            st->timings.d2h_bytes += (long long)token_words * 4;
-            for (int r = 0; r < nslots; ++r) {
-                if (!slots[r].armed || hs.active[r]) continue;
-                PassResult pr;
-                const int ng = hs.n_gen[r];
-                pr.tokens.resize(ng);
-                for (int i = 0; i < ng; ++i) {
-                    const size_t o = (size_t)r * kMaxGen + i;
-                    pr.tokens[i] = TokenData{hs.tok_id[o], hs.tok_tid[o], hs.tok_p[o], hs.tok_plog[o], hs.tok_pt[o], hs.tok_ptsum[o]};
-                }
-                pr.result_len = hs.result_len[r];
-                pr.seek_delta = hs.seek_delta[r];
-                pr.has_ts = hs.has_ts[r];
-                pr.failed = hs.failed[r];
-                pr.completed = hs.completed[r];
-                st->timings.n_tokens += ng;
-                slots[r].armed = false;
-                n_armed--;
-                if (evaluate(pr, 0)) finish_window(r, pr);
-                else {
-                    st->timings.n_fallbacks++;
-                    parked.push_back(PassRow{slots[r].item, r, slots[r].prompt});
-                }
-            }
-        }
-        st->timings.decode_ms += std::chrono::duration<float, std::milli>(clk::now() - t1).count();
-    }
-    st->timings.total_ms = std::chrono::duration<float, std::milli>(clk::now() - t_begin).count();
-    st->timings.n_kernel_launches = g_launch_count - launches0;
     return OH_OK;
 }
 

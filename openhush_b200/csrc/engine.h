@@ -1,9 +1,11 @@
-// Context / state objects behind the C ABI and the batched full() driver.
+// Context / state objects behind the C ABI, the stage runners and the continuous-batching full() scheduler.
 #pragma once
+#include <chrono>
+#include <deque>
 #include <map>
-#include <set>
 #include <memory>
 #include <random>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -50,36 +52,104 @@ struct DevBuf {
     size_t bytes = 0;
 };
 
+// ---- the scheduler's objects (full.cu) ----------------------------------------------------------------------------
+// A submission is one oh_full / oh_full_batch / oh_stream_submit call: its items, their log-mel, and the decode policy
+// derived from its params.  Submissions stay live until they are waited for; windows of different live submissions share
+// the decoder rows, which is what keeps the rows full across calls.
+struct Submission {
+    int ticket = 0;
+    oh_full_params p{};
+    std::string language;  // owns p.language
+    std::vector<float> temperatures;
+    std::vector<int> prompt_init;
+    bool no_timestamps = false;
+    std::vector<Item> items;
+    std::vector<std::mt19937>* rngs = nullptr;  // per item (A.7); the blocking calls use the state's persistent generators
+    std::vector<std::mt19937> own_rngs;
+    int n_done = 0;
+    DevBuf pcm_stage, mel_raw, clip_meta;  // clip_meta: [max_key int per clip]
+    int mel_ld = 0;
+    cudaEvent_t ev_mel = nullptr;  // recorded on the front-end stream after this submission's log-mel
+    std::chrono::steady_clock::time_point t_begin;
+    bool finished() const { return n_done >= (int)items.size(); }
+};
+
+struct WinRef {  // a window of an item: waiting for the encoder, in an encoder pass, or encoded and waiting for a row
+    Submission* sub = nullptr;
+    int item = -1;
+    int slot = -1;
+};
+struct EncoderPass {
+    cudaEvent_t done = nullptr;
+    std::vector<WinRef> wins;
+};
+struct RowInfo {
+    Submission* sub = nullptr;
+    int item = -1, slot = -1;
+    bool armed = false;
+    std::vector<int> prompt;
+};
+struct ParkedRow {  // a window whose t = 0 result failed the A.5 checks: waits (with its cross K/V slot) for the temperature ladder
+    Submission* sub = nullptr;
+    int item = -1, slot = -1;
+    std::vector<int> prompt;
+};
+
+struct Sched {
+    std::deque<std::unique_ptr<Submission>> subs;  // live submissions in ticket order
+    int next_ticket = 1;
+    std::vector<int> free_slots;
+    std::vector<RowInfo> rows;
+    int n_armed = 0;
+    std::deque<WinRef> need_window;  // windows waiting for an encoder pass (continuations first)
+    std::deque<EncoderPass> passes;  // in flight on the encoder stream, oldest first
+    std::deque<WinRef> ready;        // encoded, waiting for a free row
+    std::vector<ParkedRow> parked;
+    std::vector<cudaEvent_t> event_pool;
+    std::vector<DevBuf> buf_pool;    // device buffers of finished submissions, reused by the next ones
+    bool rules_valid = false;
+    DecodeRules rules{};
+    bool mirror_dirty = false;       // the pinned host mirror of the row scalars has changes that are not on the device yet
+    int desc_cursor = 0;             // ring position in the pinned window-descriptor area
+};
+
 }  // namespace oh
 
 struct oh_state {
     oh_context* ctx = nullptr;
-    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t own_stream = nullptr, stream = nullptr;  // decode stream (the caller may substitute its own)
+    cudaStream_t enc_stream = nullptr;                     // encoder passes run here, concurrently with decode steps
+    cudaStream_t fe_stream = nullptr;                      // front end: PCM upload + log-mel of a new submission
+    void* green_ctx = nullptr;                             // CUgreenCtx of the encoder's SM partition (OH_ENC_SMS), or null
+    int enc_sms = 0;                                       // SMs of that partition (0: the encoder stream may use every SM)
     cudaStream_t stream2 = nullptr;  // second row group of the interleaved decode step
     cudaEvent_t ev_dual[3] = {nullptr, nullptr, nullptr};
     int dual_min_rows = 1 << 30;     // OH_DUAL=n: batches of >= n rows decode as two interleaved row groups (measured slower on B200: off)
-    int max_batch = 1;   // KV-cache slots
+    int max_batch = 1;   // decoder rows resident on the GPU (oh_context_params.max_batch)
+    int n_slots = 1;     // cross-attention K/V slots: rows + look-ahead (windows encoded before a row is free for them)
     int enc_chunk = 1;   // windows per encoder pass
     int esz = 2;         // bytes per activation element
+    bool async_encoder = true;  // OH_ASYNC_ENC=0: encoder passes are issued on the decode stream (serialised, round-1 behaviour)
+    int check_steps = 8;        // decode steps between two host look-ins
 
-    // --- mel
-    oh::DevBuf pcm_stage;          // device copy of host PCM (concatenated)
-    oh::DevBuf mel_raw;            // [clips][n_mel][mel_ld]
+    // --- stage API mel (oh_pcm_to_mel_*): its own small submission-like block
+    oh::DevBuf pcm_stage, mel_raw, clip_meta;
     int mel_ld = 0, mel_clips = 0;
-    oh::DevBuf clip_meta;          // device: pcm ptrs | n_samples | n_active | n_len | max_key | clip_of_slot | seek_of_slot
     // --- encoder activations (enc_chunk windows)
     oh::DevBuf xin, x1, x, h, qkv, hid, enc_f32;
-    // --- caches (max_batch slots)
-    oh::DevBuf xkv;                // [L][slots][1500][2d]
-    oh::DevBuf kself, vself;       // [L][slots][448][d]
+    oh::DevBuf win_desc;           // device WindowDesc ring
+    oh::WindowDesc* win_desc_host = nullptr;  // pinned mirror of the ring
+    int win_desc_cap = 0;
+    // --- caches
+    oh::DevBuf xkv;                // [L][n_slots][2][heads][1500][64]
+    oh::DevBuf kself, vself;       // [L][rows][heads][448][64]
     // --- decoder activations (max_batch rows)
     oh::DevBuf dx, dh, dqkv, datt, dq, dhid, logits, dump_lp, dump_p;
     int ld_logits = 0;
     oh::DevBuf seq_dev;            // DecodeSeqState arrays
     oh::DevBuf rules_dev;
     oh::DecodeSeqState seq{};
-    std::vector<int> seq_host_i;   // staging
-    void* pinned = nullptr;        // small pinned scratch
+    void* pinned = nullptr;        // pinned host mirror of the DecodeSeqState block + small scratch
     size_t pinned_bytes = 0;
     std::map<int, cudaGraphExec_t> step_graphs;  // keyed by rows
     std::set<int> warmed_rows;
@@ -92,10 +162,14 @@ struct oh_state {
     oh::Profiler* prof = nullptr;
     bool profiling = false;
 
-    // --- results
+    oh::Sched sched;
+
+    // --- results of the last waited submission
     std::vector<oh::Item> items;
-    std::vector<std::mt19937> rngs;  // one per slot, seeded 0 at state creation, never reseeded (A.7)
-    oh_timings timings{};
+    std::vector<std::mt19937> rngs;  // one per item index of the blocking calls, seeded 0 on first use, never reseeded (A.7)
+    oh_timings timings{};            // accumulates since the previous wait returned
+    oh_timings timings_out{};        // what oh_get_timings reports: the activity up to the last wait
+    long long launches_mark = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::string scratch_text;
 };
@@ -106,14 +180,58 @@ int state_alloc(oh_state* st);
 void state_release(oh_state* st);
 
 // stages
+// stage-API log-mel into the state's own block (oh_pcm_to_mel_*); items of the call land in st->items
 int run_mel(oh_state* st, const float* const* pcm, const int* n, int batch, bool pcm_on_device);
+// encoder pass over the windows staged in st->xin; window w's cross K/V goes to slot slot_list[w] (default slot0 + w)
 int run_encoder(oh_state* st, int n_windows, int slot0, float* d_enc_f32_out /* nullable, [n_windows][1500][d] */,
-                const int* slot_list = nullptr /* per-window KV slot; default slot0 + w */);
+                const int* slot_list = nullptr, cudaStream_t stream = nullptr /* default: the decode stream */);
 int run_decode_step(oh_state* st, int rows, bool dump_probs);
+int run_decode_step_graph(oh_state* st, int rows, bool with_k9 = true);
+
+// the full() driver (full.cu)
 int run_full(oh_state* st, const oh_full_params& p, const float* const* pcm, const int* n, int batch, bool pcm_on_device);
+int sched_submit(oh_state* st, const oh_full_params& p, const float* const* pcm, const int* n, int batch, bool pcm_on_device, bool persistent_rngs,
+                 int* ticket);
+int sched_wait(oh_state* st, int ticket);
+int sched_pending(const oh_state* st);
+void sched_abort(oh_state* st);    // drop every live submission, reset rows and slots
+void sched_release(oh_state* st);
 
 int ensure(DevBuf& b, size_t bytes);
-const int* clip_max_key(oh_state* st, int batch, int clip);
+void release(DevBuf& b);
+const int* clip_max_key(oh_state* st, int batch, int clip);  // stage-API block
+const int* clip_max_key(const DevBuf& clip_meta, int batch, int clip);
 int decode_tokens_stage(oh_state* st, const int* tokens, int n_tokens, int n_past, int batch, float* out_logits);
+
+// mel of `batch` clips into caller-provided buffers on `stream` (shared by the stage API and the scheduler)
+struct MelPlan {
+    std::vector<size_t> pcm_off;  // float offset of each clip in the staging buffer
+    size_t stage_floats = 0;
+    int max_active = 0, ld = 0;
+};
+MelPlan plan_mel(std::vector<Item>& items, const int* n, int batch);
+int launch_mel(oh_state* st, const MelPlan& plan, const std::vector<Item>& items, const float* const* pcm, bool pcm_on_device, DevBuf& pcm_stage,
+               DevBuf& mel_raw, DevBuf& clip_meta, cudaStream_t stream, long long* h2d_bytes);
+
+// DecodeSeqState block layout helpers (engine.cu)
+namespace seqlay {
+enum { SLOT, SSLOT, ACTIVE, POS, CUR, PLEN, NGEN, HAS_TS, SDELTA, RLEN, FAILED, COMPLETED, SEEK, SEEKEND, N_SCALARS };
+}
+struct SeqLayout {
+    size_t rows, prompt_off, tok_off[6], counter_off, total_words;
+    explicit SeqLayout(size_t r) : rows(r) {
+        size_t o = seqlay::N_SCALARS * rows;
+        prompt_off = o;
+        o += rows * kMaxPrompt;
+        for (int i = 0; i < 6; ++i) {
+            tok_off[i] = o;
+            o += rows * kMaxGen;
+        }
+        counter_off = o;
+        total_words = o + 4;
+    }
+};
+DecodeSeqState seq_view(int32_t* base, const SeqLayout& L);
+DecodeRules make_rules(const Model& m, const oh_full_params& p, bool no_timestamps, float temperature);
 
 }  // namespace oh

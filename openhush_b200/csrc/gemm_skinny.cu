@@ -184,10 +184,15 @@ int launch_mt(const SkParams& p, int cs, cudaStream_t st) {
     const int MP = 16 * MT;
     const size_t xs = (p.ks % 64 == 0) ? p.ks + 32 : p.ks;
     const size_t smem = std::max((size_t)MP * xs * 2, (size_t)MP * SK_ROWS * 4);
-    static size_t configured = 0;
-    if (smem > configured) {
-        OH_CUDA_CHECK(cudaFuncSetAttribute(gemm_skinny_kernel<T, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+    {   // shared-memory opt-in: per device and per instantiation, grown on demand
+        static std::mutex mu;
+        static size_t configured[PerDeviceInit::kMaxDevices] = {};
+        std::lock_guard<std::mutex> lk(mu);
+        size_t& cur = configured[PerDeviceInit::current_device()];
+        if (smem > cur) {
+            OH_CUDA_CHECK(cudaFuncSetAttribute(gemm_skinny_kernel<T, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cur = smem;
+        }
     }
     const int n_slices = (p.N + SK_ROWS - 1) / SK_ROWS;
     cudaLaunchConfig_t cfg{};
@@ -231,11 +236,10 @@ int launch_gemm_skinny(const GemmArgs& g, cudaStream_t st) {
     // cluster size: enough CTAs to cover the machine, K-range a multiple of 32
     const int n_slices = (g.N + SK_ROWS - 1) / SK_ROWS;
     int cs = 1;
-    static int cs_cap = -1;
-    if (cs_cap < 0) {
+    static const int cs_cap = [] {
         const char* e = getenv("OH_SKINNY_CS");
-        cs_cap = e ? std::max(1, atoi(e)) : 8;
-    }
+        return e ? std::max(1, atoi(e)) : 8;
+    }();
     while (cs < cs_cap && n_slices * cs < 148 && (g.K / (cs * 2)) % 32 == 0 && g.K / (cs * 2) >= 64) cs *= 2;
     const int kc = g.K / cs;
     int ks = 0;

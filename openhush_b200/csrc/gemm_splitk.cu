@@ -23,6 +23,7 @@
 #include <cudaTypedefs.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <mutex>
 #include <vector>
@@ -278,29 +279,19 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     cluster.barrier_wait();  // nobody leaves while a peer may still read its partial tile
 }
 
-PFN_cuTensorMapEncodeTiled_v12000 g_spk_encode = nullptr;
-int g_spk_state = 0;  // 0 unknown, 1 usable, -1 unusable
-std::once_flag g_spk_once;
+std::atomic<PFN_cuTensorMapEncodeTiled_v12000> g_spk_encode{nullptr};
+PerDeviceInit g_spk_init;  // the shared-memory opt-in is per device
 
-void spk_init_once() {
+bool spk_init_device() {
     cudaDriverEntryPointQueryResult qres;
     void* fn = nullptr;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
-        g_spk_state = -1;
-        return;
-    }
-    g_spk_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
-    int dev = 0;
-    cudaGetDevice(&dev);
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+        return false;
+    g_spk_encode.store(reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn));
     cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess || prop.major != 10) {
-        g_spk_state = -1;
-        return;
-    }
-    g_spk_state = cudaFuncSetAttribute(gemm_splitk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SpkCfg<1>::SMEM_BYTES) == cudaSuccess &&
-                          cudaFuncSetAttribute(gemm_splitk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SpkCfg<2>::SMEM_BYTES) == cudaSuccess
-                      ? 1
-                      : -1;
+    if (cudaGetDeviceProperties(&prop, PerDeviceInit::current_device()) != cudaSuccess || prop.major != 10) return false;
+    return cudaFuncSetAttribute(gemm_splitk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SpkCfg<1>::SMEM_BYTES) == cudaSuccess &&
+           cudaFuncSetAttribute(gemm_splitk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SpkCfg<2>::SMEM_BYTES) == cudaSuccess;
 }
 
 bool spk_encode_map(CUtensorMap* map, CUtensorMapDataType dt, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems, uint32_t box_outer) {
@@ -308,7 +299,7 @@ bool spk_encode_map(CUtensorMap* map, CUtensorMapDataType dt, const void* base, 
     const uint64_t strides[1] = {ld_elems * 2};
     const uint32_t box[2] = {SPK_K, box_outer};
     const uint32_t estr[2] = {1, 1};
-    return g_spk_encode(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+    return g_spk_encode.load()(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -317,11 +308,10 @@ bool spk_encode_map(CUtensorMap* map, CUtensorMapDataType dt, const void* base, 
 // cluster size for an (N, K) problem: the largest power of two <= 8 that keeps every rank at least one k-block and the
 // grid within one resident wave (2 CTAs per SM)
 int gemm_splitk_cluster_size(int N, int K) {
-    static int cap = -1;
-    if (cap < 0) {
+    static const int cap = [] {
         const char* e = getenv("OH_SPLITK_CS");
-        cap = e ? std::max(1, std::min(8, atoi(e))) : 8;
-    }
+        return e ? std::max(1, std::min(8, atoi(e))) : 8;
+    }();
     const int n_tiles = (N + SPK_N - 1) / SPK_N, num_kb = (K + SPK_K - 1) / SPK_K;
     int cs = 1;
     while (cs * 2 <= cap && cs * 2 <= num_kb && n_tiles * cs * 2 <= 296) cs *= 2;  // 296 = 2 resident CTAs x 148 SMs (MT = 1)
@@ -329,8 +319,7 @@ int gemm_splitk_cluster_size(int N, int K) {
 }
 
 int launch_gemm_splitk(const GemmArgs& g, cudaStream_t st) {
-    std::call_once(g_spk_once, spk_init_once);
-    if (g_spk_state != 1) return OH_ERR_UNSUPPORTED;
+    if (!g_spk_init.ensure(spk_init_device)) return OH_ERR_UNSUPPORTED;
     const int M = g.batch * g.rows;
     if (g.a_type == DT_F32 || g.a_type != g.w_type || g.batch != 1 || M < 1 || M > 256 || g.n_taps != 1 || g.c_hsplit != 0) return OH_ERR_UNSUPPORTED;
     const int c_es = g.c_type == DT_F32 ? 4 : 2;

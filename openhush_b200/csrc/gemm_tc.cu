@@ -17,6 +17,7 @@
 #include <cudaTypedefs.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <mutex>
 #include <vector>
@@ -325,39 +326,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 }
 
 // ---- host side ----------------------------------------------------------------------------------------
-PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
-int g_num_sms = 0;
-int g_tc_state = 0;  // 0 unknown, 1 usable, -1 unusable
-std::once_flag g_once;
+std::atomic<PFN_cuTensorMapEncodeTiled_v12000> g_encode{nullptr};
+int g_num_sms[PerDeviceInit::kMaxDevices] = {};
+PerDeviceInit g_tc_init;  // shared-memory opt-ins and the SM count are per device
 
-void tc_init_once() {
+bool tc_init_device() {
     cudaDriverEntryPointQueryResult qres;
     void* fn = nullptr;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
-        g_tc_state = -1;
-        return;
-    }
-    g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
-    int dev = 0;
-    cudaGetDevice(&dev);
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+        return false;
+    g_encode.store(reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn));
+    const int dev = PerDeviceInit::current_device();
     cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess || prop.major != 10) {
-        g_tc_state = -1;
-        return;
-    }
-    g_num_sms = prop.multiProcessorCount;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess || prop.major != 10) return false;
+    g_num_sms[dev] = prop.multiProcessorCount;
     bool ok = cudaFuncSetAttribute(gemm_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcConfig<16>::SMEM_BYTES) == cudaSuccess &&
               cudaFuncSetAttribute(gemm_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcConfig<32>::SMEM_BYTES) == cudaSuccess &&
               cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcConfig<64>::SMEM_BYTES) == cudaSuccess &&
               cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcConfig<128>::SMEM_BYTES) == cudaSuccess &&
               cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcConfig<256>::SMEM_BYTES) == cudaSuccess;
-    g_tc_state = ok ? 1 : -1;
+    return ok;
 }
 
 bool encode_map(CUtensorMap* map, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims, const uint64_t* strides_bytes,
                 const uint32_t* box) {
     uint32_t estr[3] = {1, 1, 1};
-    CUresult r = g_encode(map, dt, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = g_encode.load()(map, dt, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
@@ -395,7 +389,8 @@ int launch_t(const GemmArgs& g, cudaStream_t st) {
     p.bias = g.bias; p.C = g.C; p.c_type = g.c_type; p.c_bstride = g.c_bstride; p.ldc = g.ldc;
     p.R = g.R; p.r_bstride = g.r_bstride; p.ldr = g.ldr; p.gelu = g.gelu; p.round_type = g.round_type; p.lut = g.lut;
     p.c_hsplit = g.c_hsplit; p.c_hstride = g.c_hstride;
-    const int grid = std::min(p.num_tiles, g_num_sms);
+    const int sm_cap = g_sm_limit > 0 ? std::min(g_sm_limit, g_num_sms[PerDeviceInit::current_device()]) : g_num_sms[PerDeviceInit::current_device()];
+    const int grid = std::min(p.num_tiles, sm_cap);
     OH_SKIP_IF(g.N > 40000 ? PC_LOGITS : (g.batch * g.rows <= 512 ? PC_GEMM_DEC : PC_GEMM_ENC));  // timing experiments only
     ProfScope ps(g.batch * g.rows <= 512 ? PC_GEMM_DEC : PC_GEMM_ENC, 2.0 * g.batch * (double)g.rows * g.N * g.K, st);
     OH_CUDA_CHECK(launch_k(gemm_tc_kernel<BLOCK_N>, grid, TC_THREADS, Cfg::SMEM_BYTES, st, ma[0], ma[1], ma[2], mw, p));
@@ -406,10 +401,7 @@ int launch_t(const GemmArgs& g, cudaStream_t st) {
 
 }  // namespace
 
-bool gemm_tc_available() {
-    std::call_once(g_once, tc_init_once);
-    return g_tc_state == 1;
-}
+bool gemm_tc_available() { return g_tc_init.ensure(tc_init_device); }
 
 bool tc_encode_tiled(CUtensorMap* map, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims, const uint64_t* strides_bytes,
                      const uint32_t* box) {

@@ -23,15 +23,14 @@ size_t mel_smem_bytes();
 int launch_mel_frames(const MelArgs& a, int batch, int max_active_frames, cudaStream_t st);
 int launch_mel_normalize(const float* raw, int ld, int n_mel, int n_active, int n_len, const int* max_key, float* out, cudaStream_t st);
 
-struct WindowGatherArgs {
-    const float* raw;
-    int ld, n_mel;
-    const int* max_key;
-    const int *n_active, *n_len;  // per clip
-    const int *clip_of_slot, *seek_of_slot;
+// one encoder-input window: frames [seek, seek + 3000) of a clip's un-normalised log-mel (device array, one per window of a pass)
+struct WindowDesc {
+    const float* raw;    // the clip's raw log10 mel, [n_mel][ld]
+    const int* max_key;  // the clip-wide max (order-preserving int key), written by the mel kernel
+    int ld, n_active, n_len, seek;
 };
-// act_type: OH_COMPUTE_F32 / F16 / BF16 selects the element type of X ([slots][3002][n_mel])
-int launch_window_gather(const WindowGatherArgs& a, int n_slots, void* X, int act_type, cudaStream_t st);
+// act_type: OH_COMPUTE_F32 / F16 / BF16 selects the element type of X ([windows][3002][n_mel])
+int launch_window_gather(const WindowDesc* d_windows, int n_mel, int n_windows, void* X, int act_type, cudaStream_t st);
 int launch_window_from_mel(const float* mel, int n_mel, int n_slots, void* X, int act_type, cudaStream_t st);
 
 // ---- K3/K4: dense contractions (gemm_simt.cu, gemm_tc.cu) --------------------------------------------
@@ -99,7 +98,8 @@ constexpr int kMaxPrompt = 232;   // [prev] + 224 past tokens + sot/lang/task/no
 constexpr int kMaxGen = 224;      // n_max = 448/2 - 4 = 220 sampled tokens per window, rounded up
 
 struct DecodeSeqState {  // struct of arrays, one entry per batch row; lives in device memory
-    int* slot;        // KV-cache slot of this row
+    int* slot;        // cross-attention K/V slot of this row (the encoded window it decodes; beams of a window share one)
+    int* sslot;       // self-attention K/V cache line of this row (a beam inherits its parent's by index)
     int* active;      // 1 while the row still decodes
     int* pos;         // tokens already in the self-attention cache (= n_past of the next step)
     int* cur_token;   // input token of the next step

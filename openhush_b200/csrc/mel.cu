@@ -27,7 +27,7 @@ constexpr int MEL_THREADS = 256;             // 8 warps
 constexpr int MEL_WARPS = MEL_THREADS / 32;
 constexpr int SEG = kHop * (FB - 1) + kNFFT;  // 5360 staged samples
 constexpr int MAX_MEL = 128;
-constexpr int MAX_FILT_W = 1024;
+constexpr int MAX_FILT_W = kMaxMelFilterWeights;  // load_model rejects denser banks
 
 __device__ __forceinline__ int float_to_ordered(float f) {
     int b = __float_as_int(f);
@@ -164,14 +164,15 @@ __global__ void mel_normalize_kernel(const float* __restrict__ raw, int ld, int 
 // plain mat-mul over overlapping 3-row views (see encoder.cu).  Frames in [n_active, n_len) are the padding
 // value -10 (then clamped), frames >= n_len are 0 (A.3 step 6).
 template <typename T>
-__global__ void __launch_bounds__(256) window_gather_kernel(WindowGatherArgs a, T* __restrict__ X) {
+__global__ void __launch_bounds__(256) window_gather_kernel(const WindowDesc* __restrict__ wins, int n_mel_, T* __restrict__ X) {
     __shared__ float tile[32][MAX_MEL + 1];
     const int slot = blockIdx.y;
-    const int clip = a.clip_of_slot[slot];
-    const int seek = a.seek_of_slot[slot];
-    const int n_active = a.n_active[clip], n_len = a.n_len[clip];
-    const float floor_v = ordered_to_float(a.max_key[clip]) - 8.0f;
-    const float* __restrict__ raw = a.raw + (size_t)clip * a.n_mel * a.ld;
+    const WindowDesc w = wins[slot];
+    struct { int n_mel, ld; } a{n_mel_, w.ld};
+    const int seek = w.seek;
+    const int n_active = w.n_active, n_len = w.n_len;
+    const float floor_v = ordered_to_float(*w.max_key) - 8.0f;
+    const float* __restrict__ raw = w.raw;
     const int j0 = blockIdx.x * 32;  // window column
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     for (int m = ty; m < a.n_mel; m += 8) {
@@ -228,10 +229,10 @@ __global__ void __launch_bounds__(256) window_from_mel_kernel(const float* __res
 size_t mel_smem_bytes() { return sizeof(MelSmem); }
 
 int launch_mel_frames(const MelArgs& a, int batch, int max_active_frames, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        OH_CUDA_CHECK(cudaFuncSetAttribute(mel_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MelSmem)));
-        attr_set = true;
+    static PerDeviceInit attr;
+    if (!attr.ensure([] { return cudaFuncSetAttribute(mel_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MelSmem)) == cudaSuccess; })) {
+        set_error("mel_frames: shared-memory opt-in failed");
+        return OH_ERR_CUDA;
     }
     mel_init_max_kernel<<<(batch + 127) / 128, 128, 0, st>>>(a.max_key, batch);
     OH_COUNT_LAUNCH();
@@ -256,12 +257,12 @@ int launch_mel_normalize(const float* raw, int ld, int n_mel, int n_active, int 
     return OH_OK;
 }
 
-int launch_window_gather(const WindowGatherArgs& a, int n_slots, void* X, int act_type, cudaStream_t st) {
+int launch_window_gather(const WindowDesc* d_windows, int n_mel, int n_slots, void* X, int act_type, cudaStream_t st) {
     dim3 grid((kChunkFrames + 31) / 32, n_slots);
-    ProfScope ps(PC_GATHER, (double)n_slots * kChunkFrames * a.n_mel * (4.0 + (act_type == OH_COMPUTE_F32 ? 4 : 2)), st);
-    if (act_type == OH_COMPUTE_F32) window_gather_kernel<float><<<grid, 256, 0, st>>>(a, (float*)X);
-    else if (act_type == OH_COMPUTE_F16) window_gather_kernel<__half><<<grid, 256, 0, st>>>(a, (__half*)X);
-    else window_gather_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a, (__nv_bfloat16*)X);
+    ProfScope ps(PC_GATHER, (double)n_slots * kChunkFrames * n_mel * (4.0 + (act_type == OH_COMPUTE_F32 ? 4 : 2)), st);
+    if (act_type == OH_COMPUTE_F32) window_gather_kernel<float><<<grid, 256, 0, st>>>(d_windows, n_mel, (float*)X);
+    else if (act_type == OH_COMPUTE_F16) window_gather_kernel<__half><<<grid, 256, 0, st>>>(d_windows, n_mel, (__half*)X);
+    else window_gather_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(d_windows, n_mel, (__nv_bfloat16*)X);
     OH_COUNT_LAUNCH();
     OH_CUDA_CHECK(cudaGetLastError());
     return OH_OK;

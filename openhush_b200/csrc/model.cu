@@ -162,7 +162,20 @@ Model::~Model() {
     for (void* p : allocs) cudaFree(p);
 }
 
+static Model* load_model_impl(const char* path, int device, int compute_type);
+
 Model* load_model(const char* path, int device, int compute_type) {
+    try {  // no exception may cross the C ABI (std::bad_alloc / length_error on a hostile file)
+        return load_model_impl(path, device, compute_type);
+    } catch (const std::exception& e) {
+        set_error(std::string("load_model(") + path + "): " + e.what());
+    } catch (...) {
+        set_error(std::string("load_model(") + path + "): unknown exception");
+    }
+    return nullptr;
+}
+
+static Model* load_model_impl(const char* path, int device, int compute_type) {
     FILE* f = fopen(path, "rb");
     if (!f) {
         set_error(std::string("cannot open model file ") + path);
@@ -176,15 +189,31 @@ Model* load_model(const char* path, int device, int compute_type) {
     auto fail = [&](const std::string& e) -> Model* {
         set_error("load_model(" + std::string(path) + "): " + e);
         if (f) fclose(f);
+        f = nullptr;
         return nullptr;
     };
+    struct FileGuard {  // an exception thrown while parsing must not leak the handle
+        FILE*& f;
+        ~FileGuard() {
+            if (f) fclose(f);
+        }
+    } file_guard{f};
 
+    long long file_size = 0;
+    if (fseek(f, 0, SEEK_END) == 0) {
+        file_size = ftell(f);
+        fseek(f, 0, SEEK_SET);
+    }
     uint32_t magic = 0;
     if (!rd(f, magic) || magic != 0x67676d6cu) return fail("bad magic (not a legacy ggml file)");
     HParams& hp = m->hp;
     if (fread(&hp, sizeof(int32_t), 11, f) != 11) return fail("truncated hparams");
-    if (hp.n_audio_state <= 0 || hp.n_audio_head <= 0 || hp.n_audio_state / hp.n_audio_head != kHeadDim ||
-        hp.n_text_state / hp.n_text_head != kHeadDim || hp.n_audio_state % kHeadDim || hp.n_audio_ctx != 1500 || hp.n_text_ctx != 448 ||
+    // every field is checked before it is used as a divisor, a vector size or a loop bound
+    if (hp.n_audio_state <= 0 || hp.n_audio_state > 8192 || hp.n_audio_head <= 0 || hp.n_text_state <= 0 || hp.n_text_head <= 0 ||
+        hp.n_audio_layer <= 0 || hp.n_audio_layer > 128 || hp.n_text_layer <= 0 || hp.n_text_layer > 128)
+        return fail("unsupported hparams (non-positive or oversized dimension)");
+    if (hp.n_audio_state % kHeadDim || hp.n_audio_state / hp.n_audio_head != kHeadDim || hp.n_text_state % kHeadDim ||
+        hp.n_text_state / hp.n_text_head != kHeadDim || hp.n_audio_ctx != 1500 || hp.n_text_ctx != 448 ||
         hp.n_vocab < 51864 || hp.n_vocab > 51866 || (hp.n_mels != 80 && hp.n_mels != 128) || hp.n_audio_state != hp.n_text_state)
         return fail("unsupported hparams");
     if (hp.ftype != 0 && hp.ftype != 1) return fail("quantised ftypes are not supported");
@@ -253,6 +282,15 @@ Model* load_model(const char* path, int device, int compute_type) {
         }
         std::string name(name_len, '\0');
         if (fread(&name[0], 1, name_len, f) != (size_t)name_len) return fail("truncated tensor name");
+        {   // the payload must fit in what is left of the file (also rules out overflowing dims)
+            const long long here = ftell(f);
+            long long ne_total = 1;
+            for (int i = 0; i < n_dims; ++i) {
+                if (t.ne[i] > (1LL << 40) / ne_total) return fail("tensor dims overflow for " + name);
+                ne_total *= t.ne[i];
+            }
+            if (here < 0 || ne_total * (ttype ? 2 : 4) > file_size - here) return fail("tensor " + name + " is larger than the rest of the file");
+        }
         t.data.resize((size_t)t.nelem() * (ttype ? 2 : 4));
         if (fread(t.data.data(), 1, t.data.size(), f) != t.data.size()) return fail("truncated tensor data for " + name);
         L.T[name] = std::move(t);
@@ -282,6 +320,9 @@ Model* load_model(const char* path, int device, int compute_type) {
             for (int k = 0; k < count[j]; ++k) w.push_back(mb.dense[(size_t)j * kNBins + start[j] + k]);
         }
         mb.n_weights = (int)w.size();
+        if (mb.n_weights > kMaxMelFilterWeights)  // the mel kernel stages the sparse bank in shared memory (mel.cu)
+            return fail("mel filterbank is not sparse enough (" + std::to_string(mb.n_weights) + " non-zero span weights, limit " +
+                        std::to_string(kMaxMelFilterWeights) + ")");
         mb.start = (int*)L.upload(start.data(), start.size() * 4);
         mb.count = (int*)L.upload(count.data(), count.size() * 4);
         mb.offset = (int*)L.upload(offset.data(), offset.size() * 4);

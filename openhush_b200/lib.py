@@ -31,6 +31,10 @@ SYMBOLS = {
     "oh_full": (C.c_int, [_vp, _vp, FullParams, _vp, C.c_int]),
     "oh_full_batch": (C.c_int, [_vp, _vp, FullParams, _vp, _vp, C.c_int]),
     "oh_full_batch_device": (C.c_int, [_vp, _vp, FullParams, _vp, _vp, C.c_int]),
+    "oh_stream_submit": (C.c_int, [_vp, _vp, FullParams, _vp, _vp, C.c_int, C.c_int, _ip]),
+    "oh_stream_wait": (C.c_int, [_vp, _vp, C.c_int]),
+    "oh_stream_pending": (C.c_int, [_vp]),
+    "oh_full_item_rc": (C.c_int, [_vp, C.c_int]),
     "oh_full_n_segments": (C.c_int, [_vp]),
     "oh_full_get_segment_text": (C.c_char_p, [_vp, C.c_int]),
     "oh_full_get_segment_t0": (C.c_int64, [_vp, C.c_int]),
@@ -165,6 +169,28 @@ class State:
         ns = (C.c_int * len(ptrs))(*[int(n) for n in n_samples])
         fn = self.lib.oh_full_batch_device if on_device else self.lib.oh_full_batch
         return fn(self.ctx.h, self.h, params, arr, ns, len(ptrs))
+
+    # ---- continuous batching across calls
+    def stream_submit(self, ptrs, n_samples, params: FullParams, on_device: bool = False) -> int:
+        """Register jobs (raw host/device addresses of 16 kHz f32 PCM); returns the ticket."""
+        ptrs = list(ptrs)
+        arr = (C.c_void_p * len(ptrs))(*ptrs)
+        ns = (C.c_int * len(ptrs))(*[int(n) for n in n_samples])
+        ticket = C.c_int(0)
+        rc = self.lib.oh_stream_submit(self.ctx.h, self.h, params, arr, ns, len(ptrs), 1 if on_device else 0, C.byref(ticket))
+        if rc != 0:
+            raise OhError(f"oh_stream_submit rc={rc}: " + self.lib.oh_last_error().decode(errors="replace"))
+        return ticket.value
+
+    def stream_submit_clips(self, clips, params: FullParams) -> int:
+        clips = [np.ascontiguousarray(c, dtype=np.float32) for c in clips]
+        return self.stream_submit([c.ctypes.data for c in clips], [len(c) for c in clips], params, on_device=False)
+
+    def stream_wait(self, ticket: int) -> int:
+        return self.lib.oh_stream_wait(self.ctx.h, self.h, ticket)
+
+    def item_rc(self, item: int = 0) -> int:
+        return self.lib.oh_full_item_rc(self.h, item)
 
     def segments(self, item: int = 0):
         L, h = self.lib, self.h
