@@ -210,6 +210,7 @@ def main():
     ap.add_argument("--strategy", default="greedy", choices=["greedy", "beam"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the strong-scaling and single-call latency legs")
+    ap.add_argument("--value-only", action="store_true", help="knob sweeps: only the kernel-only value leg (no e2e, profile, extras, CPU legs)")
     ap.add_argument("--blocking", action="store_true", help="one blocking oh_full_batch per step (rows drain between steps) instead of the stream API")
     args = ap.parse_args()
 
@@ -323,6 +324,23 @@ def main():
     torch.cuda.synchronize()
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
+
+    if args.value_only:
+        if world > 1:
+            tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ms = float(tms[0])
+        if rank == 0:
+            rs = cnt["rsteps"]
+            print(json.dumps(dict(value=WINDOW_S * B * world * K / (ms / 1000.0), ms_per_step=ms / K, n_gpus=world, steps=K, rows=S, batch=B, knobs=knobs,
+                                  enc_sms=None, decode_steps=cnt["dsteps"], windows=cnt["windows"], tokens=cnt["tokens"], clocks=clocks,
+                                  row_steps=dict(total=rs, idle_frac=round((rs - cnt["tokens"] - cnt["psteps"]) / max(rs, 1), 4),
+                                                 no_window_frac=round((rs - cnt["asteps"]) / max(rs, 1), 4)))), flush=True)
+        st.close()
+        ctx.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---------------- end to end: host PCM through the C ABI, records read back ----------------
     recs = {}

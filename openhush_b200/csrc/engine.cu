@@ -172,7 +172,17 @@ int state_alloc(oh_state* st) {
     if (!(enc_sms > 0 && create_partition_stream(st, enc_sms))) {
         st->green_ctx = nullptr;
         st->enc_sms = 0;
-        OH_CUDA_CHECK(cudaStreamCreateWithPriority(&st->enc_stream, cudaStreamNonBlocking, prio_lo));
+        // without a partition the encoder stream outranks the decode stream: its CTAs are placed first whenever SMs free up,
+        // so encoder passes finish at their stand-alone speed and the rows are never left without a window
+        // (OH_ENC_PRIO=lo: the encoder only gets what the decode steps leave idle)
+        const char* pe = getenv("OH_ENC_PRIO");
+        const bool enc_hi = !(pe && strcmp(pe, "lo") == 0);
+        if (enc_hi) {
+            cudaStreamDestroy(st->own_stream);
+            OH_CUDA_CHECK(cudaStreamCreateWithPriority(&st->own_stream, cudaStreamNonBlocking, prio_lo));
+            st->stream = st->own_stream;
+        }
+        OH_CUDA_CHECK(cudaStreamCreateWithPriority(&st->enc_stream, cudaStreamNonBlocking, enc_hi ? prio_hi : prio_lo));
     }
     for (auto& ev : st->ev) OH_CUDA_CHECK(cudaEventCreate(&ev));
     for (auto& ev : st->ev_dual) OH_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));

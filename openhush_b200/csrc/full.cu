@@ -1050,6 +1050,15 @@ int sched_submit(oh_state* st, const oh_full_params& p, const float* const* pcm,
         if ((rc = pump.run(nullptr))) return rc;
     }
 
+    if (sc.subs.empty()) {
+        // starting from idle: the stage entry points (oh_decode_batch ...) may have used the row-state block meanwhile
+        SeqLayout lay(st->max_batch);
+        memset(st->pinned, 0, lay.total_words * 4);
+        OH_CUDA_CHECK(cudaMemcpyAsync(st->seq_dev.p, st->pinned, lay.total_words * 4, cudaMemcpyHostToDevice, st->stream));
+        OH_CUDA_CHECK(cudaStreamSynchronize(st->stream));
+        sc.mirror_dirty = false;
+        sc.rules_valid = false;
+    }
     std::unique_ptr<Submission> sub(new Submission());
     sub->ticket = sc.next_ticket++;
     sub->p = p;

@@ -67,3 +67,25 @@ def test_product_never_links_the_oracle():
         if f.endswith((".cu", ".cuh", ".h")):
             src = open(os.path.join(lib.CSRC, f)).read()
             assert "oracle/" not in src.replace("never includes anything from oracle/", "").replace("the\n// oracle under", "")
+
+
+def test_rust_sys_crate_declares_every_symbol():
+    """rust/ohwhisper-sys/src/lib.rs (source only: no Rust toolchain in the image) must declare exactly the header's symbols,
+    and its PODs must list the header's fields in the header's order (the ctypes mirrors in _abi.py are the reference)."""
+    txt = open(os.path.join(ROOT, "rust", "ohwhisper-sys", "src", "lib.rs")).read()
+    rust_fns = sorted(set(re.findall(r"pub fn (oh_\w+)\s*\(", txt)))
+    assert rust_fns == _declared_symbols()
+
+    def rust_fields(name):
+        body = re.search(r"pub struct " + name + r" \{(.*?)\n\}", txt, flags=re.S).group(1)
+        return re.findall(r"pub (\w+):", body)
+
+    assert rust_fields("oh_full_params") == [n for n, _ in _abi.FullParams._fields_]
+    assert rust_fields("oh_context_params") == [n for n, _ in _abi.ContextParams._fields_]
+    assert rust_fields("oh_timings") == [n for n, _ in _abi.Timings._fields_]
+    assert rust_fields("oh_kernel_stat") == [n for n, _ in _abi.KernelStat._fields_]
+    hdr = open(os.path.join(ROOT, "include", "oh_whisper.h")).read()
+    body = re.search(r"typedef struct oh_timings \{(.*?)\} oh_timings;", hdr, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    hdr_fields = [f.strip() for decl in re.findall(r"(?:float|int|long long)\s+([^;]+);", body) for f in decl.split(",")]
+    assert hdr_fields == [n for n, _ in _abi.Timings._fields_]
