@@ -149,6 +149,8 @@ int state_alloc(oh_state* st) {
     st->n_slots = st->max_batch + lookahead;
     if (const char* s = getenv("OH_ASYNC_ENC")) st->async_encoder = atoi(s) != 0;
     if (const char* s = getenv("OH_CHECK")) st->check_steps = std::max(1, atoi(s));
+    st->starve_rows = std::max(1, std::min(8, st->max_batch / 16));
+    if (const char* s = getenv("OH_STARVE")) st->starve_rows = std::max(1, atoi(s));
     if (const char* s = getenv("OH_GEMM")) st->gemm_mode = strcmp(s, "simt") == 0 ? 1 : 0;
     if (const char* s = getenv("OH_ATTN")) st->attn_mode = strcmp(s, "simple") == 0 ? 1 : (strcmp(s, "flash") == 0 ? 2 : 0);  // flash: the mma.sync kernel
     if (const char* s = getenv("OH_GRAPHS")) st->use_graphs = atoi(s) != 0;

@@ -895,6 +895,15 @@ struct Pump {
             poll_passes(false);
             if ((rc = launch_passes())) return rc;
             if ((rc = arm_rows())) return rc;
+            // Decode yields to the encoder when rows run empty.  An encoder pass issued next to the decode steps only gets
+            // the SMs the steps leave idle (its persistent mat-mul needs a whole SM's shared memory, and the steps' CTAs keep
+            // every SM partly occupied), so without this the rows settle at ~60 % occupancy; with it the pass runs alone
+            // for ~100 ms exactly when windows are short, and the look-ahead slots keep that rare in steady state.
+            if (sc.n_armed > 0 && R - sc.n_armed >= st->starve_rows && sc.ready.empty() && !sc.passes.empty() && sc.parked.empty()) {
+                poll_passes(true);
+                if ((rc = launch_passes())) return rc;
+                if ((rc = arm_rows())) return rc;
+            }
             if (sc.n_armed == 0) {
                 if (!sc.parked.empty()) {
                     if ((rc = run_ladder())) return rc;

@@ -99,7 +99,8 @@ def load():
         if not os.path.exists(SO_PATH):
             raise RuntimeError(f"{SO_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                                "(there is no CPU fallback)")
-        lib = C.CDLL(SO_PATH)
+        # OH_LIB_PATH: the diagnostic twin (`make -C openhush_b200/csrc diag`) for scripts/bench_decode_step.py; tests and bench.py never set it
+        lib = C.CDLL(os.environ.get("OH_LIB_PATH") or SO_PATH)
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(lib, name)  # raises AttributeError if the header and the library disagree
             fn.restype, fn.argtypes = res, args
@@ -268,6 +269,13 @@ class State:
         if rc != 0:
             raise OhError(f"oh_decode_batch rc={rc}: " + self.lib.oh_last_error().decode(errors="replace"))
         return out
+
+    def decode_noread(self, tokens: np.ndarray, n_past: int) -> int:
+        """oh_decode_batch without the logit read-back (timing loops)."""
+        t = np.ascontiguousarray(tokens, dtype=np.int32)
+        if t.ndim == 1:
+            t = t[None]
+        return self.lib.oh_decode_batch(self.ctx.h, self.h, t.ctypes.data, t.shape[1], n_past, t.shape[0], None)
 
     def close(self):
         if self.h:

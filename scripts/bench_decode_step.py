@@ -1,9 +1,15 @@
-"""Micro-benchmark of one decoder step (graph replay through the stage API, every row active) and its
+"""Micro-benchmark of one decoder step (graph replay through the stage API, every row active, no logit read-back) and its
 breakdown by elimination: the step is re-timed with one kernel category not launched (OH_SKIP_CATS bit mask;
-results are meaningless in those runs, only the time matters).
-Usage: python scripts/bench_decode_step.py [arch] [rows] [n_past]"""
+results are meaningless in those runs, only the time matters).  The skip switch exists only in the diagnostic twin of the
+library (`make -C openhush_b200/csrc diag` -> libohwhisper_diag.so, -DOH_DIAG), which this script loads.
+Usage: python scripts/bench_decode_step.py [arch] [rows] [n_past] [quick]"""
 import os
 import sys
+
+_CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "openhush_b200", "csrc")
+if not os.path.exists(os.path.join(_CSRC, "libohwhisper_diag.so")):
+    raise SystemExit("build the diagnostic library first: make -C openhush_b200/csrc diag")
+os.environ["OH_LIB_PATH"] = os.path.join(_CSRC, "libohwhisper_diag.so")
 
 import numpy as np
 
@@ -35,13 +41,13 @@ for name, mask in variants:
     st.encode(np.repeat(mel[None], min(rows, 4), axis=0))
     toks = np.full((rows, 1), ctx.sot, dtype=np.int32)
     for i in range(max(n_past0 - 4, 0), n_past0):  # capture + warm the graph (cache contents do not matter for timing)
-        st.decode(toks, i)
+        st.decode_noread(toks, i)
     torch.cuda.synchronize()
     n = 30
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for i in range(n):
-        st.decode(toks, n_past0 + i)
+        st.decode_noread(toks, n_past0 + i)
     e1.record(stream)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
