@@ -236,6 +236,41 @@ class WhisperEngine:
             lang = LANG_CODES[code] if 0 <= code < len(LANG_CODES) else "auto"
         return TranscriptionResult(text.strip(), lang, int((time.perf_counter() - t0) * 1000), segs)
 
+    def _result_of_item(self, item: int, t0: float) -> TranscriptionResult:
+        text, segs = "", []
+        for s in self.state.segments(item):
+            try:
+                piece = s["text"].decode("utf-8")  # whisper.rs:276-280: a segment that is not valid UTF-8 is skipped
+            except UnicodeDecodeError:
+                continue
+            text += piece
+            segs.append((s["t0"], s["t1"], piece))
+        return TranscriptionResult(text.strip(), self.language if self.language != "auto" else "en", int((time.perf_counter() - t0) * 1000), segs)
+
+    def transcribe_batch(self, audios) -> list:
+        """Additive (the multi-GPU queue): `len(audios)` independent transcribe() calls as ONE oh_full_batch.
+        Returns one entry per job: a TranscriptionResult, or the WhisperError transcribe() would have raised for that job
+        (validation is per job, whisper.rs:206; a job whose log-mel cannot be computed fails alone)."""
+        out = [None] * len(audios)
+        clips, idx = [], []
+        for i, a in enumerate(audios):
+            try:
+                validate_audio(a.samples, a.sample_rate)
+            except AudioValidationError as e:
+                out[i] = ValidationFailed(e)
+                continue
+            clips.append(np.ascontiguousarray(a.samples, dtype=np.float32))
+            idx.append(i)
+        if not clips:
+            return out
+        t0 = time.perf_counter()
+        self._keepalive = self._params()
+        rc = self.state.full_batch(clips, self._keepalive)
+        for k, i in enumerate(idx):
+            item_rc = rc if rc != 0 else self.state.item_rc(k)
+            out[i] = TranscriptionFailed(_FULL_ERRORS.get(item_rc, f"GenericError({item_rc})")) if item_rc != 0 else self._result_of_item(k, t0)
+        return out
+
     def benchmark(self, safety_margin: float) -> BenchmarkResult:
         """whisper.rs:334-387: 1 warm-up + 3 timed transcriptions of 2 s of silence."""
         audio = AudioBuffer(np.zeros(32000, np.float32), 16000)
@@ -308,9 +343,24 @@ class TranscriptionWorker:
             try:
                 res = self.engine.transcribe(job.buffer)
                 text, segs = res.text, res.segments
-            except WhisperError:
+            except Exception:  # worker.rs:161-164: any engine error is logged and answered with an empty text
                 text, segs = "", []
         return JobResult(text, job.sequence_id, job.chunk_id, job.is_final, dur, segs)
+
+    def process_jobs(self, jobs) -> list:
+        """Additive: the jobs a worker drained from the queue (up to the engine's max_batch) as one batched engine call.
+        One JobResult per job, always, in the order given."""
+        if self.engine is None or len(jobs) == 1 or not hasattr(self.engine, "transcribe_batch"):
+            return [self.process_job(j) for j in jobs]
+        try:
+            res = self.engine.transcribe_batch([j.buffer for j in jobs])
+        except Exception:
+            res = [None] * len(jobs)
+        out = []
+        for j, r in zip(jobs, res):
+            ok = isinstance(r, TranscriptionResult)
+            out.append(JobResult(r.text if ok else "", j.sequence_id, j.chunk_id, j.is_final, j.buffer.duration_secs(), r.segments if ok else []))
+        return out
 
 
 def shard_jobs(n_jobs: int, rank: int, world: int):
@@ -341,31 +391,65 @@ def merge_records(per_rank_records, world: int):
 class WorkerPool:
     """One worker per GPU over ONE shared job queue (the documented-but-unimplemented multi-GPU design of the
     reference: `config.gpu.devices`, /root/reference/src/config.rs:921-929, workers as in queue/worker.rs:255-267).
-    Jobs are independent transcribe() calls, so a worker that finishes early simply pulls the next job (dynamic load
-    balance: decode length is data-dependent); results carry (sequence_id, chunk_id) and go to one result queue, where a
-    TranscriptionTracker restores the order.  Nothing is exchanged between GPUs.
+    Jobs are independent transcribe() calls, so a worker that finishes early simply pulls the next jobs (dynamic load
+    balance: decode length is data-dependent); a worker drains up to its engine's `max_batch` queued jobs and hands them to
+    the engine as ONE batched call (oh_full_batch); results carry (sequence_id, chunk_id) and go to one result queue, where
+    a TranscriptionTracker restores the order.  Nothing is exchanged between GPUs.
 
-    `engines`: one engine per device (anything with .transcribe(AudioBuffer)); None entries model a worker whose engine
-    failed to load — it still answers every job with an empty text, like the reference's worker."""
+    `engines`: one engine per device (anything with .transcribe(AudioBuffer), optionally .transcribe_batch(list)).  A None
+    entry is a worker whose engine failed to load: it takes NO jobs while another worker has an engine (it would answer
+    instantly with empty texts and empty the queue ahead of the working GPUs); only when no worker has an engine does one
+    thread answer every job with an empty text, which is the reference's rule for its single worker (worker.rs:125-142:
+    the tracker must never stall)."""
 
-    def __init__(self, engines):
+    def __init__(self, engines, max_batch: int | None = None):
         import queue
         import threading
         self.jobs: "queue.Queue" = queue.Queue()
         self.results: "queue.Queue" = queue.Queue()
         self.workers = [TranscriptionWorker(e) for e in engines]
         self.jobs_done = [0] * len(engines)
-        self._threads = [threading.Thread(target=self._run, args=(i,), daemon=True) for i in range(len(engines))]
+        self.batches_done = [0] * len(engines)
+        self._max_batch = max_batch
+        live = [i for i, e in enumerate(engines) if e is not None]
+        consumers = live if live else list(range(min(1, len(engines))))
+        self._threads = [threading.Thread(target=self._run, args=(i,), daemon=True) for i in consumers]
         for t in self._threads:
             t.start()
 
+    def _batch_limit(self, i: int) -> int:
+        if self._max_batch is not None:
+            return max(1, self._max_batch)
+        ctx = getattr(self.workers[i].engine, "context", None)
+        return max(1, getattr(ctx, "max_batch", 1))
+
     def _run(self, i: int):
+        import queue
+        limit = self._batch_limit(i)
         while True:
             job = self.jobs.get()
             if job is None:  # WorkerCommand::Shutdown
                 return
-            self.results.put(self.workers[i].process_job(job))
-            self.jobs_done[i] += 1
+            batch, stop = [job], False
+            while len(batch) < limit:
+                try:
+                    nxt = self.jobs.get_nowait()
+                except queue.Empty:
+                    break
+                if nxt is None:
+                    stop = True
+                    break
+                batch.append(nxt)
+            try:
+                results = self.workers[i].process_jobs(batch)
+            except Exception:  # a result per job, whatever happens: the tracker must never stall
+                results = [JobResult("", j.sequence_id, j.chunk_id, j.is_final, j.buffer.duration_secs(), []) for j in batch]
+            for r in results:
+                self.results.put(r)
+            self.jobs_done[i] += len(batch)
+            self.batches_done[i] += 1
+            if stop:
+                return
 
     def submit(self, job: TranscriptionJob):
         self.jobs.put(job)

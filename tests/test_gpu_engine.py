@@ -75,3 +75,32 @@ def test_cpp_host_mirror_gpu(micro_path):
     exe = os.path.join(lib.CSRC, "host", "host_test")
     r = subprocess.run([exe, micro_path, "200000"], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "HOST_TEST_OK" in r.stdout and "TEXT_LEN" in r.stdout, r.stdout + r.stderr
+
+
+def test_worker_pool_on_gpus_batches_jobs(micro_path):
+    """One worker (thread + context + state) per visible GPU inside ONE process over one job queue
+    (/root/reference/src/queue/worker.rs:255-267, config.gpu.devices /root/reference/src/config.rs:921-929): each worker
+    drains up to max_batch queued jobs into one oh_full_batch; every answer equals the single transcribe() call.  With two
+    or more GPUs this also exercises the per-device kernel set-up (contexts on different devices used from different threads)."""
+    import torch
+
+    from openhush_b200.tracker import BackpressureStrategy, TranscriptionTracker
+    n_dev = min(torch.cuda.device_count(), 2)
+    engines = [E.WhisperEngine.new(micro_path, "en", False, True, compute_type=COMPUTE_F32, gpu_device=d, max_batch=4) for d in range(n_dev)]
+    jobs = [E.TranscriptionJob(E.AudioBuffer(synth.audio(40 + i, 60000 + 9000 * i), 16000), sequence_id=i) for i in range(10)]
+    jobs.append(E.TranscriptionJob(E.AudioBuffer(np.full(32000, np.nan, np.float32), 16000), sequence_id=10))  # fails validation alone
+    ref = [engines[0].transcribe(j.buffer).text for j in jobs[:10]]
+    pool = E.WorkerPool(engines)
+    tracker = TranscriptionTracker.new_ordered()
+    for j in jobs:
+        tracker.add_pending_with_config(j.sequence_id, 0, 0, 0, BackpressureStrategy.WARN)
+        pool.submit(j)
+    got = pool.drain(len(jobs), tracker, timeout=300.0)
+    pool.shutdown()
+    assert [r.sequence_id for r in got] == list(range(11))
+    assert [r.text for r in got[:10]] == ref and got[10].text == ""
+    assert sum(pool.jobs_done) == 11 and sum(pool.batches_done) < 11      # jobs really went through batched calls
+    if n_dev == 2:
+        assert all(n > 0 for n in pool.jobs_done) or max(pool.jobs_done) == 11
+    for e in engines:
+        e.close()

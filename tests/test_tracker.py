@@ -124,30 +124,63 @@ def test_merge_timed_segments():
 
 def test_worker_pool_shared_queue_and_ordered_handout():
     """one worker per GPU pulling from one job queue; the tracker restores the order.  Engines are stubs
-    here (the GPU engines are exercised by the -m gpu tests); one worker has no engine and still answers."""
+    here (the GPU engines are exercised by the -m gpu tests).  A worker without an engine takes no jobs while another has
+    one, so every text is a real transcript; workers drain up to max_batch jobs into one batched engine call."""
+    import threading
     import time
 
     import numpy as np
 
-    from openhush_b200.engine import AudioBuffer, TranscriptionJob, TranscriptionResult, WorkerPool
+    from openhush_b200.engine import AudioBuffer, TranscriptionFailed, TranscriptionJob, TranscriptionResult, WorkerPool
 
     class StubEngine:
         def __init__(self, delay):
-            self.delay = delay
+            self.delay, self.batch_sizes = delay, []
 
         def transcribe(self, audio):
             time.sleep(self.delay)
+            if len(audio.samples) == 16000 + 5:
+                raise RuntimeError("not a WhisperError")                 # must not kill the worker thread
             return TranscriptionResult(f"n={len(audio.samples)}", "en", 1, [(0, 10, "x")])
 
-    pool = WorkerPool([StubEngine(0.02), StubEngine(0.001), None])
+        def transcribe_batch(self, audios):
+            self.batch_sizes.append(len(audios))
+            out = []
+            for a in audios:
+                try:
+                    out.append(self.transcribe(a))
+                except RuntimeError as e:
+                    out.append(TranscriptionFailed(str(e)))
+            return out
+
+    engines = [StubEngine(0.02), StubEngine(0.001), None]
+    pool = WorkerPool(engines, max_batch=4)
     tracker = TranscriptionTracker.new_ordered()
     n = 24
     for seq in range(n):
         tracker.add_pending_with_config(seq, 0, 0, 0, BackpressureStrategy.WARN)
         pool.submit(TranscriptionJob(AudioBuffer(np.zeros(16000 + seq, np.float32), 16000), seq))
-    got = pool.drain(n, tracker)
+    got = pool.drain(n, tracker, timeout=30.0)
     pool.shutdown()
     assert [r.sequence_id for r in got] == list(range(n))               # ordered hand-out despite out-of-order completion
-    assert sum(pool.jobs_done) == n                                      # every job was taken exactly once
-    assert all(r.text == "" or r.text == f"n={16000 + r.sequence_id}" for r in got)   # an engine-less worker answers with empty text
+    assert sum(pool.jobs_done) == n and pool.jobs_done[2] == 0           # every job taken exactly once, none by the engine-less worker
+    assert all(r.text == f"n={16000 + r.sequence_id}" for r in got if r.sequence_id != 5)
+    assert got[5].text == ""                                             # the failing job alone is answered with an empty text
     assert all(r.segments == [(0, 10, "x")] for r in got if r.text)
+    sizes = engines[0].batch_sizes + engines[1].batch_sizes
+    assert max(sizes) <= 4 and sum(sizes) + sum(1 for _ in []) <= n      # batched calls never exceed max_batch
+    assert threading.active_count() < 20
+
+
+def test_worker_without_any_engine_still_answers_every_job():
+    """The reference's single-worker rule (worker.rs:125-142): with no engine at all the tracker must not stall."""
+    import numpy as np
+
+    from openhush_b200.engine import AudioBuffer, TranscriptionJob, WorkerPool
+
+    pool = WorkerPool([None, None])
+    for seq in range(5):
+        pool.submit(TranscriptionJob(AudioBuffer(np.zeros(16000, np.float32), 16000), seq))
+    got = pool.drain(5, timeout=10.0)
+    pool.shutdown()
+    assert sorted(r.sequence_id for r in got) == list(range(5)) and all(r.text == "" for r in got)
