@@ -210,6 +210,7 @@ def main():
     ap.add_argument("--strategy", default="greedy", choices=["greedy", "beam"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the strong-scaling and single-call latency legs")
+    ap.add_argument("--depth", type=int, default=2, help="stream API: tickets submitted ahead of the one being waited for (bounded queue of a streaming server)")
     ap.add_argument("--value-only", action="store_true", help="knob sweeps: only the kernel-only value leg (no e2e, profile, extras, CPU legs)")
     ap.add_argument("--blocking", action="store_true", help="one blocking oh_full_batch per step (rows drain between steps) instead of the stream API")
     args = ap.parse_args()
@@ -287,14 +288,18 @@ def main():
                 if collect:
                     collect(s)
             return
-        ticket = st.stream_submit(ptrs(base_ptr, first), ns, p, on_device=on_device)
+        # a bounded queue: up to `depth` later steps are submitted before a step is waited for.  One step ahead is not
+        # enough: the last windows of a step are its longest chains of dependent windows (a clip's next window starts where
+        # the previous one's last timestamp ended), several hundred decode steps during which the rows need other work
+        tickets, nxt = {}, first
         for s in range(first, last):
-            nxt = st.stream_submit(ptrs(base_ptr, s + 1), ns, p, on_device=on_device) if s + 1 < last else None
-            rc = st.stream_wait(ticket)
+            while nxt < last and nxt <= s + max(args.depth, 0):
+                tickets[nxt] = st.stream_submit(ptrs(base_ptr, nxt), ns, p, on_device=on_device)
+                nxt += 1
+            rc = st.stream_wait(tickets.pop(s))
             assert rc == 0, (rc, st.lib.oh_last_error())
             if collect:
                 collect(s)
-            ticket = nxt
 
     # ---------------- kernel-only value: inputs resident in HBM ----------------
     run_steps(0, W, True)
@@ -487,7 +492,7 @@ def main():
                                          f"recording, {B} windows per GPU per step over {S} resident decoder rows"
                                          + ("" if (args.blocking or beam) else ", steps pipelined through the stream API (continuous batching)"),
                                 arch=args.arch, windows_per_gpu_per_step=B, decoder_rows_per_gpu=S, window_seconds=WINDOW_S, strategy=args.strategy,
-                                api="oh_full_batch (blocking)" if (args.blocking or beam) else "oh_stream_submit / oh_stream_wait",
+                                api="oh_full_batch (blocking)" if (args.blocking or beam) else f"oh_stream_submit / oh_stream_wait, {args.depth} steps submitted ahead",
                                 weights="random-init, ggml-<arch>.bin format, seed 1234", l2="per-step inputs and weights exceed the 126 MB L2",
                                 gemm_backend=st.gemm_backend(), knobs=knobs),
                     clocks=clocks,
