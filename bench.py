@@ -281,7 +281,7 @@ def main():
     # completes inside the timed region, the final drain included.
     def run_steps(first, last, on_device, collect=None):
         base_ptr = dev.data_ptr() if on_device else host.data_ptr()
-        if args.blocking or beam:
+        if args.blocking:
             for s in range(first, last):
                 rc = st.full_batch_ptrs(ptrs(base_ptr, s), ns, p, on_device=on_device)
                 assert rc == 0, (rc, st.lib.oh_last_error())
@@ -490,9 +490,9 @@ def main():
                     higher_is_better=True, scaling="weak", vs_baseline=None, dtype=args.compute, data="synthetic",
                     config=dict(workload=f"whisper {args.arch} batched {'beam-5' if beam else 'greedy'} (temperature_inc=0), independent 30 s windows of a synthetic "
                                          f"recording, {B} windows per GPU per step over {S} resident decoder rows"
-                                         + ("" if (args.blocking or beam) else ", steps pipelined through the stream API (continuous batching)"),
+                                         + ("" if args.blocking else ", steps pipelined through the stream API (continuous batching)"),
                                 arch=args.arch, windows_per_gpu_per_step=B, decoder_rows_per_gpu=S, window_seconds=WINDOW_S, strategy=args.strategy,
-                                api="oh_full_batch (blocking)" if (args.blocking or beam) else f"oh_stream_submit / oh_stream_wait, {args.depth} steps submitted ahead",
+                                api="oh_full_batch (blocking)" if args.blocking else f"oh_stream_submit / oh_stream_wait, {args.depth} steps submitted ahead",
                                 weights="random-init, ggml-<arch>.bin format, seed 1234", l2="per-step inputs and weights exceed the 126 MB L2",
                                 gemm_backend=st.gemm_backend(), knobs=knobs),
                     clocks=clocks,

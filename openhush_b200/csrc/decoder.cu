@@ -777,9 +777,46 @@ __device__ __forceinline__ bool logit_masked(int i, const DecodeRules& r, const 
 
 constexpr int K9_THREADS = 1024;
 
+// sorted (best first) candidate list of the beam-mode top-k: larger logprob first, on ties the lower id
+struct TopList {
+    float v[kTopK];
+    int i[kTopK];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int j = 0; j < kTopK; ++j) {
+            v[j] = -INFINITY;
+            i[j] = 0x7fffffff;
+        }
+    }
+    __device__ __forceinline__ void insert(float x, int id) {
+        if (!(x > v[kTopK - 1] || (x == v[kTopK - 1] && id < i[kTopK - 1]))) return;
+        v[kTopK - 1] = x;
+        i[kTopK - 1] = id;
+#pragma unroll
+        for (int j = kTopK - 1; j > 0; --j) {
+            const bool sw = v[j] > v[j - 1] || (v[j] == v[j - 1] && i[j] < i[j - 1]);
+            if (sw) {
+                const float tv = v[j]; v[j] = v[j - 1]; v[j - 1] = tv;
+                const int ti = i[j]; i[j] = i[j - 1]; i[j - 1] = ti;
+            }
+        }
+    }
+    __device__ __forceinline__ void merge_from_lane_xor(int off) {
+        float ov[kTopK];
+        int oi[kTopK];
+#pragma unroll
+        for (int j = 0; j < kTopK; ++j) {
+            ov[j] = __shfl_xor_sync(0xffffffffu, v[j], off);
+            oi[j] = __shfl_xor_sync(0xffffffffu, i[j], off);
+        }
+#pragma unroll
+        for (int j = 0; j < kTopK; ++j) insert(ov[j], oi[j]);
+    }
+};
+
 __global__ void __launch_bounds__(K9_THREADS) logits_step_kernel(const float* __restrict__ logits, int ld, DecodeSeqState s,
                                                                 const DecodeRules* __restrict__ rp, float* __restrict__ dump_logprobs,
-                                                                float* __restrict__ dump_probs) {
+                                                                float* __restrict__ dump_probs, TopKOut topk) {
     pdl_wait();  // programmatic dependent launch: nothing above depends on the preceding kernel (see common.cuh)
     pdl_launch_dependents();
     const int b = blockIdx.x;
@@ -870,6 +907,58 @@ __global__ void __launch_bounds__(K9_THREADS) logits_step_kernel(const float* __
     const float ts_logprob = sts > 0.0f ? logf(sts) + mx - lse : -INFINITY;
     const float max_text_logprob = mtxt.v > -INFINITY ? mtxt.v - lse : -INFINITY;
     const bool force_ts = ts_logprob > max_text_logprob;
+
+    if (topk.ids) {  // beam search: the row's best candidates of the filtered distribution; the host ranks across beams
+        __shared__ float sm_tv[32][kTopK];
+        __shared__ int sm_ti[32][kTopK];
+        TopList tl;
+        tl.init();
+        for (int i = tid; i < r.n_vocab; i += K9_THREADS) {
+            if (logit_masked(i, r, c) || (force_ts && i < r.beg)) continue;
+            float v = row[i];
+            if (temp > 0.0f) v = v / temp;
+            tl.insert(v - lse, i);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tl.merge_from_lane_xor(o);
+        if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < kTopK; ++j) {
+                sm_tv[warp][j] = tl.v[j];
+                sm_ti[warp][j] = tl.i[j];
+            }
+        }
+        __syncthreads();
+        if (warp == 0) {
+#pragma unroll
+            for (int j = 0; j < kTopK; ++j) {
+                tl.v[j] = sm_tv[lane][j];
+                tl.i[j] = sm_ti[lane][j];
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) tl.merge_from_lane_xor(o);
+            if (lane == 0) {
+#pragma unroll
+                for (int j = 0; j < kTopK; ++j) {
+                    topk.ids[(size_t)b * kTopK + j] = tl.v[j] > -INFINITY ? tl.i[j] : -1;
+                    topk.logprobs[(size_t)b * kTopK + j] = tl.v[j];
+                    topk.probs[(size_t)b * kTopK + j] = tl.v[j] > -INFINITY ? expf(tl.v[j]) : 0.0f;
+                }
+                int tid_tok = 0;
+                float pt = 0.0f, ptsum = 0.0f;
+                if (mts.v > -INFINITY) {
+                    const float pmax = expf(mts.v - lse);
+                    ptsum = expf(ts_logprob);
+                    if (pmax > 0.0f) tid_tok = mts.i;
+                    pt = pmax / (ptsum + 1e-10f);
+                }
+                topk.tid[b] = tid_tok;
+                topk.pt[b] = pt;
+                topk.ptsum[b] = ptsum;
+            }
+        }
+        return;
+    }
 
     if (dump_probs) {  // t > 0: the host samples (std::mt19937 + std::discrete_distribution, A.7)
         float* lp = dump_logprobs + (size_t)b * ld;
@@ -1013,11 +1102,40 @@ int launch_cross_attention_decode(const void* q, const void* xkv, int type, cons
     return OH_OK;
 }
 
+// self-attention cache lines follow the beams: grid (pair, layer * 2 + k/v); a line is [heads][n_ctx][64]
+__global__ void __launch_bounds__(256) copy_self_lines_kernel(uint4* __restrict__ kcache, uint4* __restrict__ vcache, const int4* __restrict__ pairs,
+                                                             int lines, int heads, int n_ctx, int vec_per_pos /* 64 * esz / 16 */) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int4 pr = pairs[blockIdx.x];  // (src line, dst line, positions to copy, -)
+    const int n_pos = pr.z;
+    const int layer = blockIdx.y >> 1;
+    uint4* base = (blockIdx.y & 1) ? vcache : kcache;
+    const size_t line_vecs = (size_t)heads * n_ctx * vec_per_pos;
+    const uint4* src = base + ((size_t)layer * lines + pr.x) * line_vecs;
+    uint4* dst = base + ((size_t)layer * lines + pr.y) * line_vecs;
+    const int per_head = n_pos * vec_per_pos;
+    for (int idx = threadIdx.x; idx < heads * per_head; idx += blockDim.x) {
+        const int h = idx / per_head, o = idx - h * per_head;
+        dst[(size_t)h * n_ctx * vec_per_pos + o] = src[(size_t)h * n_ctx * vec_per_pos + o];
+    }
+}
+
+int launch_copy_self_lines(void* kcache, void* vcache, int esz, const int4* pairs, int n_pairs, int n_layers, int lines, int heads, int n_ctx,
+                           cudaStream_t st) {
+    if (n_pairs <= 0) return OH_OK;
+    OH_CUDA_CHECK(launch_k(copy_self_lines_kernel, dim3(n_pairs, n_layers * 2), 256, 0, st, (uint4*)kcache, (uint4*)vcache, pairs, lines, heads, n_ctx,
+                           kHeadDim * esz / 16));
+    OH_COUNT_LAUNCH();
+    OH_CUDA_CHECK(cudaGetLastError());
+    return OH_OK;
+}
+
 int launch_logits_step(const float* logits, int ld, const DecodeSeqState& s, const DecodeRules* r, int rows, float* dump_logprobs, float* dump_probs,
-                       cudaStream_t st) {
+                       cudaStream_t st, const TopKOut& topk) {
     OH_SKIP_IF(PC_LOGITS);
     ProfScope ps(PC_LOGITS, (double)rows * ld * 4.0 * 2, st);
-    OH_CUDA_CHECK(launch_k(logits_step_kernel, rows, K9_THREADS, 0, st, logits, ld, s, r, dump_logprobs, dump_probs));
+    OH_CUDA_CHECK(launch_k(logits_step_kernel, rows, K9_THREADS, 0, st, logits, ld, s, r, dump_logprobs, dump_probs, topk));
     OH_COUNT_LAUNCH();
     OH_CUDA_CHECK(cudaGetLastError());
     return OH_OK;

@@ -233,7 +233,7 @@ void state_release(oh_state* st) {
     st->step_graphs.clear();
     DevBuf* all[] = {&st->pcm_stage, &st->mel_raw, &st->clip_meta, &st->xin, &st->x1, &st->x, &st->h, &st->qkv, &st->hid, &st->enc_f32,
                      &st->win_desc, &st->xkv, &st->kself, &st->vself, &st->dx, &st->dh, &st->dqkv, &st->datt, &st->dq, &st->dhid, &st->logits,
-                     &st->dump_lp, &st->dump_p, &st->seq_dev, &st->rules_dev};
+                     &st->dump_lp, &st->dump_p, &st->topk_dev, &st->beam_pairs, &st->seq_dev, &st->rules_dev};
     for (DevBuf* b : all) release(*b);
     if (st->pinned) cudaFreeHost(st->pinned);
     st->pinned = nullptr;
@@ -522,7 +522,8 @@ int run_encoder(oh_state* st, int nw, int slot0, float* d_enc_f32_out, const int
 // ------------------------------------------------------------------------------------------------ decoder step
 // One decoder step for rows [row0, row0 + rows) on stream `s`.  `after_q0` (optional) is recorded right after the first
 // layer's cross-attention query projection: the interleaved step starts the second row group there.
-static int decode_step_launch(oh_state* st, int row0, int rows, bool with_k9, bool dump, cudaStream_t s, cudaEvent_t after_q0 = nullptr) {
+static int decode_step_launch(oh_state* st, int row0, int rows, int k9_mode, cudaStream_t s, cudaEvent_t after_q0 = nullptr) {
+    const bool with_k9 = k9_mode != K9_NONE, dump = k9_mode == K9_DUMP;
     const Model& m = *st->ctx->model;
     const HParams& hp = m.hp;
     const int d = hp.n_text_state, T = hp.n_audio_ctx, act = st->ctx->act_type, NC = hp.n_text_ctx;
@@ -602,7 +603,19 @@ static int decode_step_launch(oh_state* st, int row0, int rows, bool with_k9, bo
             lp = (float*)st->dump_lp.p + r0 * st->ld_logits;
             pr = (float*)st->dump_p.p + r0 * st->ld_logits;
         }
-        if ((rc = launch_logits_step(logits, st->ld_logits, seq, (const DecodeRules*)st->rules_dev.p, rows, lp, pr, s))) return rc;
+        TopKOut tk;
+        if (k9_mode == K9_TOPK) {  // beam search: [ids | logprobs | probs] x kTopK per row, then tid, pt, ptsum per row
+            const size_t R = st->max_batch;
+            if ((rc = ensure(st->topk_dev, R * (3 * kTopK + 3) * 4))) return rc;
+            int32_t* base = (int32_t*)st->topk_dev.p;
+            tk.ids = base + r0 * kTopK;
+            tk.logprobs = (float*)(base + R * kTopK) + r0 * kTopK;
+            tk.probs = (float*)(base + 2 * R * kTopK) + r0 * kTopK;
+            tk.tid = base + 3 * R * kTopK + r0;
+            tk.pt = (float*)(base + 3 * R * kTopK + R) + r0;
+            tk.ptsum = (float*)(base + 3 * R * kTopK + 2 * R) + r0;
+        }
+        if ((rc = launch_logits_step(logits, st->ld_logits, seq, (const DecodeRules*)st->rules_dev.p, rows, lp, pr, s, tk))) return rc;
     }
     return OH_OK;
 }
@@ -613,38 +626,43 @@ static int decode_step_launch(oh_state* st, int row0, int rows, bool with_k9, bo
 // the two kinds of work overlap instead of alternating.  Rows are independent, so the results do not change.
 // Measured on B200 (large-v3, 128 rows): 9.3 ms against 8.8 ms for the single chain — the projections of one group
 // queue behind the other group's resident cross-attention CTAs — so the interleave is opt-in (OH_DUAL=<min rows>).
-static int decode_step_all(oh_state* st, int rows, bool with_k9, bool dump) {
+static int decode_step_all(oh_state* st, int rows, int k9_mode) {
     cudaStream_t s = st->stream;
-    if (rows < st->dual_min_rows || dump || g_prof != nullptr) return decode_step_launch(st, 0, rows, with_k9, dump, s);
+    if (rows < st->dual_min_rows || k9_mode == K9_DUMP || k9_mode == K9_TOPK || g_prof != nullptr) return decode_step_launch(st, 0, rows, k9_mode, s);
     const int ra = (rows + 1) / 2;
     int rc;
     OH_CUDA_CHECK(cudaEventRecord(st->ev_dual[0], s));
     OH_CUDA_CHECK(cudaStreamWaitEvent(st->stream2, st->ev_dual[0], 0));
-    if ((rc = decode_step_launch(st, 0, ra, with_k9, false, s, st->ev_dual[1]))) return rc;
+    if ((rc = decode_step_launch(st, 0, ra, k9_mode, s, st->ev_dual[1]))) return rc;
     OH_CUDA_CHECK(cudaStreamWaitEvent(st->stream2, st->ev_dual[1], 0));
-    if ((rc = decode_step_launch(st, ra, rows - ra, with_k9, false, st->stream2))) return rc;
+    if ((rc = decode_step_launch(st, ra, rows - ra, k9_mode, st->stream2))) return rc;
     OH_CUDA_CHECK(cudaEventRecord(st->ev_dual[2], st->stream2));
     OH_CUDA_CHECK(cudaStreamWaitEvent(s, st->ev_dual[2], 0));
     return OH_OK;
 }
 
-int run_decode_step(oh_state* st, int rows, bool dump_probs) { return decode_step_all(st, rows, true, dump_probs); }
+int run_decode_step(oh_state* st, int rows, bool dump_probs) { return decode_step_all(st, rows, dump_probs ? K9_DUMP : K9_GREEDY); }
 
-int run_decode_step_graph(oh_state* st, int rows, bool with_k9) {
-    if (!st->use_graphs || st->profiling) return decode_step_all(st, rows, with_k9, false);
-    const int key = rows * 2 + (with_k9 ? 1 : 0);
+int run_decode_step_graph(oh_state* st, int rows, int k9_mode) {
+    if (!st->use_graphs || st->profiling || k9_mode == K9_DUMP) return decode_step_all(st, rows, k9_mode);
+    if (k9_mode == K9_TOPK) {  // its buffer must exist before the step is captured
+        int rc = ensure(st->topk_dev, (size_t)st->max_batch * (3 * kTopK + 3) * 4);
+        if (rc) return rc;
+    }
+    const bool with_k9 = k9_mode != K9_NONE;
+    const int key = rows * 4 + k9_mode;
     auto it = st->step_graphs.find(key);
     if (it == st->step_graphs.end()) {
         // first use of this row count: one direct step (sets kernel attributes, faults in lazily allocated
         // buffers), capture on the second, replay from then on
         if (!st->warmed_rows.count(key)) {
             st->warmed_rows.insert(key);
-            return decode_step_all(st, rows, with_k9, false);
+            return decode_step_all(st, rows, k9_mode);
         }
         cudaGraph_t graph = nullptr;
         const long long launches_before = g_launch_count;
         OH_CUDA_CHECK(cudaStreamBeginCapture(st->stream, cudaStreamCaptureModeThreadLocal));
-        int rc = decode_step_all(st, rows, with_k9, false);
+        int rc = decode_step_all(st, rows, k9_mode);
         cudaError_t ce = cudaStreamEndCapture(st->stream, &graph);
         g_launch_count = launches_before;  // nothing ran during capture
         if (rc) {
@@ -681,7 +699,7 @@ int decode_tokens_stage(oh_state* st, const int* tokens, int n_tokens, int n_pas
             hs.cur_token[r] = tokens[(size_t)r * n_tokens + i];
         }
         OH_CUDA_CHECK(cudaMemcpyAsync(st->seq_dev.p, hb, seqlay::N_SCALARS * lay.rows * 4, cudaMemcpyHostToDevice, s));
-        if ((rc = run_decode_step_graph(st, batch, false))) return rc;
+        if ((rc = run_decode_step_graph(st, batch, K9_NONE))) return rc;
         OH_CUDA_CHECK(cudaStreamSynchronize(s));
     }
     if (out_logits) {

@@ -95,6 +95,31 @@ struct ParkedRow {  // a window whose t = 0 result failed the A.5 checks: waits 
     std::vector<int> prompt;
 };
 
+// beam search (full.cu): the beam_size decoders of one window and the row group that hosts them
+struct BeamDec {
+    std::vector<TokenData> tokens;
+    int seek_delta = 100 * 30, result_len = 0, line = 0;
+    bool has_ts = false, failed = false, completed = false;
+    double sum_logprobs_all = 0.0;
+    std::vector<TokenData> cand;  // this decoder's top candidates from the last step, best first
+};
+struct BeamCand {
+    int decoder_idx, seek_delta, result_len;
+    bool has_ts;
+    std::vector<TokenData> tokens;
+    double sum_logprobs_all;
+};
+struct BeamGroup {
+    bool busy = false, in_prompt = true;
+    Submission* sub = nullptr;
+    int item = -1, xslot = -1;
+    std::vector<int> prompt;
+    int fed = 0;  // prompt tokens that have gone through the decoder
+    int i = 0;    // index of the token being chosen (A.5's loop variable)
+    std::vector<BeamDec> dec;
+};
+
+
 struct Sched {
     std::deque<std::unique_ptr<Submission>> subs;  // live submissions in ticket order
     int next_ticket = 1;
@@ -111,6 +136,9 @@ struct Sched {
     DecodeRules rules{};
     bool mirror_dirty = false;       // the pinned host mirror of the row scalars has changes that are not on the device yet
     int desc_cursor = 0;             // ring position in the pinned window-descriptor area
+    std::vector<BeamGroup> beam_groups;   // beam search: one group of beam_size rows per window in flight
+    std::vector<int4> beam_kv_copies;     // cache-line copies queued for the next step
+    int beam_nb = 0;
 };
 
 }  // namespace oh
@@ -145,8 +173,9 @@ struct oh_state {
     oh::DevBuf xkv;                // [L][n_slots][2][heads][1500][64]
     oh::DevBuf kself, vself;       // [L][rows][heads][448][64]
     // --- decoder activations (max_batch rows)
-    oh::DevBuf dx, dh, dqkv, datt, dq, dhid, logits, dump_lp, dump_p;
+    oh::DevBuf dx, dh, dqkv, datt, dq, dhid, logits, dump_lp, dump_p, topk_dev;
     int ld_logits = 0;
+    oh::DevBuf beam_pairs;         // beam search: (src line, dst line, positions) of the step's cache-line copies
     oh::DevBuf seq_dev;            // DecodeSeqState arrays
     oh::DevBuf rules_dev;
     oh::DecodeSeqState seq{};
@@ -187,7 +216,8 @@ int run_mel(oh_state* st, const float* const* pcm, const int* n, int batch, bool
 int run_encoder(oh_state* st, int n_windows, int slot0, float* d_enc_f32_out /* nullable, [n_windows][1500][d] */,
                 const int* slot_list = nullptr, cudaStream_t stream = nullptr /* default: the decode stream */);
 int run_decode_step(oh_state* st, int rows, bool dump_probs);
-int run_decode_step_graph(oh_state* st, int rows, bool with_k9 = true);
+enum { K9_NONE = 0, K9_GREEDY = 1, K9_DUMP = 2, K9_TOPK = 3 };  // what follows the logit projection of a step
+int run_decode_step_graph(oh_state* st, int rows, int k9_mode = K9_GREEDY);
 
 // the full() driver (full.cu)
 int run_full(oh_state* st, const oh_full_params& p, const float* const* pcm, const int* n, int batch, bool pcm_on_device);

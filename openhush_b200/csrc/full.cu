@@ -290,289 +290,19 @@ static int decode_pass(oh_state* st, const oh_full_params& p, bool no_timestamps
 // Greedy) and the pinned upstream's candidate sampler cannot be verified offline, so this follows SURVEY.md A.5/A.7
 // as written — per live decoder the top beam_size ids of the filtered distribution, candidates ranked by
 // sum_logprobs_all, assigned to the decoders in order skipping repeats, KV cache inherited from the proposing decoder
-// — decision for decision the same procedure the test oracle restates.  The beam_size decoders of a window are
-// beam_size rows that share ONE cross-attention K/V slot (the window is encoded once, its K/V is never replicated) and
-// own one self-attention cache line each; a line follows its candidate by index and is copied only when two decoders
-// inherit it.
+// — decision for decision the same procedure the test oracle restates.
+//
+// Batched: the resident rows are cut into groups of beam_size rows; a group decodes one window, its rows are the window's
+// decoders.  The decoders of a window share ONE cross-attention K/V slot (the window is encoded once and its K/V is
+// streamed by beam_size rows that run side by side, so after the first row the reads hit L2) and own one self-attention
+// cache line each; a line follows its candidate by index and is copied (one batched kernel per step) only when two
+// decoders inherit it.  K9 runs in top-k mode: every row reports its beam_size best ids with logprob / prob and the
+// timestamp statistics; the host ranks the candidates of each group and writes the rows' next state.  Windows of all live
+// items decode at once (one host look-in per step), finished groups are re-armed from the encoder's look-ahead.
 namespace {
 
-struct BeamDec {
-    std::vector<TokenData> tokens;
-    int seek_delta = 100 * 30, result_len = 0, line = 0;
-    bool has_ts = false, failed = false, completed = false;
-    double sum_logprobs_all = 0.0;
-    std::vector<float> probs, logprobs;
-};
-struct BeamCand {
-    int decoder_idx, seek_delta, result_len;
-    bool has_ts;
-    std::vector<TokenData> tokens;
-    double sum_logprobs_all;
-};
-
-// the k most probable ids, best first (ties: lower id); tid / pt / ptsum as for every sampled token (A.7)
-std::vector<TokenData> topk_on_host(const Vocab& vc, const float* probs, const float* logprobs, int k) {
-    const TokenData base = timestamp_stats(vc, probs);
-    std::vector<int> ids(vc.n_vocab);
-    for (int i = 0; i < vc.n_vocab; ++i) ids[i] = i;
-    k = std::min(k, vc.n_vocab);
-    std::partial_sort(ids.begin(), ids.begin() + k, ids.end(), [&](int a, int b) {
-        if (logprobs[a] != logprobs[b]) return logprobs[a] > logprobs[b];
-        return a < b;
-    });
-    std::vector<TokenData> out;
-    for (int c = 0; c < k; ++c) {
-        TokenData r = base;
-        r.id = ids[c];
-        r.p = probs[r.id];
-        r.plog = logprobs[r.id];
-        if (r.id >= vc.token_beg) {
-            r.tid = r.id;
-            r.pt = r.p;
-        }
-        out.push_back(r);
-    }
-    return out;
-}
-
-int copy_self_kv(oh_state* st, int src_line, int dst_line) {
-    const HParams& hp = st->ctx->model->hp;
-    const size_t per_line = (size_t)hp.n_text_ctx * hp.n_text_state * st->esz;
-    for (int l = 0; l < hp.n_text_layer; ++l) {
-        const size_t base = (size_t)l * st->max_batch * per_line;
-        OH_CUDA_CHECK(cudaMemcpyAsync((char*)st->kself.p + base + dst_line * per_line, (char*)st->kself.p + base + src_line * per_line, per_line,
-                                      cudaMemcpyDeviceToDevice, st->stream));
-        OH_CUDA_CHECK(cudaMemcpyAsync((char*)st->vself.p + base + dst_line * per_line, (char*)st->vself.p + base + src_line * per_line, per_line,
-                                      cudaMemcpyDeviceToDevice, st->stream));
-    }
-    return OH_OK;
-}
-
-// one window, temperature 0, nb decoders on rows / cache lines 0..nb-1, all reading the window's cross K/V in `xslot`
-int beam_pass(oh_state* st, const oh_full_params& p, bool no_timestamps, const Item& it, const std::vector<int>& prompt, int nb, int xslot,
-              PassResult& best) {
-    const Model& m = *st->ctx->model;
-    const Vocab& vc = m.vocab;
-    const int n_max = m.hp.n_text_ctx / 2 - 4;
-    const int pl = (int)prompt.size();
-    if (pl > kMaxPrompt || pl < 1) {
-        set_error("prompt too long");
-        return OH_ERR_DECODE;
-    }
-    SeqLayout lay(st->max_batch);
-    int32_t* hb = (int32_t*)st->pinned;
-    DecodeSeqState hs = seq_view(hb, lay);
-    memset(hb, 0, lay.total_words * 4);
-    for (int r = 0; r < nb; ++r) {
-        hs.slot[r] = xslot;
-        hs.sslot[r] = r;
-        hs.prompt_len[r] = pl;
-        for (int i = 0; i < pl; ++i) hs.prompt[(size_t)r * kMaxPrompt + i] = prompt[i];
-        hs.seek_delta[r] = 100 * 30;
-        hs.seek[r] = it.seek;
-        hs.seek_end[r] = it.seek_end;
-    }
-    hs.active[0] = 1;
-    hs.cur_token[0] = prompt[0];
-    const DecodeRules R = make_rules(m, p, no_timestamps, 0.0f);
-    cudaStream_t s = st->stream;
-    OH_CUDA_CHECK(cudaMemcpyAsync(st->seq_dev.p, hb, lay.total_words * 4, cudaMemcpyHostToDevice, s));
-    OH_CUDA_CHECK(cudaMemcpyAsync(st->rules_dev.p, &R, sizeof R, cudaMemcpyHostToDevice, s));
-    OH_CUDA_CHECK(cudaStreamSynchronize(s));
-    st->sched.rules_valid = false;
-    const size_t ld = st->ld_logits;
-    int rc;
-    auto upload_rows = [&]() -> int {  // scalars, prompts and sampled-token ids (the kernel reads the last two ids of a row)
-        OH_CUDA_CHECK(cudaMemcpyAsync(st->seq_dev.p, hb, lay.tok_off[1] * 4, cudaMemcpyHostToDevice, s));
-        st->timings.h2d_bytes += (long long)lay.tok_off[1] * 4;
-        return OH_OK;
-    };
-    // the prompt through decoder 0 (A.5: "decode(prompt) -> process_logits(decoder0, is_initial)")
-    // (the kernel advances pos / cur_token through the prompt on the device by itself; the pinned host mirror must not be
-    // touched while an asynchronous upload of it could still be in flight, so nothing is uploaded in this phase)
-    for (int i = 0; i < pl; ++i) {
-        if ((rc = run_decode_step(st, nb, true))) return rc;
-        st->timings.n_decode_steps++;
-    }
-    hs.pos[0] = pl - 1;
-    hs.cur_token[0] = prompt[pl - 1];
-    std::vector<BeamDec> dec(nb);
-    dec[0].probs.resize(ld);
-    dec[0].logprobs.resize(ld);
-    OH_CUDA_CHECK(cudaMemcpyAsync(dec[0].probs.data(), st->dump_p.p, ld * 4, cudaMemcpyDeviceToHost, s));
-    OH_CUDA_CHECK(cudaMemcpyAsync(dec[0].logprobs.data(), st->dump_lp.p, ld * 4, cudaMemcpyDeviceToHost, s));
-    st->timings.d2h_bytes += (long long)ld * 8;
-    for (int j = 1; j < nb; ++j)  // "copy logits/probs/kv to the other decoders"
-        if ((rc = copy_self_kv(st, 0, j))) return rc;
-    OH_CUDA_CHECK(cudaStreamSynchronize(s));
-    for (int j = 0; j < nb; ++j) {
-        dec[j].line = j;
-        if (j > 0) {
-            dec[j].probs = dec[0].probs;
-            dec[j].logprobs = dec[0].logprobs;
-        }
-    }
-
-    for (int i = 0; i < n_max; ++i) {
-        // ---- candidates of every live decoder, ranked
-        std::vector<BeamCand> cands;
-        for (int j = 0; j < nb; ++j) {
-            BeamDec& d = dec[j];
-            if (d.completed || d.failed) continue;
-            for (const TokenData& tok : topk_on_host(vc, d.probs.data(), d.logprobs.data(), nb)) {
-                BeamCand c{j, d.seek_delta, d.result_len, d.has_ts, d.tokens, d.sum_logprobs_all + tok.plog};
-                c.tokens.push_back(tok);
-                cands.push_back(std::move(c));
-            }
-        }
-        std::stable_sort(cands.begin(), cands.end(), [](const BeamCand& a, const BeamCand& b) {
-            if (a.sum_logprobs_all != b.sum_logprobs_all) return a.sum_logprobs_all > b.sum_logprobs_all;
-            return a.decoder_idx < b.decoder_idx;
-        });
-        auto same_tokens = [](const BeamCand& a, const BeamCand& b) {
-            if (a.tokens.size() != b.tokens.size()) return false;
-            for (size_t q = 0; q < a.tokens.size(); ++q)
-                if (a.tokens[q].id != b.tokens[q].id) return false;
-            return true;
-        };
-        std::vector<int> take(nb, -1);
-        size_t cur_c = 0;
-        for (int j = 0; j < nb; ++j) {
-            if (dec[j].completed || dec[j].failed) continue;
-            if (cur_c >= cands.size()) cur_c = 0;
-            const size_t pick = cur_c++;
-            while (cur_c < cands.size() && i > 0 && same_tokens(cands[cur_c], cands[pick])) ++cur_c;
-            take[j] = (int)pick;
-        }
-        // ---- self-attention cache lines follow the candidates: a line moves with its index; only a line that two decoders
-        // inherit (or that its owner keeps while another decoder inherits it) is copied, into the line of a decoder that nobody follows
-        std::vector<int> old_line(nb), new_line(nb, -1);
-        std::vector<char> claimed(st->max_batch, 0);
-        for (int j = 0; j < nb; ++j) old_line[j] = dec[j].line;
-        for (int j = 0; j < nb; ++j)
-            if (take[j] >= 0 && cands[take[j]].decoder_idx == j) {
-                new_line[j] = old_line[j];
-                claimed[old_line[j]] = 1;
-            }
-        for (int j = 0; j < nb; ++j)
-            if (take[j] >= 0 && new_line[j] < 0) {
-                const int src = old_line[cands[take[j]].decoder_idx];
-                if (!claimed[src]) {
-                    new_line[j] = src;
-                    claimed[src] = 1;
-                }
-            }
-        for (int j = 0; j < nb; ++j)
-            if (take[j] >= 0 && new_line[j] < 0) {
-                int f = -1;
-                for (int q = 0; q < nb; ++q)
-                    if (!claimed[old_line[q]]) {
-                        f = old_line[q];
-                        break;
-                    }
-                if (f < 0) {
-                    set_error("beam search: no free cache line");
-                    return OH_ERR_DECODE;
-                }
-                if ((rc = copy_self_kv(st, old_line[cands[take[j]].decoder_idx], f))) return rc;
-                new_line[j] = f;
-                claimed[f] = 1;
-            }
-        {   // decoders that are finished keep distinct (unused) lines
-            int q = 0;
-            for (int j = 0; j < nb; ++j)
-                if (new_line[j] < 0) {
-                    while (claimed[old_line[q]]) ++q;
-                    new_line[j] = old_line[q];
-                    claimed[old_line[q]] = 1;
-                }
-        }
-        for (int j = 0; j < nb; ++j) {
-            dec[j].line = new_line[j];
-            if (take[j] < 0) continue;
-            const BeamCand& c = cands[take[j]];
-            dec[j].tokens = c.tokens;
-            dec[j].seek_delta = c.seek_delta;
-            dec[j].has_ts = c.has_ts;
-            dec[j].result_len = c.result_len;
-            dec[j].sum_logprobs_all = c.sum_logprobs_all;
-        }
-        // ---- A.5 bookkeeping for the token each live decoder ended up with
-        bool all_done = true;
-        for (int j = 0; j < nb; ++j) {
-            BeamDec& d = dec[j];
-            if (d.completed || d.failed) continue;
-            SeqFlags f{d.has_ts ? 1 : 0, d.seek_delta, d.result_len, 0, 0};
-            apply_token_rules(f, d.tokens.back().id, i, it.seek, it.seek_end, vc.token_beg, vc.token_eot, p.max_tokens, no_timestamps, p.single_segment,
-                              n_max);
-            d.has_ts = f.has_ts != 0;
-            d.seek_delta = f.seek_delta;
-            d.result_len = f.result_len;
-            d.failed = f.failed != 0;
-            d.completed = f.completed != 0;
-            if (!d.completed && !d.failed) all_done = false;
-        }
-        if (all_done || i + 1 == n_max) break;
-        // ---- one token per live decoder
-        for (int j = 0; j < nb; ++j) {
-            const BeamDec& d = dec[j];
-            const bool live = !d.completed && !d.failed;
-            hs.active[j] = live ? 1 : 0;
-            hs.sslot[j] = d.line;
-            if (!live) continue;
-            hs.pos[j] = pl + i;
-            hs.cur_token[j] = d.tokens.back().id;
-            hs.n_gen[j] = (int)d.tokens.size();
-            hs.has_ts[j] = d.has_ts ? 1 : 0;
-            hs.seek_delta[j] = d.seek_delta;
-            hs.result_len[j] = d.result_len;
-            for (size_t q = 0; q < d.tokens.size(); ++q) hs.tok_id[(size_t)j * kMaxGen + q] = d.tokens[q].id;
-        }
-        if ((rc = upload_rows())) return rc;
-        if ((rc = run_decode_step(st, nb, true))) return rc;
-        st->timings.n_decode_steps++;
-        for (int j = 0; j < nb; ++j) {
-            BeamDec& d = dec[j];
-            if (d.completed || d.failed) continue;
-            d.probs.resize(ld);
-            d.logprobs.resize(ld);
-            OH_CUDA_CHECK(cudaMemcpyAsync(d.probs.data(), (float*)st->dump_p.p + (size_t)j * ld, ld * 4, cudaMemcpyDeviceToHost, s));
-            OH_CUDA_CHECK(cudaMemcpyAsync(d.logprobs.data(), (float*)st->dump_lp.p + (size_t)j * ld, ld * 4, cudaMemcpyDeviceToHost, s));
-            st->timings.d2h_bytes += (long long)ld * 8;
-        }
-        OH_CUDA_CHECK(cudaStreamSynchronize(s));
-    }
-    // ---- rank the decoders (A.5 / A.8): first best score among the ones that did not fail
-    double best_score = -INFINITY;
-    int best_id = 0;
-    std::vector<PassResult> res(nb);
-    for (int j = 0; j < nb; ++j) {
-        PassResult& r = res[j];
-        const BeamDec& d = dec[j];
-        r.tokens = d.tokens;
-        r.result_len = d.result_len;
-        r.seek_delta = d.seek_delta;
-        r.has_ts = d.has_ts;
-        r.failed = d.failed;
-        r.completed = d.completed;
-        if (r.failed) continue;
-        r.tokens.resize(std::min<size_t>(r.tokens.size(), (size_t)r.result_len));
-        sequence_score(p, r);
-        if (r.result_len > 32 && r.entropy < p.entropy_thold) {
-            r.failed = true;
-            continue;
-        }
-        if (best_score < r.score) {
-            best_score = r.score;
-            best_id = j;
-        }
-    }
-    best = res[best_id];
-    for (const BeamDec& d : dec) st->timings.n_tokens += (int)d.tokens.size();
-    return OH_OK;
-}
-
 }  // namespace
+
 
 // --------------------------------------------------------------------------------------------------- scheduler
 namespace {
@@ -888,9 +618,391 @@ struct Pump {
         return OH_OK;
     }
 
+    // ---- beam search: groups of beam_size rows (state lives in the scheduler: windows outlive a wait) -------------------
+    std::vector<BeamGroup>& groups = sc.beam_groups;
+    std::vector<int4>& kv_copies = sc.beam_kv_copies;  // (src line, dst line, positions) queued for the next step
+
+    void beam_set_idle_rows(int g, int nb) {
+        for (int j = 0; j < nb; ++j) hs.active[g * nb + j] = 0;
+    }
+    int beam_start(int g, int nb, const WinRef& w) {
+        BeamGroup& G = groups[g];
+        Item& it = w.sub->items[w.item];
+        if (it.seek > 0 && it.seek + 500 >= it.seek_end) it.prompt_past.clear();  // short tail: drop the prompt (upstream behaviour)
+        std::vector<int> prompt;
+        build_prompt(*w.sub, hp, vc, it, w.sub->temperatures[0], prompt);
+        const int pl = (int)prompt.size();
+        if (pl > kMaxPrompt || pl < 1) {
+            set_error("prompt too long");
+            return OH_ERR_DECODE;
+        }
+        if (w.sub->temperatures[0] > 0.0f) {  // A.5: at t > 0 beam search runs best_of sampled decoders: the lock-step ladder path
+            sc.parked.push_back(ParkedRow{w.sub, w.item, w.slot, std::move(prompt)});
+            return OH_OK;
+        }
+        G = BeamGroup();
+        G.busy = true;
+        G.sub = w.sub;
+        G.item = w.item;
+        G.xslot = w.slot;
+        G.prompt = std::move(prompt);
+        G.dec.assign(nb, BeamDec());
+        for (int j = 0; j < nb; ++j) {
+            const int r = g * nb + j;
+            hs.slot[r] = w.slot;
+            hs.sslot[r] = r;
+            hs.active[r] = j == 0 ? 1 : 0;
+            hs.pos[r] = 0;
+            hs.cur_token[r] = G.prompt[0];
+            hs.prompt_len[r] = pl;
+            for (int q = 0; q < pl; ++q) hs.prompt[(size_t)r * kMaxPrompt + q] = G.prompt[q];
+            hs.n_gen[r] = 0;
+            hs.has_ts[r] = 0;
+            hs.seek_delta[r] = 100 * 30;
+            hs.result_len[r] = 0;
+            hs.failed[r] = 0;
+            hs.completed[r] = 0;
+            hs.seek[r] = it.seek;
+            hs.seek_end[r] = it.seek_end;
+            G.dec[j].line = r;
+        }
+        st->timings.n_prompt_steps += pl - 1;
+        return OH_OK;
+    }
+    // candidates of row r from the step's top-k block (beam_size best; a distribution with fewer live ids is padded with
+    // the lowest absent ids at logprob -inf, which is what a partial sort over the whole vocabulary yields)
+    void beam_read_cands(const int32_t* tk, int r, int nb, std::vector<TokenData>& out) {
+        const size_t Rr = (size_t)R;
+        const int32_t* ids = tk + (size_t)r * kTopK;
+        const float* lps = (const float*)(tk + Rr * kTopK) + (size_t)r * kTopK;
+        const float* ps = (const float*)(tk + 2 * Rr * kTopK) + (size_t)r * kTopK;
+        TokenData base;
+        base.tid = tk[3 * Rr * kTopK + r];
+        base.pt = ((const float*)(tk + 3 * Rr * kTopK + Rr))[r];
+        base.ptsum = ((const float*)(tk + 3 * Rr * kTopK + 2 * Rr))[r];
+        out.clear();
+        for (int c = 0; c < nb; ++c) {
+            TokenData t = base;
+            if (ids[c] >= 0) {
+                t.id = ids[c];
+                t.p = ps[c];
+                t.plog = lps[c];
+            } else {
+                int cand = 0;
+                auto used = [&](int id) {
+                    for (const TokenData& u : out)
+                        if (u.id == id) return true;
+                    return false;
+                };
+                while (used(cand)) ++cand;
+                t.id = cand;
+                t.p = 0.0f;
+                t.plog = -INFINITY;
+            }
+            if (t.id >= vc.token_beg) {
+                t.tid = t.id;
+                t.pt = t.p;
+            }
+            out.push_back(t);
+        }
+    }
+    // one A.5 iteration for group g after a step: rank candidates, hand them out, move / copy cache lines, apply the
+    // per-token rules; returns true when the window is finished (result in `best`)
+    int beam_select(int g, int nb, bool& finished, PassResult& best) {
+        BeamGroup& G = groups[g];
+        std::vector<BeamDec>& dec = G.dec;
+        const Item& it = G.sub->items[G.item];
+        const oh_full_params& p = G.sub->p;
+        const int pl = (int)G.prompt.size(), i = G.i;
+        finished = false;
+        std::vector<BeamCand> cands;
+        for (int j = 0; j < nb; ++j) {
+            BeamDec& d = dec[j];
+            if (d.completed || d.failed) continue;
+            for (const TokenData& tok : d.cand) {
+                BeamCand c{j, d.seek_delta, d.result_len, d.has_ts, d.tokens, d.sum_logprobs_all + tok.plog};
+                c.tokens.push_back(tok);
+                cands.push_back(std::move(c));
+            }
+        }
+        std::stable_sort(cands.begin(), cands.end(), [](const BeamCand& a, const BeamCand& b) {
+            if (a.sum_logprobs_all != b.sum_logprobs_all) return a.sum_logprobs_all > b.sum_logprobs_all;
+            return a.decoder_idx < b.decoder_idx;
+        });
+        auto same_tokens = [](const BeamCand& a, const BeamCand& b) {
+            if (a.tokens.size() != b.tokens.size()) return false;
+            for (size_t q = 0; q < a.tokens.size(); ++q)
+                if (a.tokens[q].id != b.tokens[q].id) return false;
+            return true;
+        };
+        std::vector<int> take(nb, -1);
+        size_t cur_c = 0;
+        for (int j = 0; j < nb; ++j) {
+            if (dec[j].completed || dec[j].failed) continue;
+            if (cur_c >= cands.size()) cur_c = 0;
+            const size_t pick = cur_c++;
+            while (cur_c < cands.size() && i > 0 && same_tokens(cands[cur_c], cands[pick])) ++cur_c;
+            take[j] = (int)pick;
+        }
+        // ---- cache lines follow the candidates: a line moves with its index; only a line that two decoders inherit (or that
+        // its owner keeps while another decoder inherits it) is copied, into the line of a decoder that nobody follows
+        std::vector<int> old_line(nb), new_line(nb, -1);
+        std::vector<char> claimed(nb, 0);  // indexed by line - g * nb
+        const int l0 = g * nb;
+        for (int j = 0; j < nb; ++j) old_line[j] = dec[j].line;
+        for (int j = 0; j < nb; ++j)
+            if (take[j] >= 0 && cands[take[j]].decoder_idx == j) {
+                new_line[j] = old_line[j];
+                claimed[old_line[j] - l0] = 1;
+            }
+        for (int j = 0; j < nb; ++j)
+            if (take[j] >= 0 && new_line[j] < 0) {
+                const int src = old_line[cands[take[j]].decoder_idx];
+                if (!claimed[src - l0]) {
+                    new_line[j] = src;
+                    claimed[src - l0] = 1;
+                }
+            }
+        for (int j = 0; j < nb; ++j)
+            if (take[j] >= 0 && new_line[j] < 0) {
+                int f = -1;
+                for (int q = 0; q < nb; ++q)
+                    if (!claimed[old_line[q] - l0]) {
+                        f = old_line[q];
+                        break;
+                    }
+                if (f < 0) {
+                    set_error("beam search: no free cache line");
+                    return OH_ERR_DECODE;
+                }
+                kv_copies.push_back(make_int4(old_line[cands[take[j]].decoder_idx], f, pl + i, 0));
+                new_line[j] = f;
+                claimed[f - l0] = 1;
+            }
+        {   // decoders that are finished keep distinct (unused) lines
+            int q = 0;
+            for (int j = 0; j < nb; ++j)
+                if (new_line[j] < 0) {
+                    while (claimed[old_line[q] - l0]) ++q;
+                    new_line[j] = old_line[q];
+                    claimed[old_line[q] - l0] = 1;
+                }
+        }
+        for (int j = 0; j < nb; ++j) {
+            dec[j].line = new_line[j];
+            if (take[j] < 0) continue;
+            const BeamCand& c = cands[take[j]];
+            dec[j].tokens = c.tokens;
+            dec[j].seek_delta = c.seek_delta;
+            dec[j].has_ts = c.has_ts;
+            dec[j].result_len = c.result_len;
+            dec[j].sum_logprobs_all = c.sum_logprobs_all;
+        }
+        // ---- A.5 bookkeeping for the token each live decoder ended up with
+        bool all_done = true;
+        for (int j = 0; j < nb; ++j) {
+            BeamDec& d = dec[j];
+            if (d.completed || d.failed) continue;
+            SeqFlags f{d.has_ts ? 1 : 0, d.seek_delta, d.result_len, 0, 0};
+            apply_token_rules(f, d.tokens.back().id, i, it.seek, it.seek_end, vc.token_beg, vc.token_eot, p.max_tokens, G.sub->no_timestamps,
+                              p.single_segment, n_max);
+            d.has_ts = f.has_ts != 0;
+            d.seek_delta = f.seek_delta;
+            d.result_len = f.result_len;
+            d.failed = f.failed != 0;
+            d.completed = f.completed != 0;
+            if (!d.completed && !d.failed) all_done = false;
+        }
+        if (all_done || i + 1 == n_max) {
+            // ---- rank the decoders (A.5 / A.8): first best score among the ones that did not fail
+            double best_score = -INFINITY;
+            int best_id = 0;
+            std::vector<PassResult> res(nb);
+            for (int j = 0; j < nb; ++j) {
+                PassResult& r = res[j];
+                const BeamDec& d = dec[j];
+                r.tokens = d.tokens;
+                r.result_len = d.result_len;
+                r.seek_delta = d.seek_delta;
+                r.has_ts = d.has_ts;
+                r.failed = d.failed;
+                r.completed = d.completed;
+                st->timings.n_tokens += (int)d.tokens.size();
+                if (r.failed) continue;
+                r.tokens.resize(std::min<size_t>(r.tokens.size(), (size_t)r.result_len));
+                sequence_score(p, r);
+                if (r.result_len > 32 && r.entropy < p.entropy_thold) {
+                    r.failed = true;
+                    continue;
+                }
+                if (best_score < r.score) {
+                    best_score = r.score;
+                    best_id = j;
+                }
+            }
+            best = res[best_id];
+            finished = true;
+            return OH_OK;
+        }
+        // ---- one token per live decoder
+        for (int j = 0; j < nb; ++j) {
+            const BeamDec& d = dec[j];
+            const int r = g * nb + j;
+            const bool live = !d.completed && !d.failed;
+            hs.active[r] = live ? 1 : 0;
+            hs.sslot[r] = d.line;
+            if (!live) continue;
+            hs.pos[r] = pl + i;
+            hs.cur_token[r] = d.tokens.back().id;
+            hs.n_gen[r] = (int)d.tokens.size();
+            hs.has_ts[r] = d.has_ts ? 1 : 0;
+            hs.seek_delta[r] = d.seek_delta;
+            hs.result_len[r] = d.result_len;
+            for (size_t q = 0; q < d.tokens.size(); ++q) hs.tok_id[(size_t)r * kMaxGen + q] = d.tokens[q].id;
+        }
+        G.i = i + 1;
+        return OH_OK;
+    }
+
+    int run_beam(const Submission* target, int nb) {
+        const int NG = R / nb, rows_used = NG * nb;
+        cudaStream_t s = st->stream;
+        const size_t tk_words = (size_t)R * (3 * kTopK + 3);
+        std::vector<int32_t> tk(tk_words);
+        int rc;
+        if ((int)groups.size() != NG || sc.beam_nb != nb) {
+            // first beam pass of this policy (a policy change drains the scheduler first, so nothing is in flight): the
+            // groups start idle and whatever the row-state block held belongs to nobody
+            groups.assign(NG, BeamGroup());
+            kv_copies.clear();
+            sc.beam_nb = nb;
+            memset(hb, 0, lay.total_words * 4);
+        }
+        if ((rc = ensure(st->beam_pairs, (size_t)R * sizeof(int4)))) return rc;
+        while (target ? !target->finished() : true) {
+            poll_passes(false);
+            if ((rc = launch_passes())) return rc;
+            int n_busy = 0;
+            for (int g = 0; g < NG; ++g) {
+                if (!groups[g].busy && !sc.ready.empty() && sc.parked.empty()) {
+                    WinRef w = sc.ready.front();
+                    sc.ready.pop_front();
+                    if ((rc = beam_start(g, nb, w))) return rc;
+                }
+                n_busy += groups[g].busy ? 1 : 0;
+            }
+            if (n_busy > 0 && NG - n_busy >= std::max(1, st->starve_rows / nb) && sc.ready.empty() && !sc.passes.empty() && sc.parked.empty()) {
+                poll_passes(true);  // decode yields to the encoder pass in flight when groups run empty (see run())
+                continue;
+            }
+            if (n_busy == 0) {
+                if (!sc.parked.empty()) {
+                    if ((rc = run_ladder())) return rc;
+                    memset(hb, 0, lay.total_words * 4);
+                    continue;
+                }
+                if (!sc.ready.empty()) continue;
+                if (!sc.passes.empty()) {
+                    poll_passes(true);
+                    continue;
+                }
+                if (!sc.need_window.empty()) {
+                    if (sc.free_slots.empty()) {
+                        set_error("scheduler: windows waiting, nothing running and no free K/V slot");
+                        return OH_ERR_DECODE;
+                    }
+                    continue;
+                }
+                break;
+            }
+            const auto t0 = clk::now();
+            if ((rc = ensure_rules(groups[std::find_if(groups.begin(), groups.end(), [](const BeamGroup& G) { return G.busy; }) - groups.begin()].sub))) return rc;
+            // rows' state for this step (the host is authoritative in beam mode), queued cache-line copies, the step, the candidates back
+            OH_CUDA_CHECK(cudaMemcpyAsync(st->seq_dev.p, hb, lay.tok_off[1] * 4, cudaMemcpyHostToDevice, s));
+            st->timings.h2d_bytes += (long long)lay.tok_off[1] * 4;
+            if (!kv_copies.empty()) {
+                OH_CUDA_CHECK(cudaMemcpyAsync(st->beam_pairs.p, kv_copies.data(), kv_copies.size() * sizeof(int4), cudaMemcpyHostToDevice, s));
+                if ((rc = launch_copy_self_lines(st->kself.p, st->vself.p, st->esz, (const int4*)st->beam_pairs.p, (int)kv_copies.size(), hp.n_text_layer, R,
+                                                 hp.n_text_state / kHeadDim, hp.n_text_ctx, s)))
+                    return rc;
+            }
+            g_active_rows_hint = n_busy * nb;
+            rc = run_decode_step_graph(st, rows_used, K9_TOPK);
+            g_active_rows_hint = -1;
+            if (rc) return rc == OH_ERR_CUDA ? rc : OH_ERR_DECODE;
+            st->timings.n_decode_steps++;
+            st->timings.n_row_steps += rows_used;
+            st->timings.n_armed_row_steps += n_busy * nb;
+            OH_CUDA_CHECK(cudaMemcpyAsync(tk.data(), st->topk_dev.p, tk_words * 4, cudaMemcpyDeviceToHost, s));
+            OH_CUDA_CHECK(cudaStreamSynchronize(s));  // also: kv_copies (pageable) was consumed
+            st->timings.d2h_bytes += (long long)tk_words * 4;
+            kv_copies.clear();
+            for (int g = 0; g < NG; ++g) {
+                BeamGroup& G = groups[g];
+                if (!G.busy) continue;
+                const int r0 = g * nb, pl = (int)G.prompt.size();
+                if (G.in_prompt) {
+                    G.fed++;
+                    if (G.fed < pl) {  // A.5: "decode(prompt)" through decoder 0, one token per step
+                        hs.pos[r0] = G.fed;
+                        hs.cur_token[r0] = G.prompt[G.fed];
+                        continue;
+                    }
+                    // the prompt is in: decoder 0's distribution and cache go to every decoder ("copy logits/probs/kv")
+                    G.in_prompt = false;
+                    beam_read_cands(tk.data(), r0, nb, G.dec[0].cand);
+                    for (int j = 1; j < nb; ++j) {
+                        G.dec[j].cand = G.dec[0].cand;
+                        kv_copies.push_back(make_int4(r0, r0 + j, pl, 0));
+                    }
+                } else {
+                    for (int j = 0; j < nb; ++j)
+                        if (!G.dec[j].completed && !G.dec[j].failed) beam_read_cands(tk.data(), r0 + j, nb, G.dec[j].cand);
+                }
+                bool finished = false;
+                PassResult best;
+                const size_t copies_mark = kv_copies.size();
+                const bool first_selection = G.i == 0;
+                if ((rc = beam_select(g, nb, finished, best))) return rc;
+                if (first_selection)  // every line of the group is (about to be) a copy of decoder 0's: read the original, the
+                    for (size_t q = copies_mark; q < kv_copies.size(); ++q) kv_copies[q].x = r0;  // copies of one batch run unordered
+                if (finished) {
+                    // cache-line copies queued by this very selection are moot
+                    kv_copies.erase(std::remove_if(kv_copies.begin(), kv_copies.end(), [&](const int4& c) { return c.y >= r0 && c.y < r0 + nb; }),
+                                    kv_copies.end());
+                    // A.5: fall back to the temperature ladder when the best beam fails the checks
+                    const Submission* sub = G.sub;
+                    const bool accept = sub->temperatures.size() == 1 || !(best.failed || best.avg_logprobs < sub->p.logprob_thold);
+                    if (accept) finish_window(G.sub, G.item, G.xslot, G.prompt, best);
+                    else {
+                        st->timings.n_fallbacks++;
+                        sc.parked.push_back(ParkedRow{G.sub, G.item, G.xslot, G.prompt});
+                    }
+                    beam_set_idle_rows(g, nb);
+                    G.busy = false;
+                }
+            }
+            st->timings.decode_ms += ms_since(t0);
+        }
+        bool any_busy = false;
+        for (const BeamGroup& G : groups) any_busy |= G.busy;
+        if (!any_busy) {  // idle: leave a clean row-state block behind (the greedy path relies on it)
+            groups.clear();
+            kv_copies.clear();
+            memset(hb, 0, lay.total_words * 4);
+            OH_CUDA_CHECK(cudaMemcpyAsync(st->seq_dev.p, hb, lay.total_words * 4, cudaMemcpyHostToDevice, s));
+            OH_CUDA_CHECK(cudaStreamSynchronize(s));
+            sc.mirror_dirty = false;
+        }
+        return OH_OK;
+    }
+
     // run until `target` has finished (nullptr: until nothing is left)
     int run(const Submission* target) {
         int rc;
+        // live submissions share one decode policy (sched_submit): beam search has its own loop over row groups
+        for (auto& sb : sc.subs)
+            if (!sb->finished() && sb->p.strategy == OH_SAMPLING_BEAM_SEARCH) return run_beam(target, std::max(1, sb->p.beam_size));
         while (target ? !target->finished() : true) {
             poll_passes(false);
             if ((rc = launch_passes())) return rc;
@@ -939,89 +1051,6 @@ bool same_policy(const oh_full_params& a, const oh_full_params& b, const std::st
 
 }  // namespace
 
-// full() for strategy = BEAM_SEARCH: the submission's items one after the other, windows in order (A.5), beam_size decoder
-// rows sharing the window's cross K/V slot.  Runs with the scheduler drained.
-static int run_beam_submission(oh_state* st, Submission* sub) {
-    const Model& m = *st->ctx->model;
-    const Vocab& vc = m.vocab;
-    const HParams& hp = m.hp;
-    const oh_full_params& p = sub->p;
-    Sched& sc = st->sched;
-    const int nb = std::max(1, p.beam_size);
-    if (nb > st->max_batch) {
-        set_error("beam search needs oh_context_params.max_batch >= beam_size (one decoder row per beam)");
-        return OH_ERR_INVALID;
-    }
-    cudaStream_t s = st->stream;
-    OH_CUDA_CHECK(cudaStreamWaitEvent(s, sub->ev_mel, 0));
-    int rc;
-    const int xslot = sc.free_slots.back();  // every slot is free while the scheduler is drained; the window's K/V lives here
-    for (int i = 0; i < (int)sub->items.size(); ++i) {
-        Item& it = sub->items[i];
-        while (!it.done) {
-            if (it.seek + 100 >= it.seek_end) {
-                it.done = true;
-                break;
-            }
-            // ---- encode the window once; every beam reads the same slot
-            auto t0 = clk::now();
-            WindowDesc* hd = st->win_desc_host;
-            hd->raw = (const float*)sub->mel_raw.p + (size_t)i * hp.n_mels * sub->mel_ld;
-            hd->max_key = clip_max_key(sub->clip_meta, (int)sub->items.size(), i);
-            hd->ld = sub->mel_ld;
-            hd->n_active = it.n_active;
-            hd->n_len = it.n_len;
-            hd->seek = it.seek;
-            OH_CUDA_CHECK(cudaMemcpyAsync(st->win_desc.p, hd, sizeof(WindowDesc), cudaMemcpyHostToDevice, s));
-            if ((rc = launch_window_gather((const WindowDesc*)st->win_desc.p, hp.n_mels, 1, st->xin.p, st->ctx->act_type, s))) return rc == OH_ERR_CUDA ? rc : OH_ERR_ENCODE;
-            if ((rc = run_encoder(st, 1, 0, nullptr, &xslot, s))) return rc == OH_ERR_CUDA ? rc : OH_ERR_ENCODE;
-            OH_CUDA_CHECK(cudaStreamSynchronize(s));  // the pinned descriptor is reused by the next window
-            st->timings.n_windows++;
-            st->timings.encode_ms += ms_since(t0);
-            if (it.seek > 0 && it.seek + 500 >= it.seek_end) it.prompt_past.clear();  // short tail: drop the prompt (upstream behaviour)
-
-            auto t1 = clk::now();
-            PassResult best;
-            std::vector<int> prompt;
-            for (size_t ti = 0; ti < sub->temperatures.size(); ++ti) {
-                const float t_cur = sub->temperatures[ti];
-                build_prompt(*sub, hp, vc, it, t_cur, prompt);
-                if (t_cur <= 0.0f) {
-                    if ((rc = beam_pass(st, p, sub->no_timestamps, it, prompt, nb, xslot, best))) return rc == OH_ERR_CUDA ? rc : OH_ERR_DECODE;
-                } else {
-                    // A.5: BEAM at t > 0 runs best_of decoders with sampling; best_of defaults to -1 for this strategy -> one decoder
-                    std::vector<PassRow> rows = {PassRow{sub, i, xslot, prompt}};
-                    std::vector<PassResult> res;
-                    if ((rc = decode_pass(st, p, sub->no_timestamps, rows, t_cur, res))) return rc == OH_ERR_CUDA ? rc : OH_ERR_DECODE;
-                    best = res[0];
-                    if (!best.failed) {
-                        best.tokens.resize(std::min<size_t>(best.tokens.size(), (size_t)best.result_len));
-                        sequence_score(p, best);
-                        if (best.result_len > 32 && best.entropy < p.entropy_thold) best.failed = true;
-                    }
-                }
-                if (ti + 1 != sub->temperatures.size() && (best.failed || best.avg_logprobs < p.logprob_thold)) {
-                    st->timings.n_fallbacks++;
-                    continue;
-                }
-                break;
-            }
-            emit_segments(m, p, it, best, prompt, (int)sub->prompt_init.size());
-            if (it.seek + 100 >= it.seek_end) it.done = true;
-            st->timings.decode_ms += ms_since(t1);
-        }
-    }
-    sub->n_done = (int)sub->items.size();
-    // the beam passes used the row-state block: the greedy scheduler starts from a clean slate
-    SeqLayout lay(st->max_batch);
-    memset(st->pinned, 0, lay.total_words * 4);
-    OH_CUDA_CHECK(cudaMemcpyAsync(st->seq_dev.p, st->pinned, lay.total_words * 4, cudaMemcpyHostToDevice, s));
-    OH_CUDA_CHECK(cudaStreamSynchronize(s));
-    sc.mirror_dirty = false;
-    sc.rules_valid = false;
-    return OH_OK;
-}
-
 int sched_pending(const oh_state* st) { return (int)st->sched.subs.size(); }
 
 int sched_submit(oh_state* st, const oh_full_params& p, const float* const* pcm, const int* n, int batch, bool pcm_on_device, bool persistent_rngs,
@@ -1051,7 +1080,11 @@ int sched_submit(oh_state* st, const oh_full_params& p, const float* const* pcm,
     const std::string lang = (p.language && strcmp(p.language, "auto") != 0 && p.language[0]) ? p.language : "en";
     // one decode policy at a time on the device (the rules block is per step): a submission with different params waits
     // for the live ones to finish
-    bool drain = p.strategy == OH_SAMPLING_BEAM_SEARCH;
+    if (p.strategy == OH_SAMPLING_BEAM_SEARCH && (p.beam_size < 1 || p.beam_size > kTopK || p.beam_size > st->max_batch)) {
+        set_error("beam search needs 1 <= beam_size <= " + std::to_string(kTopK) + " and oh_context_params.max_batch >= beam_size (one decoder row per beam)");
+        return OH_ERR_INVALID;
+    }
+    bool drain = false;
     for (auto& s : sc.subs)
         if (!s->finished() && !same_policy(s->p, p, s->language, lang)) drain = true;
     if (drain) {
@@ -1134,11 +1167,10 @@ int sched_submit(oh_state* st, const oh_full_params& p, const float* const* pcm,
         if (!it.done && it.seek_end < 100) it.done = true;  // < 1 s: no segments, rc 0 (A.3 step 7)
         if (!it.done && it.seek + 100 >= it.seek_end) it.done = true;
         if (it.done) sp->n_done++;
-        else if (p.strategy == OH_SAMPLING_GREEDY) sc.need_window.push_back(WinRef{sp, i, -1});
+        else sc.need_window.push_back(WinRef{sp, i, -1});
     }
     sc.subs.push_back(std::move(sub));
     if (ticket) *ticket = sp->ticket;
-    if (p.strategy == OH_SAMPLING_BEAM_SEARCH && (rc = run_beam_submission(st, sp))) return rc;
     return OH_OK;
 }
 
@@ -1200,6 +1232,8 @@ void sched_abort(oh_state* st) {
     sc.subs.clear();
     sc.rows.assign(st->max_batch, RowInfo());
     sc.n_armed = 0;
+    sc.beam_groups.clear();
+    sc.beam_kv_copies.clear();
     sc.free_slots.clear();
     for (int i = st->n_slots - 1; i >= 0; --i) sc.free_slots.push_back(i);
     SeqLayout lay(st->max_batch);

@@ -136,10 +136,26 @@ int launch_self_attention_decode(const void* qkv, void* kcache, void* vcache, in
 // q: [rows][d]; cross cache of a slot: [T][2d] (k | v per encoder position); out [rows][d]
 int launch_cross_attention_decode(const void* q, const void* xkv, int type, const DecodeSeqState& s, int rows, int d, int T, void* out,
                                   cudaStream_t st);
+// K9 in beam mode: instead of picking, a row reports its kTopK best ids of the filtered distribution (best first; ties: lower
+// id) with logprob and prob, and the timestamp statistics recorded with every token (A.7): tid, pt, ptsum.
+constexpr int kTopK = 8;  // beam_size <= kTopK
+struct TopKOut {
+    int* ids = nullptr;      // [rows][kTopK]; nullptr: not in top-k mode
+    float* logprobs = nullptr;
+    float* probs = nullptr;
+    int* tid = nullptr;      // [rows]
+    float* pt = nullptr;
+    float* ptsum = nullptr;
+};
 // K9: logit filters + log-softmax + timestamp-mass rule + greedy pick + A.5 state update, one CTA per row.
 // With dump_probs != nullptr the row's logprobs/probs are written ([rows][ld]) and nothing is sampled (t > 0 path).
 // `r` points to DEVICE memory so that a captured graph of the step survives a change of rules (temperature ladder).
+// With topk.ids != nullptr the row's top-k candidates are written and nothing is sampled (beam search; the host ranks).
 int launch_logits_step(const float* logits, int ld, const DecodeSeqState& s, const DecodeRules* r, int rows, float* dump_logprobs,
-                       float* dump_probs, cudaStream_t st);
+                       float* dump_probs, cudaStream_t st, const TopKOut& topk = TopKOut());
+// self-attention cache lines of beam search: copy positions [0, n_pos) of line src -> dst for every pair, all layers, K and V,
+// in one launch.  pairs: device array of n_pairs (src, dst, n_pos, -) int4; caches are [layer][lines][heads][n_ctx][64].
+int launch_copy_self_lines(void* kcache, void* vcache, int esz, const int4* pairs, int n_pairs, int n_layers, int lines, int heads, int n_ctx,
+                           cudaStream_t st);
 
 }  // namespace oh

@@ -96,3 +96,49 @@ def test_stream_policy_change_drains(micro_path):
     assert st.stream_wait(t0) == 0 and [st.segments(i) for i in range(2)] == rp
     st.close()
     ctx.close()
+
+
+def test_batched_beam_search_groups_match_oracle(micro_path, micro_oracle):
+    """BASELINE config 4's decode policy, batched: 16 rows = 3 groups of 5 beams, so three windows decode side by side, each
+    group's beams sharing one cross-attention K/V slot; token ids and segment times must equal the oracle's beam search
+    (which runs one window at a time) for every clip, through the blocking call and through two live stream tickets."""
+    import os
+
+    from oracle import oracle as O
+    ctx = lib.Context(micro_path, compute_type=COMPUTE_F32, max_batch=16)
+    st = lib.State(ctx)
+    p = default_full_params(1)
+    p.temperature_inc = 0.0
+    clips = [synth.audio(1), synth.audio(3, 123456), synth.audio(7, 300000), synth.audio(8), synth.audio(9, 40000), synth.audio(2)]
+    ref = []
+    for c in clips:
+        of = O.OracleState(micro_oracle, gelu=O.GELU_TANH, act_round=O.ACT_NONE)
+        assert of.full(c, p) == 0
+        ref.append(flat(of.segments()))
+        of.close()
+    assert st.full_batch(clips, p) == 0
+    assert [flat(st.segments(i)) for i in range(len(clips))] == ref
+    ta = st.stream_submit_clips(clips[:4], p)
+    tb = st.stream_submit_clips(clips[4:], p)
+    assert st.stream_wait(ta) == 0
+    assert [flat(st.segments(i)) for i in range(4)] == ref[:4]
+    assert st.stream_wait(tb) == 0
+    assert [flat(st.segments(i)) for i in range(2)] == ref[4:]
+    # reference defaults (temperature ladder on): fresh states on both sides so the t > 0 draws see the same generator
+    q = default_full_params(1)
+    for c in clips[:2]:
+        sf, of = lib.State(ctx), O.OracleState(micro_oracle, gelu=O.GELU_TANH, act_round=O.ACT_NONE)
+        assert sf.full(c, q) == 0 and of.full(c, q) == 0
+        assert flat(sf.segments(0)) == flat(of.segments())
+        assert sf.timings().n_fallbacks == of.stats()["n_fallbacks"]
+        sf.close()
+        of.close()
+    # greedy after beam on the same state: the row-state block is clean again
+    g = default_full_params()
+    g.temperature_inc = 0.0
+    of = O.OracleState(micro_oracle, gelu=O.GELU_TANH, act_round=O.ACT_NONE)
+    assert st.full(clips[0], g) == 0 and of.full(clips[0], g) == 0
+    assert flat(st.segments(0)) == flat(of.segments())
+    of.close()
+    st.close()
+    ctx.close()
