@@ -162,7 +162,7 @@ def ncu_traffic(kernel_substr: str):
 
 def set_knobs():
     """Every OH_* environment knob that is set (they select kernels / scheduler variants; the defaults are the product)."""
-    knobs = {k: v for k, v in os.environ.items() if k.startswith("OH_") and k not in ("OH_MODEL_CACHE", "OH_REF_BUDGET_S")}
+    knobs = {k: v for k, v in os.environ.items() if k.startswith("OH_") and k not in ("OH_MODEL_CACHE", "OH_REF_BUDGET_S", "OH_SCHED_TRACE")}
     if "OH_SKIP_CATS" in knobs:
         raise SystemExit("bench.py: OH_SKIP_CATS is set — that switch skips kernels (diagnostic builds only); refusing to report a number")
     return knobs

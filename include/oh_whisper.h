@@ -63,7 +63,8 @@ typedef struct oh_context_params {
 } oh_context_params;
 
 /* BEAM_SEARCH (never selected by the reference, whisper.rs:243): beam_size decoders per window; needs
- * oh_context_params.max_batch >= beam_size (one KV-cache slot per beam); items of a batched call run one after the other */
+ * oh_context_params.max_batch >= beam_size and beam_size <= 8.  The resident rows form max_batch / beam_size groups: that
+ * many windows decode side by side, the beams of a window sharing its cross-attention K/V */
 enum oh_sampling_strategy { OH_SAMPLING_GREEDY = 0, OH_SAMPLING_BEAM_SEARCH = 1 };
 
 /* replaces whisper_full_params / FullParams (src/engine/whisper.rs:243-263); defaults in

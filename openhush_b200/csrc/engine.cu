@@ -149,6 +149,10 @@ int state_alloc(oh_state* st) {
     st->n_slots = st->max_batch + lookahead;
     if (const char* s = getenv("OH_ASYNC_ENC")) st->async_encoder = atoi(s) != 0;
     if (const char* s = getenv("OH_CHECK")) st->check_steps = std::max(1, atoi(s));
+    if (const char* s = getenv("OH_SCHED_TRACE")) {
+        st->trace = fopen(s, "a");
+        if (st->trace) fprintf(st->trace, "step,armed,ready,need_window,passes,free_slots,tickets\n");
+    }
     st->starve_rows = std::max(1, std::min(8, st->max_batch / 16));
     if (const char* s = getenv("OH_STARVE")) st->starve_rows = std::max(1, atoi(s));
     if (const char* s = getenv("OH_GEMM")) st->gemm_mode = strcmp(s, "simt") == 0 ? 1 : 0;
@@ -229,6 +233,8 @@ int state_alloc(oh_state* st) {
 
 void state_release(oh_state* st) {
     sched_release(st);
+    if (st->trace) fclose(st->trace);
+    st->trace = nullptr;
     for (auto& kv : st->step_graphs) cudaGraphExecDestroy(kv.second);
     st->step_graphs.clear();
     DevBuf* all[] = {&st->pcm_stage, &st->mel_raw, &st->clip_meta, &st->xin, &st->x1, &st->x, &st->h, &st->qkv, &st->hid, &st->enc_f32,

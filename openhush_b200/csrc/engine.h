@@ -193,6 +193,8 @@ struct oh_state {
     bool profiling = false;
 
     oh::Sched sched;
+    FILE* trace = nullptr;           // OH_SCHED_TRACE=<file>: scheduler occupancy log (diagnostics)
+    long long trace_steps = 0;
 
     // --- results of the last waited submission
     std::vector<oh::Item> items;

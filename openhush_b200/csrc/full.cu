@@ -568,6 +568,11 @@ struct Pump {
             st->timings.h2d_bytes += (long long)upload_words * 4;
             sc.mirror_dirty = false;
         }
+        if (st->trace) {  // OH_SCHED_TRACE=<file>: one line per look-in (decode step count, rows armed, stock, queue, passes, tickets)
+            fprintf(st->trace, "%lld,%d,%zu,%zu,%zu,%zu,%zu\n", st->trace_steps, sc.n_armed, sc.ready.size(), sc.need_window.size(), sc.passes.size(),
+                    sc.free_slots.size(), sc.subs.size());
+            st->trace_steps += st->check_steps;
+        }
         g_active_rows_hint = sc.n_armed;
         for (int step = 0; step < st->check_steps; ++step) {
             rc = run_decode_step_graph(st, R);
