@@ -511,6 +511,8 @@ def main():
                                             "PCM resident in HBM, one blocking call per rank, max over ranks")
         if "latency_b1" in extras:
             line["latency_b1"] = extras["latency_b1"]
+        line["model_load"] = dict(ms=ctx.load_ms, file_bytes=os.path.getsize(path),
+                                  what="oh_init_from_file: parse + upload of the ggml file (page cache warm), SURVEY.md section 8f N4")
         if not args.no_cpu_baseline and world == 1:
             from oracle import oracle as O
             om = O.OracleModel(path)

@@ -198,6 +198,11 @@ OH_API int oh_token_beg(oh_context* ctx);
 OH_API int oh_token_not(oh_context* ctx);
 OH_API const char* oh_token_to_str(oh_context* ctx, int token);
 OH_API int oh_lang_id(const char* lang); /* whisper_lang_id(): -1 if unknown */
+/* model-file handling: how long oh_init_from_file spent parsing + uploading the file (the engine's
+ * load / idle-unload cycle, src/daemon.rs:2241-2283), and how many tensors of the file were block-quantised (ggml q4_0 / q4_1 /
+ * q5_0 / q5_1 / q8_0, expanded to f16 at load) */
+OH_API float oh_model_load_ms(oh_context* ctx);
+OH_API int oh_model_n_quantised(oh_context* ctx);
 
 /* ---- stage entry points (whisper_pcm_to_mel / whisper_encode / whisper_decode / whisper_get_logits
  * in whisper.h; the reference never calls them, the parity tests and bench.py do) ---------------- */

@@ -358,6 +358,8 @@ OH_API const char* oh_token_to_str(oh_context* c, int token) {
     return (token >= 0 && token < v.n_vocab) ? v.id_to_token[token].c_str() : nullptr;
 }
 OH_API int oh_lang_id(const char* lang) { return lang_id_from_code(lang); }
+OH_API float oh_model_load_ms(oh_context* c) { return c && c->model ? c->model->load_ms : 0.0f; }
+OH_API int oh_model_n_quantised(oh_context* c) { return c && c->model ? c->model->n_quantised_tensors : 0; }
 
 // ---- stage entry points
 OH_API int oh_pcm_to_mel_batch(oh_context* ctx, oh_state* st, const float* const* samples, const int* n_samples, int batch, float* const* out_mel,

@@ -1,4 +1,5 @@
 // Model loader: legacy-ggml file -> device tensors (see model.h for the reference citations).
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <memory>
@@ -20,7 +21,7 @@ static const char* k_lang_codes[100] = {
 struct HostTensor {
     int n_dims = 0;
     int64_t ne[4] = {1, 1, 1, 1};
-    int ttype = 0;
+    int ttype = 0;  // after load_model's read loop: 0 f32 or 1 f16 (quantised blocks are expanded while reading)
     std::vector<uint8_t> data;
     int64_t nelem() const { return ne[0] * ne[1] * ne[2] * ne[3]; }
     float at(int64_t i) const {
@@ -28,6 +29,86 @@ struct HostTensor {
         return __half2float(((const __half*)data.data())[i]);
     }
 };
+
+// ---- ggml block-quantised tensor types -------------------------------------------------------
+// The reference downloads only f16 files (whisper.rs:71-79), but users drop quantised ggml-*.bin files into the model
+// directory; whisper.cpp's quantize tool writes them in this same container with per-tensor types below.  Blocks of 32
+// consecutive elements along the contiguous (K) dimension.  They are expanded to f16 at load (x = q * d [+ m] evaluated
+// in f32, rounded once): the tensor-core path multiplies f16 operands, like ggml's own CUDA backend does for these
+// types; ggml's CPU kernels instead quantise the activations to 8 bits per block, which this library does not imitate.
+enum { GGML_F32 = 0, GGML_F16 = 1, GGML_Q4_0 = 2, GGML_Q4_1 = 3, GGML_Q5_0 = 6, GGML_Q5_1 = 7, GGML_Q8_0 = 8 };
+constexpr int kQK = 32;
+size_t ggml_block_bytes(int t) {
+    switch (t) {
+        case GGML_Q4_0: return 2 + 16;
+        case GGML_Q4_1: return 2 + 2 + 16;
+        case GGML_Q5_0: return 2 + 4 + 16;
+        case GGML_Q5_1: return 2 + 2 + 4 + 16;
+        case GGML_Q8_0: return 2 + 32;
+        default: return 0;
+    }
+}
+inline float f16_bits_to_f32(const uint8_t* p) {
+    __half h;
+    std::memcpy(&h, p, 2);
+    return __half2float(h);
+}
+// one block -> 32 f16 values
+void dequant_block(int t, const uint8_t* b, __half* out) {
+    float v[kQK];
+    switch (t) {
+        case GGML_Q4_0: {
+            const float d = f16_bits_to_f32(b);
+            const uint8_t* qs = b + 2;
+            for (int j = 0; j < 16; ++j) {
+                v[j] = (float)((qs[j] & 0x0F) - 8) * d;
+                v[j + 16] = (float)((qs[j] >> 4) - 8) * d;
+            }
+            break;
+        }
+        case GGML_Q4_1: {
+            const float d = f16_bits_to_f32(b), m = f16_bits_to_f32(b + 2);
+            const uint8_t* qs = b + 4;
+            for (int j = 0; j < 16; ++j) {
+                v[j] = (float)(qs[j] & 0x0F) * d + m;
+                v[j + 16] = (float)(qs[j] >> 4) * d + m;
+            }
+            break;
+        }
+        case GGML_Q5_0: {
+            const float d = f16_bits_to_f32(b);
+            uint32_t qh;
+            std::memcpy(&qh, b + 2, 4);
+            const uint8_t* qs = b + 6;
+            for (int j = 0; j < 16; ++j) {
+                const uint8_t xh0 = ((qh >> j) << 4) & 0x10, xh1 = (qh >> (j + 12)) & 0x10;
+                v[j] = (float)(((qs[j] & 0x0F) | xh0) - 16) * d;
+                v[j + 16] = (float)(((qs[j] >> 4) | xh1) - 16) * d;
+            }
+            break;
+        }
+        case GGML_Q5_1: {
+            const float d = f16_bits_to_f32(b), m = f16_bits_to_f32(b + 2);
+            uint32_t qh;
+            std::memcpy(&qh, b + 4, 4);
+            const uint8_t* qs = b + 8;
+            for (int j = 0; j < 16; ++j) {
+                const uint8_t xh0 = ((qh >> j) << 4) & 0x10, xh1 = (qh >> (j + 12)) & 0x10;
+                v[j] = (float)((qs[j] & 0x0F) | xh0) * d + m;
+                v[j + 16] = (float)((qs[j] >> 4) | xh1) * d + m;
+            }
+            break;
+        }
+        case GGML_Q8_0: {
+            const float d = f16_bits_to_f32(b);
+            const int8_t* qs = (const int8_t*)(b + 2);
+            for (int j = 0; j < kQK; ++j) v[j] = (float)qs[j] * d;
+            break;
+        }
+        default: return;
+    }
+    for (int j = 0; j < kQK; ++j) out[j] = __float2half_rn(v[j]);
+}
 
 struct Loader {
     Model* m;
@@ -176,6 +257,7 @@ Model* load_model(const char* path, int device, int compute_type) {
 }
 
 static Model* load_model_impl(const char* path, int device, int compute_type) {
+    const auto t_load0 = std::chrono::steady_clock::now();
     FILE* f = fopen(path, "rb");
     if (!f) {
         set_error(std::string("cannot open model file ") + path);
@@ -216,7 +298,8 @@ static Model* load_model_impl(const char* path, int device, int compute_type) {
         hp.n_text_state / hp.n_text_head != kHeadDim || hp.n_audio_ctx != 1500 || hp.n_text_ctx != 448 ||
         hp.n_vocab < 51864 || hp.n_vocab > 51866 || (hp.n_mels != 80 && hp.n_mels != 128) || hp.n_audio_state != hp.n_text_state)
         return fail("unsupported hparams");
-    if (hp.ftype != 0 && hp.ftype != 1) return fail("quantised ftypes are not supported");
+    // ftype is informational (whisper.cpp: 0 f32, 1 f16, 2 q4_0, 3 q4_1, 7 q8_0, 8 q5_0, 9 q5_1, possibly + 1000 x version);
+    // what decides is every tensor's own type below
 
     int32_t fm = 0, ff = 0;
     if (!rd(f, fm) || !rd(f, ff) || fm != hp.n_mels || ff != kNBins) return fail("bad mel filter dims");
@@ -270,8 +353,9 @@ static Model* load_model_impl(const char* path, int device, int compute_type) {
         int32_t n_dims = 0, name_len = 0, ttype = 0;
         if (!rd(f, n_dims)) break;  // EOF
         if (!rd(f, name_len) || !rd(f, ttype)) return fail("truncated tensor header");
-        if (n_dims < 1 || n_dims > 4 || name_len <= 0 || name_len > 255 || (ttype != 0 && ttype != 1))
-            return fail("bad tensor header (quantised tensors are not supported)");
+        const size_t qblock = ggml_block_bytes(ttype);
+        if (n_dims < 1 || n_dims > 4 || name_len <= 0 || name_len > 255 || (ttype != GGML_F32 && ttype != GGML_F16 && qblock == 0))
+            return fail("bad tensor header (unsupported ggml tensor type " + std::to_string(ttype) + ")");
         HostTensor t;
         t.n_dims = n_dims;
         t.ttype = ttype;
@@ -289,10 +373,28 @@ static Model* load_model_impl(const char* path, int device, int compute_type) {
                 if (t.ne[i] > (1LL << 40) / ne_total) return fail("tensor dims overflow for " + name);
                 ne_total *= t.ne[i];
             }
-            if (here < 0 || ne_total * (ttype ? 2 : 4) > file_size - here) return fail("tensor " + name + " is larger than the rest of the file");
+            if (qblock && (t.ne[0] % kQK)) return fail("quantised tensor " + name + ": row length is not a multiple of 32");
+            const long long payload = qblock ? ne_total / kQK * (long long)qblock : ne_total * (ttype ? 2 : 4);
+            if (here < 0 || payload > file_size - here) return fail("tensor " + name + " is larger than the rest of the file");
         }
-        t.data.resize((size_t)t.nelem() * (ttype ? 2 : 4));
-        if (fread(t.data.data(), 1, t.data.size(), f) != t.data.size()) return fail("truncated tensor data for " + name);
+        if (qblock) {  // expand to f16 while reading, a few MB at a time
+            const int64_t n_blocks = t.nelem() / kQK;
+            t.data.resize((size_t)t.nelem() * 2);
+            __half* out = (__half*)t.data.data();
+            std::vector<uint8_t> raw;
+            const int64_t chunk = 1 << 16;
+            for (int64_t b0 = 0; b0 < n_blocks; b0 += chunk) {
+                const int64_t nb = std::min(chunk, n_blocks - b0);
+                raw.resize((size_t)nb * qblock);
+                if (fread(raw.data(), 1, raw.size(), f) != raw.size()) return fail("truncated tensor data for " + name);
+                for (int64_t b = 0; b < nb; ++b) dequant_block(ttype, raw.data() + (size_t)b * qblock, out + (size_t)(b0 + b) * kQK);
+            }
+            t.ttype = GGML_F16;
+            m->n_quantised_tensors++;
+        } else {
+            t.data.resize((size_t)t.nelem() * (ttype ? 2 : 4));
+            if (fread(t.data.data(), 1, t.data.size(), f) != t.data.size()) return fail("truncated tensor data for " + name);
+        }
         L.T[name] = std::move(t);
     }
     fclose(f);
@@ -387,6 +489,7 @@ static Model* load_model_impl(const char* path, int device, int compute_type) {
     }
     if (!L.err.empty()) return fail(L.err);
     if (cudaDeviceSynchronize() != cudaSuccess) return fail("device error while loading");
+    m->load_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_load0).count();
     return m.release();
 }
 

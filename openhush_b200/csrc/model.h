@@ -71,6 +71,8 @@ struct Model {
     LayerNormW ln;
     uint16_t* gelu_lut = nullptr;  // [65536] f16 -> f16
     size_t bytes_on_device = 0;
+    int n_quantised_tensors = 0;   // tensors stored block-quantised in the file (expanded to f16 at load)
+    float load_ms = 0.0f;          // file parse + upload time of load_model
     std::vector<void*> allocs;
     ~Model();
 };

@@ -67,6 +67,8 @@ SYMBOLS = {
     "oh_token_not": (C.c_int, [_vp]),
     "oh_token_to_str": (C.c_char_p, [_vp, C.c_int]),
     "oh_lang_id": (C.c_int, [C.c_char_p]),
+    "oh_model_load_ms": (C.c_float, [_vp]),
+    "oh_model_n_quantised": (C.c_int, [_vp]),
     "oh_pcm_to_mel_batch": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp, _vp]),
     "oh_pcm_to_mel_device": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp]),
     "oh_encode_batch": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp]),
@@ -131,6 +133,7 @@ class Context:
         self.n_text_ctx, self.n_text_state, self.n_text_layer = L.oh_n_text_ctx(h), L.oh_n_text_state(h), L.oh_n_text_layer(h)
         self.eot, self.sot, self.beg, self.not_ = L.oh_token_eot(h), L.oh_token_sot(h), L.oh_token_beg(h), L.oh_token_not(h)
         self.max_batch = max_batch
+        self.load_ms, self.n_quantised = L.oh_model_load_ms(h), L.oh_model_n_quantised(h)
 
     def token_to_str(self, i: int) -> bytes:
         return self.lib.oh_token_to_str(self.h, i)

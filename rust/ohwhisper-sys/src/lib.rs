@@ -152,6 +152,8 @@ extern "C" {
     pub fn oh_token_not(ctx: *mut oh_context) -> c_int;
     pub fn oh_token_to_str(ctx: *mut oh_context, token: c_int) -> *const c_char;
     pub fn oh_lang_id(lang: *const c_char) -> c_int;
+    pub fn oh_model_load_ms(ctx: *mut oh_context) -> c_float;
+    pub fn oh_model_n_quantised(ctx: *mut oh_context) -> c_int;
     // ---- stage entry points
     pub fn oh_pcm_to_mel_batch(ctx: *mut oh_context, state: *mut oh_state, samples: *const *const f32, n_samples: *const c_int, batch: c_int,
                                out_mel: *const *mut f32, out_n_len: *mut c_int) -> c_int;

@@ -104,3 +104,37 @@ def test_worker_pool_on_gpus_batches_jobs(micro_path):
         assert all(n > 0 for n in pool.jobs_done) or max(pool.jobs_done) == 11
     for e in engines:
         e.close()
+
+
+@pytest.mark.parametrize("kind", ["q8_0", "q5_0", "q5_1", "q4_0", "q4_1"])
+def test_quantised_ggml_files_load_and_match_their_f16_expansion(micro_path, tmp_path, kind):
+    """model files whose 2-D weights are ggml block-quantised (what whisper.cpp's quantize tool
+    writes) load, and give exactly the results of the same file with those blocks expanded to f16 beforehand — i.e. the
+    loader's dequantisation is the published x = q * d (+ m) per block of 32; also the load-time getter."""
+    from _ggml_quant import requantise
+    from openhush_b200 import lib
+    qpath, fpath = str(tmp_path / f"ggml-micro-{kind}.bin"), str(tmp_path / "ggml-micro-expanded.bin")
+    n_q = requantise(micro_path, qpath, fpath, kind)
+    assert n_q > 10
+    p = default_full_params()
+    p.temperature_inc = 0.0
+    clip = synth.audio(31, 250000)
+    out = []
+    for path in (qpath, fpath):
+        ctx = lib.Context(path, compute_type=COMPUTE_F32, max_batch=1)
+        st = lib.State(ctx)
+        assert ctx.load_ms > 0.0 and ctx.n_quantised == (n_q if path == qpath else 0)
+        assert st.full(clip, p) == 0
+        out.append(st.segments(0))
+        lg = st.decode(np.array([[ctx.sot, ctx.sot + 1, 50359, 1000]], np.int32), 0)[0]
+        out.append(lg)
+        st.close()
+        ctx.close()
+    assert out[0] == out[2] and len(out[0]) > 0
+    assert np.array_equal(out[1], out[3])
+    # a truncated quantised file is rejected with a load error, not a crash
+    blob = open(qpath, "rb").read()
+    bad = str(tmp_path / "ggml-micro-truncated.bin")
+    open(bad, "wb").write(blob[:len(blob) - 1000])
+    with pytest.raises(lib.OhError):
+        lib.Context(bad, compute_type=COMPUTE_F32, max_batch=1)
