@@ -129,6 +129,8 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 #endif
 extern thread_local int g_sm_limit;  // > 0: persistent kernels launched by this thread size their grid for this many SMs (encoder on an SM partition)
+extern thread_local int g_gemm_compact;        // > 0: tcgen05 mat-muls launched by this thread use 128-wide tiles and a ring of at most
+extern thread_local int g_gemm_compact_bytes;  //      g_gemm_compact_bytes, leaving shared memory / TMEM to co-resident decode kernels
 extern thread_local int g_pdl;  // > 0 while the calling thread is inside a decode step (set by decode_step_launch)
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {

@@ -593,7 +593,7 @@ __device__ __forceinline__ void xa_unpack8<__nv_bfloat16>(const uint4& u, float 
 
 template <typename T>
 __global__ void __launch_bounds__(XA_THREADS) cross_attention_decode_bulk_kernel(const T* __restrict__ q, const T* __restrict__ xkv, DecodeSeqState s,
-                                                                                int d, int Tn, T* __restrict__ out) {
+                                                                                int d, int Tn, T* __restrict__ out, int n_stages) {
     // Programmatic dependent launch: the only input written by the preceding kernel (the q projection) is q.  The
     // row state was last written by the previous step's K9 and the cross K/V by the encoder, both complete before the
     // predecessor passed its own pdl_wait, so the producer warp starts streaming K/V at once and only the consumers
@@ -607,7 +607,7 @@ __global__ void __launch_bounds__(XA_THREADS) cross_attention_decode_bulk_kernel
     // layout: [stage][K 64x64 | V 64x64] (16 KB per stage), then merge scratch, then the barriers
     constexpr int STAGE_BYTES = 2 * XA_KEYS * kHeadDim * 2;
     T* stage0 = reinterpret_cast<T*>(xa_smem);
-    float* sm_o = reinterpret_cast<float*>(xa_smem + XA_STAGES * STAGE_BYTES);  // [32][64]
+    float* sm_o = reinterpret_cast<float*>(xa_smem + n_stages * STAGE_BYTES);  // [32][64]
     float* sm_m = sm_o + 32 * kHeadDim;                                           // [32]
     float* sm_l = sm_m + 32;                                                      // [32]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm_l + 32);                      // full[STAGES], empty[STAGES]
@@ -623,7 +623,7 @@ __global__ void __launch_bounds__(XA_THREADS) cross_attention_decode_bulk_kernel
     const int n_it = (Tn + XA_KEYS - 1) / XA_KEYS;
 
     if (tid == 0) {
-        for (int st = 0; st < XA_STAGES; ++st) {
+        for (int st = 0; st < n_stages; ++st) {
             xa_mbar_init(full_bar(st), 1);
             xa_mbar_init(empty_bar(st), XA_CONSUMERS / 32);
         }
@@ -644,7 +644,7 @@ __global__ void __launch_bounds__(XA_THREADS) cross_attention_decode_bulk_kernel
                 xa_mbar_expect_tx(full_bar(st), 2 * bytes);
                 xa_bulk_copy(dstK, Kg + (size_t)key0 * kHeadDim, bytes, full_bar(st));
                 xa_bulk_copy(dstV, Vg + (size_t)key0 * kHeadDim, bytes, full_bar(st));
-                if (++st == XA_STAGES) {
+                if (++st == n_stages) {
                     st = 0;
                     phase ^= 1;
                 }
@@ -713,7 +713,7 @@ __global__ void __launch_bounds__(XA_THREADS) cross_attention_decode_bulk_kernel
             }
             __syncwarp();
             if (lane == 0) xa_mbar_arrive(empty_bar(st));  // this warp is done with the stage
-            if (++st == XA_STAGES) {
+            if (++st == n_stages) {
                 st = 0;
                 phase ^= 1;
             }
@@ -738,7 +738,8 @@ __global__ void __launch_bounds__(XA_THREADS) cross_attention_decode_bulk_kernel
         out[(size_t)b * d + h * kHeadDim + tid] = Cvt<T>::from_f32(O / L);
     }
 }
-constexpr int XA_SMEM_BYTES = XA_STAGES * 2 * XA_KEYS * kHeadDim * 2 + 32 * kHeadDim * 4 + 64 * 4 + 2 * XA_STAGES * 8 + 64;
+constexpr int xa_smem_bytes(int stages) { return stages * 2 * XA_KEYS * kHeadDim * 2 + 32 * kHeadDim * 4 + 64 * 4 + 2 * XA_STAGES * 8 + 64; }
+constexpr int XA_SMEM_BYTES = xa_smem_bytes(XA_STAGES);
 
 // ------------------------------------------------------------------------------------------------ K9
 struct MaxIdx {
@@ -1075,9 +1076,14 @@ int launch_cross_attention_decode(const void* q, const void* xkv, int type, cons
     ProfScope ps(PC_CROSS_ATTN, (double)rows_work * T * 2.0 * d * (type == DT_F32 ? 4 : 2), st);
     // OH_XATTN_OCC=1: one CTA per SM (shared memory padded past half an SM) so that other kernels always find room next
     // to it; the 6-stage ring of a single CTA per SM still covers the HBM latency
+    // OH_XATTN_STAGES=n (2..6): depth of the K/V ring.  Fewer stages leave shared memory for a co-resident encoder CTA
+    static const int xa_stages = [] {
+        const char* o = getenv("OH_XATTN_STAGES");
+        return o ? std::max(2, std::min(XA_STAGES, atoi(o))) : XA_STAGES;
+    }();
     static const int xa_smem = [] {
         const char* o = getenv("OH_XATTN_OCC");
-        return (o && atoi(o) == 1) ? 116 * 1024 : XA_SMEM_BYTES;
+        return (o && atoi(o) == 1) ? 116 * 1024 : xa_smem_bytes(xa_stages);
     }();
     static const bool want_bulk = [] {
         const char* e = getenv("OH_XATTN");
@@ -1090,9 +1096,9 @@ int launch_cross_attention_decode(const void* q, const void* xkv, int type, cons
     });
     if (type == DT_F32) OH_CUDA_CHECK(launch_k(cross_attention_decode_kernel<float>, grid, 128, 0, st, (const float*)q, (const float*)xkv, s, d, T, (float*)out));
     else if (use_bulk && type == DT_F16)
-        OH_CUDA_CHECK(launch_k(cross_attention_decode_bulk_kernel<__half>, grid, XA_THREADS, xa_smem, st, (const __half*)q, (const __half*)xkv, s, d, T, (__half*)out));
+        OH_CUDA_CHECK(launch_k(cross_attention_decode_bulk_kernel<__half>, grid, XA_THREADS, xa_smem, st, (const __half*)q, (const __half*)xkv, s, d, T, (__half*)out, xa_stages));
     else if (use_bulk)
-        OH_CUDA_CHECK(launch_k(cross_attention_decode_bulk_kernel<__nv_bfloat16>, grid, XA_THREADS, xa_smem, st, (const __nv_bfloat16*)q, (const __nv_bfloat16*)xkv, s, d, T, (__nv_bfloat16*)out));
+        OH_CUDA_CHECK(launch_k(cross_attention_decode_bulk_kernel<__nv_bfloat16>, grid, XA_THREADS, xa_smem, st, (const __nv_bfloat16*)q, (const __nv_bfloat16*)xkv, s, d, T, (__nv_bfloat16*)out, xa_stages));
     else if (type == DT_F16)
         OH_CUDA_CHECK(launch_k(attention_decode_online_kernel<__half, false>, grid, 128, 0, st, (const __half*)q, d, (const __half*)xkv, (const __half*)xkv, nullptr, nullptr, s, d, T, (__half*)out));
     else

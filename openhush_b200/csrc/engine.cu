@@ -22,6 +22,8 @@ namespace oh {
 thread_local long long g_launch_count = 0;
 thread_local int g_pdl = 0;
 thread_local int g_sm_limit = 0;
+thread_local int g_gemm_compact = 0;
+thread_local int g_gemm_compact_bytes = 96 * 1024;
 thread_local Profiler* g_prof = nullptr;
 thread_local int g_active_rows_hint = -1;
 #ifdef OH_DIAG
@@ -149,6 +151,7 @@ int state_alloc(oh_state* st) {
     st->n_slots = st->max_batch + lookahead;
     if (const char* s = getenv("OH_ASYNC_ENC")) st->async_encoder = atoi(s) != 0;
     if (const char* s = getenv("OH_CHECK")) st->check_steps = std::max(1, atoi(s));
+    if (const char* s = getenv("OH_ENC_COMPACT")) st->enc_compact_bytes = atoi(s) > 0 ? std::max(64, atoi(s)) * 1024 : 0;  // KB of ring per encoder mat-mul CTA
     if (const char* s = getenv("OH_SCHED_TRACE")) {
         st->trace = fopen(s, "a");
         if (st->trace) fprintf(st->trace, "step,armed,ready,need_window,passes,free_slots,tickets\n");
@@ -413,6 +416,12 @@ int run_encoder(oh_state* st, int nw, int slot0, float* d_enc_f32_out, const int
         explicit SmLimit(int v) : saved(g_sm_limit) { g_sm_limit = v; }
         ~SmLimit() { g_sm_limit = saved; }
     } sm_limit((stream && stream == st->enc_stream && st->enc_sms > 0) ? st->enc_sms : 0);
+    struct Compact {  // OH_ENC_COMPACT: the pass shares the SMs with decode steps (see gemm_tc.cu)
+        int saved;
+        explicit Compact(int v) : saved(g_gemm_compact) { g_gemm_compact = v; }
+        ~Compact() { g_gemm_compact = saved; }
+    } compact((st->enc_compact_bytes > 0 && ((stream && stream == st->enc_stream) || getenv("OH_ENC_COMPACT_ALL"))) ? 1 : 0);
+    if (st->enc_compact_bytes > 0) g_gemm_compact_bytes = st->enc_compact_bytes;
     auto gemm = [&](oh_state* st_, GemmArgs g_) { return oh::gemm(st_, g_, s); };
     int rc;
     char* x1 = (char*)st->x1.p;

@@ -159,6 +159,7 @@ struct oh_state {
     int esz = 2;         // bytes per activation element
     bool async_encoder = true;  // OH_ASYNC_ENC=0: encoder passes are issued on the decode stream (serialised, round-1 behaviour)
     int check_steps = 8;        // decode steps between two host look-ins
+    int enc_compact_bytes = 0;  // OH_ENC_COMPACT=<KB>: encoder mat-muls on the encoder stream use 128-wide tiles and this much ring (co-residency experiment)
     int starve_rows = 8;        // empty rows at which the decode steps pause for the encoder pass in flight (OH_STARVE)
 
     // --- stage API mel (oh_pcm_to_mel_*): its own small submission-like block

@@ -52,6 +52,7 @@ struct TcParams {
     const uint16_t* lut;
     int c_hsplit;
     long long c_hstride;
+    int stages;
 };
 
 template <int BLOCK_N>
@@ -69,9 +70,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_a2,
                const __grid_constant__ CUtensorMap map_w, const TcParams p) {
     using Cfg = TcConfig<BLOCK_N>;
+    const int NS = p.stages;  // ring depth of this launch (<= Cfg::STAGES): a shallower ring leaves shared memory to co-resident kernels
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
-    const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+    const uint32_t bar_base = smem_base + NS * Cfg::STAGE_BYTES;
     // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then the TMEM base address
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
@@ -84,7 +86,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < Cfg::STAGES; ++s) {
+        for (int s = 0; s < NS; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
@@ -121,7 +123,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                     const CUtensorMap* ma = tap == 0 ? &map_a0 : (tap == 1 ? &map_a1 : &map_a2);
                     tma_load_3d(ma, sa, full_bar(stage), kc, i0, b);
                     tma_load_2d(&map_w, sb, full_bar(stage), tap * p.tap_k + kc, n_blk * BLOCK_N);
-                    if (++stage == Cfg::STAGES) {
+                    if (++stage == NS) {
                         stage = 0;
                         phase ^= 1;
                     }
@@ -149,7 +151,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                         tc_mma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     tc_commit(empty_bar(stage));  // frees the smem slot once these MMAs have read it
-                    if (++stage == Cfg::STAGES) {
+                    if (++stage == NS) {
                         stage = 0;
                         phase ^= 1;
                     }
@@ -389,11 +391,15 @@ int launch_t(const GemmArgs& g, cudaStream_t st) {
     p.bias = g.bias; p.C = g.C; p.c_type = g.c_type; p.c_bstride = g.c_bstride; p.ldc = g.ldc;
     p.R = g.R; p.r_bstride = g.r_bstride; p.ldr = g.ldr; p.gelu = g.gelu; p.round_type = g.round_type; p.lut = g.lut;
     p.c_hsplit = g.c_hsplit; p.c_hstride = g.c_hstride;
+    // compact mode (encoder passes that run next to decode steps): at most 3 stages / 96 KB of ring, so that a decode CTA
+    // (cross-attention: ~58 KB with a 3-deep ring, split-K mat-mul: 96 KB) fits on the same SM
+    p.stages = g_gemm_compact > 0 ? std::min(Cfg::STAGES, std::max(2, g_gemm_compact_bytes / Cfg::STAGE_BYTES)) : Cfg::STAGES;
+    const int smem_bytes = p.stages * Cfg::STAGE_BYTES + 1024 + 256;
     const int sm_cap = g_sm_limit > 0 ? std::min(g_sm_limit, g_num_sms[PerDeviceInit::current_device()]) : g_num_sms[PerDeviceInit::current_device()];
     const int grid = std::min(p.num_tiles, sm_cap);
     OH_SKIP_IF(g.N > 40000 ? PC_LOGITS : (g.batch * g.rows <= 512 ? PC_GEMM_DEC : PC_GEMM_ENC));  // timing experiments only
     ProfScope ps(g.batch * g.rows <= 512 ? PC_GEMM_DEC : PC_GEMM_ENC, 2.0 * g.batch * (double)g.rows * g.N * g.K, st);
-    OH_CUDA_CHECK(launch_k(gemm_tc_kernel<BLOCK_N>, grid, TC_THREADS, Cfg::SMEM_BYTES, st, ma[0], ma[1], ma[2], mw, p));
+    OH_CUDA_CHECK(launch_k(gemm_tc_kernel<BLOCK_N>, grid, TC_THREADS, smem_bytes, st, ma[0], ma[1], ma[2], mw, p));
     OH_COUNT_LAUNCH();
     OH_CUDA_CHECK(cudaGetLastError());
     return OH_OK;
@@ -434,6 +440,7 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
         return launch_t<16>(g, st);
     }
     if (g.N < 128) return launch_t<64>(g, st);
+    if (g_gemm_compact > 0) return launch_t<128>(g, st);  // 128-wide tiles: 32 KB stages, 256 TMEM columns
     if (g.N % 256 == 0 || g.N >= 2048) return launch_t<256>(g, st);
     return launch_t<128>(g, st);
 }
