@@ -204,6 +204,19 @@ OH_API int oh_lang_id(const char* lang); /* whisper_lang_id(): -1 if unknown */
 OH_API float oh_model_load_ms(oh_context* ctx);
 OH_API int oh_model_n_quantised(oh_context* ctx);
 
+/* ---- pre-engine DSP on the device: what load_wav_file does between the WAV reader and the engine
+ * (src/input/audio.rs:368-424) — samples to f32 (format 0: f32, 1: i16, 2: i32 carrying `bits`-bit integers, value / 2^(bits-1)),
+ * mono = mean of a frame's channels, sinc resampling to 16 kHz with the parameters of resample_sinc (audio.rs:1007-1095:
+ * 256 taps, cutoff 0.95, 256x oversampled, linear interpolation, Blackman-Harris^2, 1024-frame chunks, last chunk cut to
+ * ceil(len * ratio)), zero padding to 1.1 s.  `pcm`: n_frames interleaved frames.  oh_pcm_16k_len gives the output length.
+ * The host variant copies in and out; the device variant reads and writes device memory on the state's stream (its output
+ * feeds oh_full_batch_device / oh_stream_submit(on_device) without touching the host). */
+OH_API long long oh_pcm_16k_len(int sample_rate, long long n_frames);
+OH_API int oh_load_pcm_16k(oh_context* ctx, oh_state* state, const void* pcm, int format, int bits, int channels, int sample_rate,
+                           long long n_frames, float* out, long long cap, long long* out_n);
+OH_API int oh_load_pcm_16k_device(oh_context* ctx, oh_state* state, const void* d_pcm, int format, int bits, int channels, int sample_rate,
+                                  long long n_frames, float* d_out, long long cap, long long* out_n);
+
 /* ---- stage entry points (whisper_pcm_to_mel / whisper_encode / whisper_decode / whisper_get_logits
  * in whisper.h; the reference never calls them, the parity tests and bench.py do) ---------------- */
 

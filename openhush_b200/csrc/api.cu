@@ -361,6 +361,55 @@ OH_API int oh_lang_id(const char* lang) { return lang_id_from_code(lang); }
 OH_API float oh_model_load_ms(oh_context* c) { return c && c->model ? c->model->load_ms : 0.0f; }
 OH_API int oh_model_n_quantised(oh_context* c) { return c && c->model ? c->model->n_quantised_tensors : 0; }
 
+// ---- pre-engine DSP (resample.cu)
+OH_API long long oh_pcm_16k_len(int sample_rate, long long n_frames) { return resample_out_len(sample_rate, n_frames, true); }
+
+OH_API int oh_load_pcm_16k_device(oh_context* ctx, oh_state* st, const void* d_pcm, int format, int bits, int channels, int sample_rate,
+                                  long long n_frames, float* d_out, long long cap, long long* out_n) {
+    if (!ctx || !st || st->ctx != ctx) return OH_ERR_INVALID;
+    if (select_device(ctx)) return OH_ERR_CUDA;
+    set_error("");
+    try {
+        if (cap < resample_out_len(sample_rate, n_frames, true)) {
+            set_error("oh_load_pcm_16k: output buffer too small (see oh_pcm_16k_len)");
+            return OH_ERR_INVALID;
+        }
+        return resample_to_16k_device(st, d_pcm, format, bits, channels, sample_rate, n_frames, d_out, out_n, st->stream);
+    } catch (const std::exception& e) {
+        set_error(std::string("oh_load_pcm_16k: ") + e.what());
+        return OH_ERR_INVALID;
+    }
+}
+
+OH_API int oh_load_pcm_16k(oh_context* ctx, oh_state* st, const void* pcm, int format, int bits, int channels, int sample_rate, long long n_frames,
+                           float* out, long long cap, long long* out_n) {
+    if (!ctx || !st || st->ctx != ctx || !pcm || !out || n_frames <= 0 || channels < 1 || format < 0 || format > 2) return OH_ERR_INVALID;
+    if (select_device(ctx)) return OH_ERR_CUDA;
+    set_error("");
+    try {
+        const long long need = resample_out_len(sample_rate, n_frames, true);
+        if (cap < need) {
+            set_error("oh_load_pcm_16k: output buffer too small (see oh_pcm_16k_len)");
+            return OH_ERR_INVALID;
+        }
+        const size_t in_bytes = (size_t)n_frames * channels * (format == 1 ? 2 : 4);
+        int rc;
+        if ((rc = ensure(st->resample_in, in_bytes))) return rc;
+        if ((rc = ensure(st->resample_out, (size_t)need * 4))) return rc;
+        OH_CUDA_CHECK(cudaMemcpyAsync(st->resample_in.p, pcm, in_bytes, cudaMemcpyHostToDevice, st->stream));
+        long long n16 = 0;
+        if ((rc = resample_to_16k_device(st, st->resample_in.p, format, bits, channels, sample_rate, n_frames, (float*)st->resample_out.p, &n16, st->stream)))
+            return rc;
+        OH_CUDA_CHECK(cudaMemcpyAsync(out, st->resample_out.p, (size_t)n16 * 4, cudaMemcpyDeviceToHost, st->stream));
+        OH_CUDA_CHECK(cudaStreamSynchronize(st->stream));
+        if (out_n) *out_n = n16;
+        return OH_OK;
+    } catch (const std::exception& e) {
+        set_error(std::string("oh_load_pcm_16k: ") + e.what());
+        return OH_ERR_INVALID;
+    }
+}
+
 // ---- stage entry points
 OH_API int oh_pcm_to_mel_batch(oh_context* ctx, oh_state* st, const float* const* samples, const int* n_samples, int batch, float* const* out_mel,
                                int* out_n_len) {
@@ -466,7 +515,7 @@ OH_API float oh_gemm_selftest_error(void) { return g_selftest_err; }
 
 // ---- per-kernel timing
 static const char* k_cat_names[PC_COUNT] = {"mel_frames", "window_gather", "gemm_encoder", "gemm_decoder", "layernorm",
-                                            "attention_encoder", "self_attention_decode", "cross_attention_decode", "embed", "logits_step"};
+                                            "attention_encoder", "self_attention_decode", "cross_attention_decode", "embed", "logits_step", "resample_sinc"};
 OH_API int oh_profile(oh_state* st, int on) {
     if (!st) return OH_ERR_INVALID;
     if (on) {

@@ -41,7 +41,7 @@ extern thread_local long long g_launch_count;
 // Optional per-kernel timing (oh_profile): every launch wrapper opens a ProfScope, which brackets the launch with
 // two CUDA events on the launching stream when a profiler is attached to the calling thread (and costs one
 // thread-local load otherwise).  `work` is the launch's algorithmic work: FLOPs for mat-muls, bytes otherwise.
-enum ProfCat { PC_MEL = 0, PC_GATHER, PC_GEMM_ENC, PC_GEMM_DEC, PC_LN, PC_ATTN_ENC, PC_SELF_ATTN, PC_CROSS_ATTN, PC_EMBED, PC_LOGITS, PC_COUNT };
+enum ProfCat { PC_MEL = 0, PC_GATHER, PC_GEMM_ENC, PC_GEMM_DEC, PC_LN, PC_ATTN_ENC, PC_SELF_ATTN, PC_CROSS_ATTN, PC_EMBED, PC_LOGITS, PC_RESAMPLE, PC_COUNT };
 struct Profiler {
     struct Rec {
         int cat;

@@ -176,6 +176,7 @@ struct oh_state {
     // --- decoder activations (max_batch rows)
     oh::DevBuf dx, dh, dqkv, datt, dq, dhid, logits, dump_lp, dump_p, topk_dev;
     int ld_logits = 0;
+    oh::DevBuf resample_plan, resample_in, resample_out;  // pre-engine DSP (resample.cu): chunk plan, staging of the host entry point
     oh::DevBuf beam_pairs;         // beam search: (src line, dst line, positions) of the step's cache-line copies
     oh::DevBuf seq_dev;            // DecodeSeqState arrays
     oh::DevBuf rules_dev;
@@ -230,6 +231,11 @@ int sched_wait(oh_state* st, int ticket);
 int sched_pending(const oh_state* st);
 void sched_abort(oh_state* st);    // drop every live submission, reset rows and slots
 void sched_release(oh_state* st);
+
+// pre-engine DSP (resample.cu): interleaved PCM -> mono 16 kHz f32, the reference's load_wav_file steps on the device
+long long resample_out_len(int sample_rate, long long n_frames, bool pad_min_duration);
+int resample_to_16k_device(oh_state* st, const void* d_pcm, int format, int bits, int channels, int sample_rate, long long n_frames, float* d_out,
+                           long long* out_n, cudaStream_t stream);
 
 int ensure(DevBuf& b, size_t bytes);
 void release(DevBuf& b);

@@ -69,6 +69,9 @@ SYMBOLS = {
     "oh_lang_id": (C.c_int, [C.c_char_p]),
     "oh_model_load_ms": (C.c_float, [_vp]),
     "oh_model_n_quantised": (C.c_int, [_vp]),
+    "oh_pcm_16k_len": (C.c_longlong, [C.c_int, C.c_longlong]),
+    "oh_load_pcm_16k": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong, _vp, C.c_longlong, C.POINTER(C.c_longlong)]),
+    "oh_load_pcm_16k_device": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong, _vp, C.c_longlong, C.POINTER(C.c_longlong)]),
     "oh_pcm_to_mel_batch": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp, _vp]),
     "oh_pcm_to_mel_device": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp]),
     "oh_encode_batch": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp]),
@@ -233,6 +236,23 @@ class State:
 
     def set_stream(self, cuda_stream: int | None):
         return self.lib.oh_state_set_stream(self.h, C.c_void_p(cuda_stream or 0))
+
+    # ---- pre-engine DSP
+    def load_pcm_16k(self, frames: np.ndarray, sample_rate: int, bits: int = 0) -> np.ndarray:
+        """frames: [n_frames, channels] (or [n_frames]) f32 / int16 / int32 (then `bits` = the integer width, e.g. 24).
+        Returns the 16 kHz mono f32 clip the reference's load_wav_file would hand to the engine."""
+        a = np.ascontiguousarray(frames)
+        if a.ndim == 1:
+            a = a[:, None]
+        fmt = {np.dtype(np.float32): 0, np.dtype(np.int16): 1, np.dtype(np.int32): 2}[a.dtype]
+        n = self.lib.oh_pcm_16k_len(sample_rate, a.shape[0])
+        out = np.empty(max(int(n), 1), dtype=np.float32)
+        got = C.c_longlong(0)
+        rc = self.lib.oh_load_pcm_16k(self.ctx.h, self.h, a.ctypes.data, fmt, bits or (16 if fmt == 1 else 32), a.shape[1], sample_rate, a.shape[0],
+                                      out.ctypes.data, len(out), C.byref(got))
+        if rc != 0:
+            raise OhError(f"oh_load_pcm_16k rc={rc}: " + self.lib.oh_last_error().decode(errors="replace"))
+        return out[:got.value]
 
     # ---- stages
     def pcm_to_mel(self, clips):

@@ -71,12 +71,35 @@ def lib():
             "orc_full_window_n_tokens": (C.c_int, [vp, C.c_int]),
             "orc_full_window_token": (C.c_int, [vp, C.c_int, C.c_int]),
             "orc_model_round_weights_bf16": (None, [vp]),
+            "orc_resample_sinc_table": (None, [C.c_double, vp]),
+            "orc_mono_mix": (None, [vp, C.c_int, C.c_int, C.c_int, C.c_longlong, vp]),
+            "orc_resample_sinc": (C.c_longlong, [vp, C.c_longlong, C.c_int, C.c_int, vp, C.c_longlong]),
+            "orc_min_duration_padding": (C.c_longlong, [C.c_longlong]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
         _LIB = L
     return _LIB
+
+
+def load_pcm_16k(frames: np.ndarray, sample_rate: int, bits: int = 0, pad: bool = True) -> np.ndarray:
+    """The reference's load_wav_file steps after the WAV reader (src/input/audio.rs:368-424): to f32, mono mix, sinc
+    resampling to 16 kHz, 1.1 s padding.  frames: [n_frames, channels] f32 / int16 / int32 (`bits`-bit integers)."""
+    L = lib()
+    a = np.ascontiguousarray(frames)
+    if a.ndim == 1:
+        a = a[:, None]
+    fmt = {np.dtype(np.float32): 0, np.dtype(np.int16): 1, np.dtype(np.int32): 2}[a.dtype]
+    mono = np.empty(a.shape[0], dtype=np.float32)
+    L.orc_mono_mix(a.ctypes.data, fmt, bits or (16 if fmt == 1 else 32), a.shape[1], a.shape[0], mono.ctypes.data)
+    n = L.orc_resample_sinc(mono.ctypes.data, len(mono), sample_rate, 16000, None, 0)
+    out = np.empty(max(int(n), 1), dtype=np.float32)
+    L.orc_resample_sinc(mono.ctypes.data, len(mono), sample_rate, 16000, out.ctypes.data, len(out))
+    out = out[:n]
+    if pad:
+        out = np.concatenate([out, np.zeros(int(L.orc_min_duration_padding(len(out))), np.float32)])
+    return out
 
 
 class OracleModel:
