@@ -207,6 +207,8 @@ int state_alloc(oh_state* st) {
     st->win_desc_cap = 4 * chunk;  // ring: up to two passes in flight plus the one being filled
     if ((rc = ensure(st->win_desc, (size_t)st->win_desc_cap * sizeof(WindowDesc)))) return rc;
     OH_CUDA_CHECK(cudaMallocHost((void**)&st->win_desc_host, (size_t)st->win_desc_cap * sizeof(WindowDesc)));
+    if ((rc = ensure(st->slot_ring, (size_t)st->win_desc_cap * sizeof(int)))) return rc;
+    OH_CUDA_CHECK(cudaMallocHost((void**)&st->slot_ring_host, (size_t)st->win_desc_cap * sizeof(int)));
     const size_t R = st->max_batch, S = st->n_slots;
     if ((rc = ensure(st->xkv, (size_t)L * S * T * 2 * d * e))) return rc;
     if ((rc = ensure(st->kself, (size_t)L * R * hp.n_text_ctx * d * e))) return rc;
@@ -241,13 +243,15 @@ void state_release(oh_state* st) {
     for (auto& kv : st->step_graphs) cudaGraphExecDestroy(kv.second);
     st->step_graphs.clear();
     DevBuf* all[] = {&st->pcm_stage, &st->mel_raw, &st->clip_meta, &st->xin, &st->x1, &st->x, &st->h, &st->qkv, &st->hid, &st->enc_f32,
-                     &st->win_desc, &st->xkv, &st->kself, &st->vself, &st->dx, &st->dh, &st->dqkv, &st->datt, &st->dq, &st->dhid, &st->logits,
+                     &st->win_desc, &st->slot_ring, &st->xkv, &st->kself, &st->vself, &st->dx, &st->dh, &st->dqkv, &st->datt, &st->dq, &st->dhid, &st->logits,
                      &st->dump_lp, &st->dump_p, &st->topk_dev, &st->beam_pairs, &st->resample_plan, &st->resample_in, &st->resample_out, &st->seq_dev, &st->rules_dev};
     for (DevBuf* b : all) release(*b);
     if (st->pinned) cudaFreeHost(st->pinned);
     st->pinned = nullptr;
     if (st->win_desc_host) cudaFreeHost(st->win_desc_host);
     st->win_desc_host = nullptr;
+    if (st->slot_ring_host) cudaFreeHost(st->slot_ring_host);
+    st->slot_ring_host = nullptr;
     if (st->prof) {
         if (g_prof == st->prof) g_prof = nullptr;
         for (auto& r : st->prof->recs) {
@@ -507,29 +511,31 @@ int run_encoder(oh_state* st, int nw, int slot0, float* d_enc_f32_out, const int
     if (d_enc_f32_out) {
         if ((rc = launch_layernorm(x, M, d, m.ln_post.w, m.ln_post.b, d_enc_f32_out, DT_F32, s))) return rc;
     }
-    // cross-attention K/V of every decoder layer, straight into the slots' caches: [L][slots][T][2d]
-    // slot_list (optional): window w goes to slot slot_list[w]; runs of consecutive slots share one mat-mul
-    for (int w0 = 0; w0 < nw;) {
-        int w1 = w0 + 1;
-        if (slot_list)
-            while (w1 < nw && slot_list[w1] == slot_list[w1 - 1] + 1) ++w1;
-        else
-            w1 = nw;
-        const int first_slot = slot_list ? slot_list[w0] : slot0;
-        for (int l = 0; l < hp.n_text_layer; ++l) {
-            const DecLayer& D = m.dec[l];
-            GemmArgs g;  // one "batch" per window so that the slot index separates from the row index
-            g.A = (char*)st->h.p + (size_t)w0 * T * d * e; g.a_type = act; g.lda = d; g.batch = w1 - w0; g.rows = T; g.a_bstride = (long long)T * d;
-            g.W = D.xkv.w; g.N = 2 * d; g.K = d; g.bias = D.xkv.b;
-            g.C = (char*)st->xkv.p + ((size_t)l * st->n_slots + first_slot) * T * 2 * d * e;
-            g.c_type = act;
-            g.c_bstride = (long long)T * 2 * d;       // one slot: [2 (k,v)][heads][T][64]
-            g.c_hsplit = kHeadDim;                    // column n = (kv * heads + head) * 64 + c
-            g.c_hstride = (long long)T * kHeadDim;
-            g.ldc = kHeadDim;
-            if ((rc = gemm(st, g))) return rc;
-        }
-        w0 = w1;
+    // cross-attention K/V of every decoder layer, straight into the slots' caches: [L][slots][2][heads][T][64].
+    // slot_list (optional): window w goes to slot slot_list[w]; the mat-mul scatters its batches through a device copy of
+    // the list, so one launch per layer serves the pass however fragmented the free slots are
+    const int* d_slots = nullptr;
+    if (slot_list) {
+        const int area = st->slot_cursor++ % 4;
+        int* hs = st->slot_ring_host + (size_t)area * st->enc_chunk;
+        int* ds = (int*)st->slot_ring.p + (size_t)area * st->enc_chunk;
+        memcpy(hs, slot_list, (size_t)nw * sizeof(int));
+        OH_CUDA_CHECK(cudaMemcpyAsync(ds, hs, (size_t)nw * sizeof(int), cudaMemcpyHostToDevice, s));
+        d_slots = ds;
+    }
+    for (int l = 0; l < hp.n_text_layer; ++l) {
+        const DecLayer& D = m.dec[l];
+        GemmArgs g;  // one "batch" per window so that the slot index separates from the row index
+        g.A = st->h.p; g.a_type = act; g.lda = d; g.batch = nw; g.rows = T; g.a_bstride = (long long)T * d;
+        g.W = D.xkv.w; g.N = 2 * d; g.K = d; g.bias = D.xkv.b;
+        g.C = (char*)st->xkv.p + ((size_t)l * st->n_slots + (slot_list ? 0 : slot0)) * T * 2 * d * e;
+        g.c_type = act;
+        g.c_bstride = (long long)T * 2 * d;       // one slot: [2 (k,v)][heads][T][64]
+        g.c_bidx = d_slots;
+        g.c_hsplit = kHeadDim;                    // column n = (kv * heads + head) * 64 + c
+        g.c_hstride = (long long)T * kHeadDim;
+        g.ldc = kHeadDim;
+        if ((rc = gemm(st, g))) return rc;
     }
     return OH_OK;
 }

@@ -170,6 +170,9 @@ struct oh_state {
     oh::DevBuf win_desc;           // device WindowDesc ring
     oh::WindowDesc* win_desc_host = nullptr;  // pinned mirror of the ring
     int win_desc_cap = 0;
+    oh::DevBuf slot_ring;          // device copies of the passes' slot lists (same ring discipline)
+    int* slot_ring_host = nullptr;
+    int slot_cursor = 0;
     // --- caches
     oh::DevBuf xkv;                // [L][n_slots][2][heads][1500][64]
     oh::DevBuf kself, vself;       // [L][rows][heads][448][64]

@@ -421,7 +421,9 @@ struct Pump {
             const int avail = (int)std::min<size_t>(std::min(sc.need_window.size(), sc.free_slots.size()), (size_t)st->enc_chunk);
             const int fed = sc.n_armed + (int)sc.ready.size() + inflight_windows();
             const bool starving = fed < R;
-            if (avail < std::max(1, st->enc_chunk / 2) && !starving) break;
+            // full passes run the mat-muls at their best; a half pass goes when the stock of encoded windows is getting low
+            const bool low_stock = (int)sc.ready.size() + inflight_windows() < st->enc_chunk;
+            if (!starving && avail < st->enc_chunk && !(low_stock && avail >= std::max(1, st->enc_chunk / 2))) break;
             int rc = launch_pass(avail);
             if (rc) return rc;
         }
@@ -554,9 +556,10 @@ struct Pump {
         return OH_OK;
     }
 
-    // `check_steps` greedy steps over every row (inactive rows exit at once), then the look-in
-    int step_and_look() {
-        const auto t0 = clk::now();
+    // `check_steps` greedy steps over every row (inactive rows exit at once); asynchronous
+    clk::time_point t_steps;
+    int launch_steps() {
+        t_steps = clk::now();
         cudaStream_t s = st->stream;
         int rc;
         Submission* any = nullptr;
@@ -583,6 +586,12 @@ struct Pump {
             st->timings.n_armed_row_steps += sc.n_armed;
         }
         g_active_rows_hint = -1;
+        return OH_OK;
+    }
+    // the look-in: wait for the steps, read the rows' scalars, collect the rows that finished
+    int look() {
+        const auto t0 = t_steps;
+        cudaStream_t s = st->stream;
         OH_CUDA_CHECK(cudaMemcpyAsync(hb, st->seq_dev.p, scalar_words * 4, cudaMemcpyDeviceToHost, s));
         OH_CUDA_CHECK(cudaStreamSynchronize(s));
         st->timings.d2h_bytes += (long long)scalar_words * 4;
@@ -1010,7 +1019,7 @@ struct Pump {
             if (!sb->finished() && sb->p.strategy == OH_SAMPLING_BEAM_SEARCH) return run_beam(target, std::max(1, sb->p.beam_size));
         while (target ? !target->finished() : true) {
             poll_passes(false);
-            if ((rc = launch_passes())) return rc;
+            if (sc.n_armed < R && sc.ready.empty() && sc.passes.empty() && (rc = launch_passes())) return rc;  // nothing encoded, nothing in flight
             if ((rc = arm_rows())) return rc;
             // Decode yields to the encoder when rows run empty.  An encoder pass issued next to the decode steps only gets
             // the SMs the steps leave idle (its persistent mat-mul needs a whole SM's shared memory, and the steps' CTAs keep
@@ -1036,11 +1045,15 @@ struct Pump {
                         set_error("scheduler: windows waiting, nothing running and no free K/V slot");
                         return OH_ERR_DECODE;
                     }
-                    continue;  // launch_passes issues them (nothing is fed, so any size goes)
+                    if ((rc = launch_passes())) return rc;  // nothing is fed, so any size goes
+                    continue;
                 }
                 break;  // idle
             }
-            if ((rc = step_and_look())) return rc;
+            // the steps go first; the host then issues the next encoder passes (hundreds of launches) while the GPU decodes
+            if ((rc = launch_steps())) return rc;
+            if ((rc = launch_passes())) return rc;
+            if ((rc = look())) return rc;
         }
         return OH_OK;
     }

@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(THREADS) gemm_simt_kernel(GemmArgs g) {
         const int m = m0 + ty * TM + i;
         if (m >= M) continue;
         const int b = m / g.rows, r = m - b * g.rows;
-        TC* crow = C + (long long)b * g.c_bstride + (long long)r * g.ldc;
+        TC* crow = C + (long long)(g.c_bidx ? g.c_bidx[b] : b) * g.c_bstride + (long long)r * g.ldc;
         const float* rrow = g.R ? g.R + (long long)b * g.r_bstride + (long long)r * g.ldr : nullptr;
 #pragma unroll
         for (int j = 0; j < TN; ++j) {

@@ -53,6 +53,7 @@ struct TcParams {
     int c_hsplit;
     long long c_hstride;
     int stages;
+    const int* c_bidx;  // optional: batch b writes the C block of index c_bidx[b] (scattered K/V slots)
 };
 
 template <int BLOCK_N>
@@ -180,7 +181,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             const int b = m_blk / p.tiles_per_batch, i0 = (m_blk % p.tiles_per_batch) * BLOCK_M;
             const int row = i0 + lane_grp * 32 + lane;
             const bool row_ok = row < p.rows;
-            const long long c_off = (long long)b * p.c_bstride + (long long)row * p.ldc;
+            const long long c_off = (long long)(p.c_bidx ? __ldg(p.c_bidx + b) : b) * p.c_bstride + (long long)row * p.ldc;
             const float* rrow = (p.R && row_ok) ? p.R + (long long)b * p.r_bstride + (long long)row * p.ldr : nullptr;
             const int n_lim = min(p.N, (n_blk + 1) * BLOCK_N);  // columns of this tile only
             float4 rnext[8];
@@ -388,7 +389,7 @@ int launch_t(const GemmArgs& g, cudaStream_t st) {
     p.num_kb = p.kb_per_tap * n_taps;
     const uint32_t fmt = g.a_type == DT_BF16 ? 1u : 0u;
     p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
-    p.bias = g.bias; p.C = g.C; p.c_type = g.c_type; p.c_bstride = g.c_bstride; p.ldc = g.ldc;
+    p.bias = g.bias; p.C = g.C; p.c_type = g.c_type; p.c_bstride = g.c_bstride; p.ldc = g.ldc; p.c_bidx = g.c_bidx;
     p.R = g.R; p.r_bstride = g.r_bstride; p.ldr = g.ldr; p.gelu = g.gelu; p.round_type = g.round_type; p.lut = g.lut;
     p.c_hsplit = g.c_hsplit; p.c_hstride = g.c_hstride;
     // compact mode (encoder passes that run next to decode steps): at most 3 stages / 96 KB of ring, so that a decode CTA

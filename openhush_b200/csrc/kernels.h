@@ -67,6 +67,9 @@ struct GemmArgs {
     //   C[b*c_bstride + (n / c_hsplit) * c_hstride + i*ldc + (n % c_hsplit)]      (c_hsplit must be a multiple of 32)
     int c_hsplit = 0;
     long long c_hstride = 0;
+    // scattered batch store (cross K/V of an encoder pass into non-adjacent slots): batch b writes block c_bidx[b] (device array)
+    // instead of block b; nullptr = identity.  Honoured by the tcgen05 and SIMT kernels (the decode-time kernels take batch = 1).
+    const int* c_bidx = nullptr;
 };
 // one-off numerical self-check of the tcgen05 path against the SIMT kernel (called at context creation)
 int gemm_tc_selftest(cudaStream_t st, float* max_rel_err);
