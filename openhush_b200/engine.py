@@ -471,3 +471,47 @@ class WorkerPool:
             self.jobs.put(None)
         for t in self._threads:
             t.join()
+
+
+# ---------------------------------------------------------------------------------------------- recording.rs: overlapped chunks
+CHUNK_OVERLAP_SECS = 0.5  # /root/reference/src/recording.rs:32
+
+
+def cut_overlapping_windows(samples: np.ndarray, window_secs: float = 30.0, overlap_secs: float = CHUNK_OVERLAP_SECS, sample_rate: int = 16000):
+    """BASELINE config 4's windowing: consecutive windows of `window_secs` in which every window after the first starts
+    with the last `overlap_secs` of the previous one (recording.rs:419-426 keeps that tail "for continuity").
+    Returns [(start_sample, window_samples)]."""
+    n_win, n_ov = int(round(window_secs * sample_rate)), int(overlap_secs * sample_rate)
+    assert n_win > n_ov >= 0
+    out, start = [], 0
+    while True:
+        out.append((start, samples[start:start + n_win]))
+        if start + n_win >= len(samples):
+            return out
+        start += n_win - n_ov
+
+
+def transcribe_recording(engine, samples: np.ndarray, *, sequence_id: int = 0, window_secs: float = 30.0, overlap_secs: float = CHUNK_OVERLAP_SECS,
+                         separator: str = " "):
+    """A long recording through the hot path the way config 4 states it: overlapped 30 s windows as independent jobs of one
+    sequence (batched: the engine decodes up to its max_batch of them side by side), handed to the TranscriptionTracker in
+    streaming mode so that the words repeated across a window boundary are dropped (queue/mod.rs:213-274), and the windows'
+    timed segments put on the recording's clock (merge_timed_segments; chunk k starts at k * (window - overlap)).
+    Returns (text, [(t0, t1, text)] in 10 ms units, [JobResult per window])."""
+    from .tracker import BackpressureStrategy, TranscriptionTracker, merge_timed_segments
+    windows = cut_overlapping_windows(samples, window_secs, overlap_secs)
+    jobs = [TranscriptionJob(AudioBuffer(np.ascontiguousarray(w, dtype=np.float32), 16000), sequence_id, k, k == len(windows) - 1)
+            for k, (_, w) in enumerate(windows)]
+    tracker = TranscriptionTracker.new()  # streaming mode
+    worker = TranscriptionWorker(engine)
+    limit = max(1, getattr(getattr(engine, "context", None), "max_batch", 1))
+    texts, results = [], []
+    for j in jobs:
+        tracker.add_pending_with_config(j.sequence_id, j.chunk_id, 0, 0, BackpressureStrategy.WARN)
+    for b0 in range(0, len(jobs), limit):
+        for r in worker.process_jobs(jobs[b0:b0 + limit]):
+            results.append(r)
+            tracker.add_result(r)
+            texts.extend(t.text for t in tracker.take_ready() if t.text)
+    offsets = {k: int(round(start / 160.0)) for k, (start, _) in enumerate(windows)}  # 10 ms units
+    return separator.join(texts), merge_timed_segments(results, chunk_offsets_cs=offsets), results

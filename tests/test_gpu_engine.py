@@ -138,3 +138,48 @@ def test_quantised_ggml_files_load_and_match_their_f16_expansion(micro_path, tmp
     open(bad, "wb").write(blob[:len(blob) - 1000])
     with pytest.raises(lib.OhError):
         lib.Context(bad, compute_type=COMPUTE_F32, max_batch=1)
+
+
+@pytest.mark.parametrize("strategy", ["greedy", "beam"])
+def test_overlap_streaming_recording_matches_oracle(micro_path, micro_oracle, strategy):
+    """BASELINE config 4's host side: a 70 s recording cut into 30 s windows with 0.5 s overlap
+    (/root/reference/src/recording.rs:28-35, :419-426), the windows decoded side by side (beam 5 or greedy), texts merged by the
+    tracker's streaming hand-out with word-overlap de-duplication (/root/reference/src/queue/mod.rs:213-274) and the
+    timed segments moved to the recording's clock.  Every window's text and times must equal the oracle's for that window."""
+    from openhush_b200 import _abi
+    from openhush_b200.tracker import TranscriptionTracker
+    rec = np.concatenate([synth.audio(60), synth.audio(61), synth.audio(62, 160000)])
+    e = E.WhisperEngine.new(micro_path, "en", False, True, compute_type=COMPUTE_F32, max_batch=16)
+    p = default_full_params(1 if strategy == "beam" else 0)
+    p.temperature_inc = 0.0
+    p.translate = 1  # what the engine passes for config.translate = false (whisper.rs:257)
+    e._params = lambda: p  # the reference's engine only ever builds Greedy (whisper.rs:243); config 4 selects beam search
+    text, timed, results = E.transcribe_recording(e, rec)
+    windows = E.cut_overlapping_windows(rec)
+    assert [s for s, _ in windows] == [0, 472000, 944000] and len(results) == 3
+    tracker = TranscriptionTracker.new()
+    ref_texts, ref_timed = [], []
+    for k, (start, w) in enumerate(windows):
+        ost = O.OracleState(micro_oracle, gelu=O.GELU_TANH, act_round=O.ACT_NONE)
+        assert ost.full(np.ascontiguousarray(w), p) == 0
+        segs = ost.segments()
+        wtext = ""
+        for s in segs:  # whisper.rs:276-280: a segment that is not valid UTF-8 is skipped
+            try:
+                wtext += s["text"].decode("utf-8")
+            except UnicodeDecodeError:
+                pass
+        wtext = wtext.strip()
+        assert results[k].text == wtext, k
+        tracker.add_result(E.JobResult(wtext, 0, k, k == 2, len(w) / 16000.0))
+        ref_texts += [t.text for t in tracker.take_ready() if t.text]
+        for s in segs:
+            try:
+                s["text"].decode("utf-8")
+                ref_timed.append((start // 160 + s["t0"], start // 160 + s["t1"]))
+            except UnicodeDecodeError:
+                pass
+        ost.close()
+    assert text == " ".join(ref_texts) and len(text) > 0
+    assert [(a, b) for a, b, _ in timed] == sorted(ref_timed)
+    e.close()
