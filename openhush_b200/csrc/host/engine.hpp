@@ -10,11 +10,15 @@
 #pragma once
 #include <chrono>
 #include <cmath>
+#include <condition_variable>
 #include <cstdint>
 #include <cstdio>
+#include <deque>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <sys/stat.h>
+#include <thread>
 #include <variant>
 #include <vector>
 
@@ -131,6 +135,7 @@ class WhisperEngine {
         e->state_ = st;
         e->language_ = language;
         e->translate_ = translate;
+        e->max_batch_ = max_batch < 1 ? 1 : max_batch;
         return e;
     }
     ~WhisperEngine() {
@@ -163,6 +168,53 @@ class WhisperEngine {
         r.duration_ms = (uint64_t)std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count();
         return r;
     }
+    // additive (the multi-GPU queue): n independent transcribe() calls as ONE oh_full_batch; one entry
+    // per job, the error a job would have got from transcribe() stays with that job alone
+    std::vector<Result<TranscriptionResult>> transcribe_batch(const std::vector<const AudioBuffer*>& audios) const {
+        std::vector<Result<TranscriptionResult>> out(audios.size(), WhisperError{WhisperError::TranscriptionFailed, "not run"});
+        std::vector<const float*> ptrs;
+        std::vector<int> lens;
+        std::vector<size_t> idx;
+        for (size_t i = 0; i < audios.size(); ++i) {
+            auto v = validate_audio(audios[i]->samples.data(), audios[i]->samples.size(), audios[i]->sample_rate);
+            if (auto* err = std::get_if<AudioValidationError>(&v)) {
+                out[i] = WhisperError{WhisperError::ValidationFailed, err->message()};
+                continue;
+            }
+            ptrs.push_back(audios[i]->samples.data());
+            lens.push_back((int)audios[i]->samples.size());
+            idx.push_back(i);
+        }
+        if (ptrs.empty()) return out;
+        const auto t0 = std::chrono::steady_clock::now();
+        oh_full_params p = oh_full_default_params(OH_SAMPLING_GREEDY);
+        p.greedy_best_of = 1;
+        if (language_ != "auto") p.language = language_.c_str();
+        p.translate = translate_ ? 0 : 1;
+        const int rc = oh_full_batch(ctx_, state_, p, ptrs.data(), lens.data(), (int)ptrs.size());
+        const uint64_t ms = (uint64_t)std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count();
+        for (size_t k = 0; k < idx.size(); ++k) {
+            const int item_rc = rc != 0 ? rc : oh_full_item_rc(state_, (int)k);
+            if (item_rc != 0) {
+                const char* name = item_rc == OH_ERR_MEL ? "UnableToCalculateSpectrogram" : item_rc == OH_ERR_ENCODE ? "FailedToEncode" : item_rc == OH_ERR_DECODE ? "FailedToDecode" : nullptr;
+                out[idx[k]] = WhisperError{WhisperError::TranscriptionFailed, name ? std::string(name) : "GenericError(" + std::to_string(item_rc) + ")"};
+                continue;
+            }
+            std::string text;
+            const int n = oh_full_n_segments_item(state_, (int)k);
+            for (int i = 0; i < n; ++i) {
+                const char* s = oh_full_get_segment_text_item(state_, (int)k, i);
+                if (s && valid_utf8(s)) text += s;
+            }
+            TranscriptionResult r;
+            r.text = trim(text);
+            r.language = language_ == "auto" ? "en" : language_;
+            r.duration_ms = ms;
+            out[idx[k]] = r;
+        }
+        return out;
+    }
+    int max_batch() const { return max_batch_; }
     // whisper.rs:334-387
     BenchmarkResult benchmark(float safety_margin) const {
         AudioBuffer a;
@@ -199,6 +251,7 @@ class WhisperEngine {
     oh_state* state_ = nullptr;
     std::string language_;
     bool translate_ = false;
+    int max_batch_ = 1;
 };
 
 // queue/mod.rs:18-43 and the hot-path caller queue/worker.rs:119-193
@@ -222,5 +275,94 @@ inline JobResult process_job(const WhisperEngine* engine, const TranscriptionJob
     if (auto* ok = std::get_if<TranscriptionResult>(&res)) r.text = ok->text;  // worker.rs:159-165: error -> logged + empty text
     return r;
 }
+
+
+// One worker thread per GPU over ONE shared job queue (the reference's documented multi-GPU design: config.gpu.devices,
+// /root/reference/src/config.rs:921-929; spawn_worker, /root/reference/src/queue/worker.rs:255-267).  A worker drains up to its
+// engine's max_batch queued jobs and hands them to the engine as one oh_full_batch; results go to one queue, a
+// TranscriptionTracker restores the order.  A worker without an engine takes no jobs while another worker has one; with no
+// engine at all one thread answers every job with an empty text (worker.rs:125-142).  Nothing is exchanged between GPUs.
+class WorkerPool {
+  public:
+    explicit WorkerPool(std::vector<std::unique_ptr<WhisperEngine>> engines) : engines_(std::move(engines)), jobs_done_(engines_.size(), 0) {
+        bool any = false;
+        for (auto& e : engines_) any |= (bool)e;
+        for (size_t i = 0; i < engines_.size(); ++i)
+            if (engines_[i] || (!any && i == 0)) threads_.emplace_back([this, i] { run(i); });
+    }
+    ~WorkerPool() { shutdown(); }
+    void submit(TranscriptionJob job) {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            jobs_.push_back(std::move(job));
+        }
+        cv_jobs_.notify_one();
+    }
+    // blocks until n results are available (in completion order)
+    std::vector<JobResult> drain(size_t n) {
+        std::vector<JobResult> out;
+        std::unique_lock<std::mutex> lk(mu_);
+        while (out.size() < n) {
+            cv_results_.wait(lk, [&] { return !results_.empty(); });
+            while (!results_.empty() && out.size() < n) {
+                out.push_back(std::move(results_.front()));
+                results_.pop_front();
+            }
+        }
+        return out;
+    }
+    void shutdown() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_jobs_.notify_all();
+        for (auto& t : threads_)
+            if (t.joinable()) t.join();
+        threads_.clear();
+    }
+    const std::vector<size_t>& jobs_done() const { return jobs_done_; }
+
+  private:
+    void run(size_t i) {
+        const WhisperEngine* eng = engines_[i].get();
+        const size_t limit = eng ? (size_t)eng->max_batch() : 1;
+        while (true) {
+            std::vector<TranscriptionJob> batch;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_jobs_.wait(lk, [&] { return stop_ || !jobs_.empty(); });
+                if (jobs_.empty()) return;  // stop requested and nothing left
+                while (!jobs_.empty() && batch.size() < limit) {
+                    batch.push_back(std::move(jobs_.front()));
+                    jobs_.pop_front();
+                }
+            }
+            std::vector<JobResult> res;
+            for (auto& j : batch) res.push_back(JobResult{"", j.sequence_id, j.chunk_id, j.is_final, j.buffer.duration_secs()});
+            if (eng) {
+                std::vector<const AudioBuffer*> bufs;
+                for (auto& j : batch) bufs.push_back(&j.buffer);
+                auto out = eng->transcribe_batch(bufs);
+                for (size_t k = 0; k < out.size(); ++k)
+                    if (auto* ok = std::get_if<TranscriptionResult>(&out[k])) res[k].text = ok->text;  // error -> empty text (worker.rs:159-165)
+            }
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                for (auto& r : res) results_.push_back(std::move(r));
+                jobs_done_[i] += batch.size();
+            }
+            cv_results_.notify_all();
+        }
+    }
+    std::vector<std::unique_ptr<WhisperEngine>> engines_;
+    std::vector<size_t> jobs_done_;
+    std::vector<std::thread> threads_;
+    std::mutex mu_;
+    std::condition_variable cv_jobs_, cv_results_;
+    std::deque<TranscriptionJob> jobs_;
+    std::deque<JobResult> results_;
+    bool stop_ = false;
+};
 
 }  // namespace openhush

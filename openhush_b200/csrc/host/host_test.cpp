@@ -99,6 +99,35 @@ int main(int argc, char** argv) {
         a.samples[5] = NAN;
         auto bad = eng->transcribe(a);
         CHECK(std::get_if<WhisperError>(&bad) && std::get<WhisperError>(bad).kind == WhisperError::ValidationFailed);
+        a.samples[5] = 0.0f;
+        // one worker thread per visible GPU (up to 2) over one job queue, each draining up to max_batch jobs into one
+        // oh_full_batch (queue/worker.rs:255-267; config.gpu.devices): every answer equals the single transcribe() call
+        const std::string ref_text = std::get<TranscriptionResult>(eng->transcribe(a)).text;
+        const int n_dev = argc >= 5 ? atoi(argv[4]) : 1;
+        std::vector<std::unique_ptr<WhisperEngine>> engines;
+        for (int d = 0; d < n_dev; ++d) {
+            auto er = WhisperEngine::create(argv[1], "en", false, true, d, 4);
+            CHECK(std::get_if<std::unique_ptr<WhisperEngine>>(&er) != nullptr);
+            engines.push_back(std::move(std::get<std::unique_ptr<WhisperEngine>>(er)));
+        }
+        engines.push_back(nullptr);  // a worker whose engine failed to load takes no jobs
+        WorkerPool pool(std::move(engines));
+        const int n_jobs = 9;
+        for (int j = 0; j < n_jobs; ++j) {
+            TranscriptionJob job;
+            job.buffer = a;
+            if (j == 4) job.buffer.samples[7] = INFINITY;  // fails validation alone
+            job.sequence_id = (uint64_t)j;
+            pool.submit(std::move(job));
+        }
+        auto got = pool.drain(n_jobs);
+        pool.shutdown();
+        CHECK((int)got.size() == n_jobs);
+        size_t taken = 0;
+        for (size_t w = 0; w < pool.jobs_done().size(); ++w) taken += pool.jobs_done()[w];
+        CHECK((int)taken == n_jobs && pool.jobs_done().back() == 0);
+        for (auto& r : got) CHECK(r.sequence_id == 4 ? r.text.empty() : r.text == ref_text);
+        printf("POOL_OK workers=%d\n", n_dev);
     }
     printf("HOST_TEST_OK\n");
     return 0;
