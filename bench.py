@@ -149,12 +149,13 @@ def ncu_traffic(kernel_substr: str):
         try:
             with open(path, newline="") as f:
                 rows = list(csv.reader(f))
-            hdr = rows[0]
+            hdr, units = rows[0], rows[1]
             i_name, i_grid = hdr.index("Kernel Name"), hdr.index("launch__grid_size")
             i_rd, i_wr = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
             for r in rows[2:]:
                 if len(r) > max(i_rd, i_wr) and kernel_substr in r[i_name]:
-                    best = ((float(r[i_rd]) + float(r[i_wr])) * 1e6, int(float(r[i_grid])), os.path.relpath(path, ROOT))
+                    best = (float(r[i_rd]) * scale[units[i_rd]] + float(r[i_wr]) * scale[units[i_wr]], int(float(r[i_grid])), os.path.relpath(path, ROOT))
         except (OSError, ValueError, IndexError):
             continue
     return best
