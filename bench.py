@@ -211,7 +211,7 @@ def main():
     ap.add_argument("--strategy", default="greedy", choices=["greedy", "beam"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the strong-scaling and single-call latency legs")
-    ap.add_argument("--depth", type=int, default=2, help="stream API: tickets submitted ahead of the one being waited for (bounded queue of a streaming server)")
+    ap.add_argument("--depth", type=int, default=3, help="stream API: tickets submitted ahead of the one being waited for (bounded queue of a streaming server)")
     ap.add_argument("--value-only", action="store_true", help="knob sweeps: only the kernel-only value leg (no e2e, profile, extras, CPU legs)")
     ap.add_argument("--blocking", action="store_true", help="one blocking oh_full_batch per step (rows drain between steps) instead of the stream API")
     args = ap.parse_args()
