@@ -129,7 +129,10 @@ OH_API oh_full_params oh_full_default_params(int strategy);
 OH_API int oh_full(oh_context* ctx, oh_state* state, oh_full_params params, const float* samples, int n_samples);
 
 /* additive: `batch` independent oh_full calls run as one batched job (BASELINE configs 2-5).
- * Item i is exactly oh_full(samples[i], n_samples[i]); results are read with the *_item getters. */
+ * Item i is exactly oh_full(samples[i], n_samples[i]) on a freshly created state; results are read with the *_item getters.
+ * (Sampled tokens of the temperature fallback, A.7: oh_full draws from the state's generator, which is seeded 0 at state
+ * creation and continues across calls like upstream's; every item of a batched or streamed call draws from a generator
+ * seeded 0 for that call, so its result does not depend on what the state or its neighbours decoded before.) */
 OH_API int oh_full_batch(oh_context* ctx, oh_state* state, oh_full_params params, const float* const* samples,
                          const int* n_samples, int batch);
 

@@ -78,13 +78,12 @@ OH_API oh_context* oh_init_from_file(const char* path_model, oh_context_params p
                 return nullptr;
             }
             const bool ok = selftest.ensure([&] {
-                float err = -1.0f, e2 = -1.0f, e3 = -1.0f, e4 = -1.0f;
+                float err = -1.0f, e3 = -1.0f, e4 = -1.0f;
                 int rc = gemm_tc_selftest(nullptr, &err);
-                if (rc == OH_OK) rc = gemm_skinny_selftest(nullptr, &e2);
                 if (rc == OH_OK) rc = gemm_splitk_selftest(nullptr, &e3);
                 // attention compares two different summation orders with 16-bit P: own (looser) bound inside
                 if (rc == OH_OK) rc = encoder_attention_tc_selftest(nullptr, &e4);
-                err = std::max(err, std::max(e2, e3));
+                err = std::max(err, e3);
                 selftest_err[dev] = err;
                 selftest_rc[dev] = rc;
                 g_attn_selftest_err = e4;
@@ -188,7 +187,8 @@ OH_API oh_full_params oh_full_default_params(int strategy) {
     return p;
 }
 
-static int full_impl(oh_context* ctx, oh_state* st, const oh_full_params& p, const float* const* samples, const int* n, int batch, bool on_device) {
+static int full_impl(oh_context* ctx, oh_state* st, const oh_full_params& p, const float* const* samples, const int* n, int batch, bool on_device,
+                     bool persistent_rng) {
     if (!ctx || !st || st->ctx != ctx || !samples || !n) return OH_ERR_INVALID;
     if (select_device(ctx)) return OH_ERR_CUDA;
     set_error("");
@@ -196,7 +196,7 @@ static int full_impl(oh_context* ctx, oh_state* st, const oh_full_params& p, con
         if (n[i] < 0 || (!samples[i] && n[i] > 0)) return OH_ERR_INVALID;
     int rc;
     try {  // no exception may cross the C ABI
-        rc = run_full(st, p, samples, n, batch, on_device);
+        rc = run_full(st, p, samples, n, batch, on_device, persistent_rng);
     } catch (const std::exception& e) {
         set_error(std::string("oh_full: ") + e.what());
         sched_abort(st);
@@ -246,14 +246,15 @@ OH_API int oh_full_item_rc(oh_state* st, int item) {
 OH_API int oh_full(oh_context* ctx, oh_state* st, oh_full_params params, const float* samples, int n_samples) {
     const float* ptrs[1] = {samples};
     int ns[1] = {n_samples};
-    return full_impl(ctx, st, params, ptrs, ns, 1, false);
+    // the state's generator for sampled (t > 0) tokens continues across oh_full calls, like upstream's (A.7)
+    return full_impl(ctx, st, params, ptrs, ns, 1, false, true);
 }
 OH_API int oh_full_batch(oh_context* ctx, oh_state* st, oh_full_params params, const float* const* samples, const int* n_samples, int batch) {
-    return full_impl(ctx, st, params, samples, n_samples, batch, false);
+    return full_impl(ctx, st, params, samples, n_samples, batch, false, false);
 }
 OH_API int oh_full_batch_device(oh_context* ctx, oh_state* st, oh_full_params params, const float* const* d_samples, const int* n_samples,
                                 int batch) {
-    return full_impl(ctx, st, params, d_samples, n_samples, batch, true);
+    return full_impl(ctx, st, params, d_samples, n_samples, batch, true, false);
 }
 
 // ---- results

@@ -259,135 +259,6 @@ __global__ void __launch_bounds__(128) cross_attention_decode_kernel(const T* __
     if (tid < kHeadDim) out[(size_t)b * d + h * kHeadDim + tid] = Cvt<T>::from_f32((part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid]));
 }
 
-// ------------------------------------------------------------- K8 (16-bit modes): single-pass decode attention
-// One CTA per (head, row), 128 threads = 16 groups of 8 lanes.  Group g owns keys j = g (mod 16); per iteration it
-// has 4 K rows and 4 V rows (8 x 16 B per lane) in flight, and keeps its own online-softmax state (running max,
-// running sum, 8 output channels per lane) so that K and V are each read exactly once in one sweep with no CTA-wide
-// barrier in the loop; the 16 partial states are merged through shared memory at the end (log-sum-exp merge).
-// IS_SELF: first append this step's k,v to the cache at [slot][pos], then attend over [0, pos].
-template <typename T, bool IS_SELF>
-__global__ void __launch_bounds__(128) attention_decode_online_kernel(const T* __restrict__ qsrc, int q_ld, const T* kbase, const T* vbase,
-                                                                      T* kcache, T* vcache, DecodeSeqState s, int d, int n_ctx_or_T,
-                                                                      T* __restrict__ out) {
-    pdl_wait();  // programmatic dependent launch: nothing above depends on the preceding kernel (see common.cuh)
-    pdl_launch_dependents();
-    const int h = blockIdx.x, b = blockIdx.y;
-    if (!s.active[b]) return;
-    __shared__ float sm_m[16], sm_l[16];
-    __shared__ float sm_o[16][kHeadDim];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int sub = lane & 7, grp = lane >> 3;
-    const int gidx = warp * 4 + grp;
-    const int slot = IS_SELF ? s.sslot[b] : s.slot[b];
-    const int H = d / kHeadDim;
-    int n_kv;
-    size_t ld;
-    const T *Kb, *Vb;
-    if (IS_SELF) {
-        const int pos = s.pos[b];
-        n_kv = pos + 1;
-        ld = kHeadDim;
-        T* K = kcache + ((size_t)slot * H + h) * n_ctx_or_T * kHeadDim;
-        T* V = vcache + ((size_t)slot * H + h) * n_ctx_or_T * kHeadDim;
-        if (tid < kHeadDim) {  // qsrc = qkv row of this step: q | k | v
-            const T* row = qsrc + (size_t)b * q_ld;
-            K[(size_t)pos * kHeadDim + tid] = row[d + h * kHeadDim + tid];
-            V[(size_t)pos * kHeadDim + tid] = row[2 * d + h * kHeadDim + tid];
-        }
-        __syncthreads();
-        Kb = K + sub * 8;
-        Vb = V + sub * 8;
-    } else {
-        n_kv = n_ctx_or_T;
-        ld = kHeadDim;
-        Kb = kbase + (((size_t)slot * 2 + 0) * H + h) * n_kv * kHeadDim + sub * 8;
-        Vb = vbase + (((size_t)slot * 2 + 1) * H + h) * n_kv * kHeadDim + sub * 8;
-    }
-    float qv[8];
-    {
-        const T* qr = qsrc + (size_t)b * q_ld + h * kHeadDim + sub * 8;
-        const float sc = 0.125f * 1.44269504088896340736f;  // 1/sqrt(64) * log2(e): scores live in the exp2 domain
-#pragma unroll
-        for (int i = 0; i < 8; ++i) qv[i] = Cvt<T>::to_f32(qr[i]) * sc;
-    }
-    float m_run = -INFINITY, l_run = 0.0f, o[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = 0.0f;
-
-    // NOTE: the trip count must be warp-uniform (full-mask shuffles below); validity is handled per key
-    for (int base = 0; base < n_kv; base += 64) {
-        const int j0 = base + gidx;
-        Vec8<T> kv[4], vv[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int j = j0 + 16 * u;
-            if (j < n_kv) {
-                if (IS_SELF) {  // the cache is written by this kernel: coherent (L2) loads, not the read-only path
-                    kv[u].load_cg(Kb + (size_t)j * ld);
-                    vv[u].load_cg(Vb + (size_t)j * ld);
-                } else {
-                    kv[u].load(Kb + (size_t)j * ld);
-                    vv[u].load(Vb + (size_t)j * ld);
-                }
-            }
-        }
-        float sc4[4];
-        float mx = -INFINITY;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int j = j0 + 16 * u;
-            float acc = 0.0f;
-            if (j < n_kv) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) acc = fmaf(qv[i], kv[u].v[i], acc);
-            }
-            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-            acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-            sc4[u] = j < n_kv ? acc : -INFINITY;
-            mx = fmaxf(mx, sc4[u]);
-        }
-        if (mx > -INFINITY) {  // this group has at least one valid key in this sweep (uniform over its 8 lanes)
-            const float m_new = fmaxf(m_run, mx);
-            const float corr = exp2f(m_run - m_new);
-            m_run = m_new;
-            l_run *= corr;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] *= corr;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (j0 + 16 * u < n_kv) {
-                    const float p = exp2f(sc4[u] - m_new);
-                    l_run += p;
-                    const float pr = Cvt<T>::to_f32(Cvt<T>::from_f32(p));
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) o[i] = fmaf(pr, vv[u].v[i], o[i]);
-                }
-            }
-        }
-    }
-    if (sub == 0) {
-        sm_m[gidx] = m_run;
-        sm_l[gidx] = l_run;
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) sm_o[gidx][sub * 8 + i] = o[i];
-    __syncthreads();
-    if (tid < kHeadDim) {
-        float M = -INFINITY;
-#pragma unroll
-        for (int g2 = 0; g2 < 16; ++g2) M = fmaxf(M, sm_m[g2]);
-        float L = 0.0f, O = 0.0f;
-#pragma unroll
-        for (int g2 = 0; g2 < 16; ++g2) {
-            const float w = sm_m[g2] == -INFINITY ? 0.0f : exp2f(sm_m[g2] - M);
-            L = fmaf(sm_l[g2], w, L);
-            O = fmaf(sm_o[g2][tid], w, O);
-        }
-        out[(size_t)b * d + h * kHeadDim + tid] = Cvt<T>::from_f32(O / L);
-    }
-}
-
 // eight 16-bit elements (one 16-byte load) -> f32
 template <typename T>
 __device__ __forceinline__ void raw8_to_f32(const uint4& u, float (&v)[8]);
@@ -1048,15 +919,7 @@ int launch_self_attention_decode(const void* qkv, void* kcache, void* vcache, in
     if (n_ctx > 448) return OH_ERR_INVALID;
     OH_SKIP_IF(PC_SELF_ATTN);
     ProfScope ps(PC_SELF_ATTN, 0.0, st);
-    static const int use_warp = [] {
-        const char* e = getenv("OH_SELFATTN");
-        return (e && strcmp(e, "online") == 0) ? 0 : 1;
-    }();
     if (type == DT_F32) OH_CUDA_CHECK(launch_k(self_attention_decode_kernel<float>, grid, 128, 0, st, (const float*)qkv, (float*)kcache, (float*)vcache, s, d, n_ctx, (float*)out));
-    else if (!use_warp && type == DT_F16)
-        OH_CUDA_CHECK(launch_k(attention_decode_online_kernel<__half, true>, grid, 128, 0, st, (const __half*)qkv, 3 * d, nullptr, nullptr, (__half*)kcache, (__half*)vcache, s, d, n_ctx, (__half*)out));
-    else if (!use_warp)
-        OH_CUDA_CHECK(launch_k(attention_decode_online_kernel<__nv_bfloat16, true>, grid, 128, 0, st, (const __nv_bfloat16*)qkv, 3 * d, nullptr, nullptr, (__nv_bfloat16*)kcache, (__nv_bfloat16*)vcache, s, d, n_ctx, (__nv_bfloat16*)out));
     else if (type == DT_F16)
         OH_CUDA_CHECK(launch_k(self_attention_decode_warp_kernel<__half>, (rows * (d / kHeadDim) + 3) / 4, 128, 0, st, (const __half*)qkv, (__half*)kcache, (__half*)vcache, s, d, n_ctx, rows, (__half*)out));
     else
@@ -1099,10 +962,10 @@ int launch_cross_attention_decode(const void* q, const void* xkv, int type, cons
         OH_CUDA_CHECK(launch_k(cross_attention_decode_bulk_kernel<__half>, grid, XA_THREADS, xa_smem, st, (const __half*)q, (const __half*)xkv, s, d, T, (__half*)out, xa_stages));
     else if (use_bulk)
         OH_CUDA_CHECK(launch_k(cross_attention_decode_bulk_kernel<__nv_bfloat16>, grid, XA_THREADS, xa_smem, st, (const __nv_bfloat16*)q, (const __nv_bfloat16*)xkv, s, d, T, (__nv_bfloat16*)out, xa_stages));
-    else if (type == DT_F16)
-        OH_CUDA_CHECK(launch_k(attention_decode_online_kernel<__half, false>, grid, 128, 0, st, (const __half*)q, d, (const __half*)xkv, (const __half*)xkv, nullptr, nullptr, s, d, T, (__half*)out));
+    else if (type == DT_F16)  // OH_XATTN=online, or the shared-memory opt-in failed: the two-pass kernel of the parity mode
+        OH_CUDA_CHECK(launch_k(cross_attention_decode_kernel<__half>, grid, 128, 0, st, (const __half*)q, (const __half*)xkv, s, d, T, (__half*)out));
     else
-        OH_CUDA_CHECK(launch_k(attention_decode_online_kernel<__nv_bfloat16, false>, grid, 128, 0, st, (const __nv_bfloat16*)q, d, (const __nv_bfloat16*)xkv, (const __nv_bfloat16*)xkv, nullptr, nullptr, s, d, T, (__nv_bfloat16*)out));
+        OH_CUDA_CHECK(launch_k(cross_attention_decode_kernel<__nv_bfloat16>, grid, 128, 0, st, (const __nv_bfloat16*)q, (const __nv_bfloat16*)xkv, s, d, T, (__nv_bfloat16*)out));
     OH_COUNT_LAUNCH();
     OH_CUDA_CHECK(cudaGetLastError());
     return OH_OK;

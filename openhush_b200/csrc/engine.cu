@@ -167,8 +167,7 @@ int state_alloc(oh_state* st) {
 #ifdef OH_DIAG
     if (const char* s = getenv("OH_SKIP_CATS")) g_skip_mask = (unsigned)strtoul(s, nullptr, 0);
 #endif
-    if (const char* s = getenv("OH_SKINNY")) st->skinny_mode = atoi(s) == 0 ? 1 : 0;  // OH_SKINNY=0: decode mat-muls through the persistent tcgen05 kernel
-    if (const char* s = getenv("OH_DECODE_GEMM")) st->skinny_mode = strcmp(s, "skinny") == 0 ? 0 : (strcmp(s, "tc") == 0 ? 1 : 2);
+    if (const char* s = getenv("OH_DECODE_GEMM")) st->splitk_decode = strcmp(s, "tc") != 0;  // OH_DECODE_GEMM=tc: decode mat-muls through the persistent tcgen05 kernel
 
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // lo = numerically largest = least urgent
@@ -397,8 +396,8 @@ static int gemm(oh_state* st, GemmArgs g, cudaStream_t stream = nullptr) {
     g.round_type = act;
     if (g.gelu != GELU_NONE) g.gelu = act == DT_F32 ? (st->gelu_lut_f32 ? GELU_LUT : GELU_TANH) : GELU_FAST;
     if (act != DT_F32 && st->gemm_mode == 0 && gemm_tc_available()) {
-        if (g.batch * g.rows <= 256 && st->skinny_mode != 1) {
-            int rc = st->skinny_mode == 2 ? launch_gemm_splitk(g, stream) : launch_gemm_skinny(g, stream);
+        if (g.batch * g.rows <= 256 && st->splitk_decode) {
+            int rc = launch_gemm_splitk(g, stream);
             if (rc != OH_ERR_UNSUPPORTED) return rc;
         }
         int rc = launch_gemm_tc(g, stream);

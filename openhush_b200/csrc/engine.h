@@ -191,7 +191,7 @@ struct oh_state {
     bool use_graphs = true;
     int gemm_mode = 0;             // 0 auto (tcgen05 when 16-bit), 1 force SIMT
     int attn_mode = 0;             // 0 auto, 1 force the simple kernel
-    int skinny_mode = 2;           // decode mat-muls: 2 cluster split-K tcgen05 kernel (default), 0 register-streaming mma.sync kernel, 1 persistent tcgen05 kernel
+    bool splitk_decode = true;     // decode mat-muls (M <= 256): cluster split-K tcgen05 kernel; false (OH_DECODE_GEMM=tc): the persistent tcgen05 kernel
     bool use_pdl = true;           // OH_PDL=0: decode-step kernels are launched fully serialised
     bool gelu_lut_f32 = false;     // OH_GELU=lut: f32 mode evaluates GELU through ggml's f16 table instead of f32 tanh
     oh::Profiler* prof = nullptr;
@@ -227,9 +227,11 @@ enum { K9_NONE = 0, K9_GREEDY = 1, K9_DUMP = 2, K9_TOPK = 3 };  // what follows 
 int run_decode_step_graph(oh_state* st, int rows, int k9_mode = K9_GREEDY);
 
 // the full() driver (full.cu)
-int run_full(oh_state* st, const oh_full_params& p, const float* const* pcm, const int* n, int batch, bool pcm_on_device);
+// persistent_rng: sampled (t > 0) tokens draw from the state's generators, which continue across calls (oh_full: upstream's
+// behaviour); otherwise every item draws from a generator seeded 0 for this call (batched / streamed jobs: each equals oh_full on a fresh state)
+int run_full(oh_state* st, const oh_full_params& p, const float* const* pcm, const int* n, int batch, bool pcm_on_device, bool persistent_rng);
 int sched_submit(oh_state* st, const oh_full_params& p, const float* const* pcm, const int* n, int batch, bool pcm_on_device, bool persistent_rngs,
-                 int* ticket);
+                 int* ticket, bool carry_context = false);
 int sched_wait(oh_state* st, int ticket);
 int sched_pending(const oh_state* st);
 void sched_abort(oh_state* st);    // drop every live submission, reset rows and slots

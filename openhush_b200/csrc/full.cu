@@ -1072,7 +1072,7 @@ bool same_policy(const oh_full_params& a, const oh_full_params& b, const std::st
 int sched_pending(const oh_state* st) { return (int)st->sched.subs.size(); }
 
 int sched_submit(oh_state* st, const oh_full_params& p, const float* const* pcm, const int* n, int batch, bool pcm_on_device, bool persistent_rngs,
-                 int* ticket) {
+                 int* ticket, bool carry_context) {
     const Model& m = *st->ctx->model;
     const Vocab& vc = m.vocab;
     const HParams& hp = m.hp;
@@ -1144,7 +1144,7 @@ int sched_submit(oh_state* st, const oh_full_params& p, const float* const* pcm,
 
     // the prompts of earlier calls survive only with no_context = false (blocking calls: item i continues item i)
     std::vector<std::vector<int>> carried(batch);
-    if (!p.no_context && persistent_rngs)
+    if (!p.no_context && carry_context)
         for (int i = 0; i < batch && i < (int)st->items.size(); ++i) carried[i] = st->items[i].prompt_past;
 
     // ---- front end: PCM upload + log-mel on the front-end stream
@@ -1222,9 +1222,9 @@ int sched_wait(oh_state* st, int ticket) {
     return OH_OK;
 }
 
-int run_full(oh_state* st, const oh_full_params& p, const float* const* pcm, const int* n, int batch, bool pcm_on_device) {
+int run_full(oh_state* st, const oh_full_params& p, const float* const* pcm, const int* n, int batch, bool pcm_on_device, bool persistent_rng) {
     int ticket = 0;
-    int rc = sched_submit(st, p, pcm, n, batch, pcm_on_device, /*persistent_rngs=*/true, &ticket);
+    int rc = sched_submit(st, p, pcm, n, batch, pcm_on_device, persistent_rng, &ticket, /*carry_context=*/true);
     if (rc == OH_OK) rc = sched_wait(st, ticket);
     if (rc && rc != OH_ERR_INVALID && rc != OH_ERR_UNSUPPORTED) sched_abort(st);  // a device-side failure: nothing half-done stays behind
     return rc;

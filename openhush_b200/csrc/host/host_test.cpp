@@ -102,7 +102,12 @@ int main(int argc, char** argv) {
         a.samples[5] = 0.0f;
         // one worker thread per visible GPU (up to 2) over one job queue, each draining up to max_batch jobs into one
         // oh_full_batch (queue/worker.rs:255-267; config.gpu.devices): every answer equals the single transcribe() call
-        const std::string ref_text = std::get<TranscriptionResult>(eng->transcribe(a)).text;
+        std::string ref_text;
+        {   // a fresh engine: the first call on a fresh state is what every job of a batched call equals (oh_whisper.h)
+            auto fr = WhisperEngine::create(argv[1], "en", false, true);
+            CHECK(std::get_if<std::unique_ptr<WhisperEngine>>(&fr) != nullptr);
+            ref_text = std::get<TranscriptionResult>(std::get<std::unique_ptr<WhisperEngine>>(fr)->transcribe(a)).text;
+        }
         const int n_dev = argc >= 5 ? atoi(argv[4]) : 1;
         std::vector<std::unique_ptr<WhisperEngine>> engines;
         for (int d = 0; d < n_dev; ++d) {

@@ -73,9 +73,6 @@ struct GemmArgs {
 };
 // one-off numerical self-check of the tcgen05 path against the SIMT kernel (called at context creation)
 int gemm_tc_selftest(cudaStream_t st, float* max_rel_err);
-// decode-time mat-muls (M <= 256 rows): weight-streaming kernel with cluster split-K (gemm_skinny.cu)
-int launch_gemm_skinny(const GemmArgs& g, cudaStream_t st);
-int gemm_skinny_selftest(cudaStream_t st, float* max_rel_err);
 // decode-time mat-muls on tcgen05 with cluster split-K and a DSMEM reduction (gemm_splitk.cu); the default for M <= 256
 int launch_gemm_splitk(const GemmArgs& g, cudaStream_t st);
 int gemm_splitk_selftest(cudaStream_t st, float* max_rel_err);

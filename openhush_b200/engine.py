@@ -511,7 +511,7 @@ def transcribe_recording(engine, samples: np.ndarray, *, sequence_id: int = 0, w
     for b0 in range(0, len(jobs), limit):
         for r in worker.process_jobs(jobs[b0:b0 + limit]):
             results.append(r)
-            tracker.add_result(r)
+            tracker.add_result(JobResult(r.text, r.sequence_id, r.chunk_id, r.is_final, r.duration_secs, list(r.segments)))  # the tracker edits its copy
             texts.extend(t.text for t in tracker.take_ready() if t.text)
     offsets = {k: int(round(start / 160.0)) for k, (start, _) in enumerate(windows)}  # 10 ms units
     return separator.join(texts), merge_timed_segments(results, chunk_offsets_cs=offsets), results
