@@ -220,6 +220,11 @@ OH_API int oh_load_pcm_16k(oh_context* ctx, oh_state* state, const void* pcm, in
 OH_API int oh_load_pcm_16k_device(oh_context* ctx, oh_state* state, const void* d_pcm, int format, int bits, int channels, int sample_rate,
                                   long long n_frames, float* d_out, long long cap, long long* out_n);
 
+/* RMS level in dB full scale of every `chunk`-sample block of a 16 kHz clip (host in, host out), one launch for the whole
+ * clip: the per-chunk feature of the stand-in VAD engine behind the reference's VadEngine trait (src/vad/mod.rs:34-55; the
+ * reference's own engine, Silero, is an ONNX model whose weights are not in its tree).  SURVEY.md section 8f N3. */
+OH_API int oh_chunk_rms_db(oh_context* ctx, oh_state* state, const float* pcm, long long n_samples, int chunk, float* out, int n_chunks);
+
 /* ---- stage entry points (whisper_pcm_to_mel / whisper_encode / whisper_decode / whisper_get_logits
  * in whisper.h; the reference never calls them, the parity tests and bench.py do) ---------------- */
 

@@ -411,6 +411,20 @@ OH_API int oh_load_pcm_16k(oh_context* ctx, oh_state* st, const void* pcm, int f
     }
 }
 
+OH_API int oh_chunk_rms_db(oh_context* ctx, oh_state* st, const float* pcm, long long n, int chunk, float* out, int n_chunks) {
+    if (!ctx || !st || st->ctx != ctx || !pcm || !out || chunk < 1 || n_chunks < 0 || (long long)n_chunks * chunk > n) return OH_ERR_INVALID;
+    if (select_device(ctx)) return OH_ERR_CUDA;
+    if (n_chunks == 0) return OH_OK;
+    int rc;
+    if ((rc = ensure(st->resample_in, (size_t)n_chunks * chunk * 4))) return rc;
+    if ((rc = ensure(st->resample_out, (size_t)n_chunks * 4))) return rc;
+    OH_CUDA_CHECK(cudaMemcpyAsync(st->resample_in.p, pcm, (size_t)n_chunks * chunk * 4, cudaMemcpyHostToDevice, st->stream));
+    if ((rc = chunk_rms_db_device((const float*)st->resample_in.p, chunk, n_chunks, (float*)st->resample_out.p, st->stream))) return rc;
+    OH_CUDA_CHECK(cudaMemcpyAsync(out, st->resample_out.p, (size_t)n_chunks * 4, cudaMemcpyDeviceToHost, st->stream));
+    OH_CUDA_CHECK(cudaStreamSynchronize(st->stream));
+    return OH_OK;
+}
+
 // ---- stage entry points
 OH_API int oh_pcm_to_mel_batch(oh_context* ctx, oh_state* st, const float* const* samples, const int* n_samples, int batch, float* const* out_mel,
                                int* out_n_len) {

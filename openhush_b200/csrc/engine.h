@@ -242,6 +242,8 @@ long long resample_out_len(int sample_rate, long long n_frames, bool pad_min_dur
 int resample_to_16k_device(oh_state* st, const void* d_pcm, int format, int bits, int channels, int sample_rate, long long n_frames, float* d_out,
                            long long* out_n, cudaStream_t stream);
 
+int chunk_rms_db_device(const float* d_pcm, int chunk, int n_chunks, float* d_out, cudaStream_t stream);
+
 int ensure(DevBuf& b, size_t bytes);
 void release(DevBuf& b);
 const int* clip_max_key(oh_state* st, int batch, int clip);  // stage-API block

@@ -167,6 +167,18 @@ __global__ void __launch_bounds__(RS_THREADS) resample_sinc_kernel(const void* _
     }
 }
 
+// RMS level (dB full scale) of every `chunk`-sample block of a 16 kHz clip: one warp per block (the stand-in VAD engine of
+// SURVEY.md section 8f N3 — the reference's Silero model is not in its tree; see openhush_b200/vad.py)
+__global__ void __launch_bounds__(256) chunk_rms_db_kernel(const float* __restrict__ pcm, int chunk, int n_chunks, float* __restrict__ out) {
+    const int w = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (w >= n_chunks) return;
+    const float* x = pcm + (size_t)w * chunk;
+    float acc = 0.0f;
+    for (int i = lane; i < chunk; i += 32) acc = fmaf(x[i], x[i], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) out[w] = 20.0f * log10f(fmaxf(sqrtf(acc / (float)chunk), 1e-10f));
+}
+
 // same-rate input: conversion and mono mix only
 template <int FORMAT>
 __global__ void mono_mix_kernel(const void* __restrict__ pcm, int channels, float inv_max, long long n_frames, float* __restrict__ out) {
@@ -231,6 +243,14 @@ int resample_to_16k_device(oh_state* st, const void* d_pcm, int format, int bits
         n16 = need;
     }
     if (out_n) *out_n = n16;
+    return OH_OK;
+}
+
+int chunk_rms_db_device(const float* d_pcm, int chunk, int n_chunks, float* d_out, cudaStream_t stream) {
+    if (n_chunks <= 0) return OH_OK;
+    chunk_rms_db_kernel<<<(n_chunks + 7) / 8, 256, 0, stream>>>(d_pcm, chunk, n_chunks, d_out);
+    OH_COUNT_LAUNCH();
+    OH_CUDA_CHECK(cudaGetLastError());
     return OH_OK;
 }
 

@@ -72,6 +72,7 @@ SYMBOLS = {
     "oh_pcm_16k_len": (C.c_longlong, [C.c_int, C.c_longlong]),
     "oh_load_pcm_16k": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong, _vp, C.c_longlong, C.POINTER(C.c_longlong)]),
     "oh_load_pcm_16k_device": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong, _vp, C.c_longlong, C.POINTER(C.c_longlong)]),
+    "oh_chunk_rms_db": (C.c_int, [_vp, _vp, _vp, C.c_longlong, C.c_int, _vp, C.c_int]),
     "oh_pcm_to_mel_batch": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp, _vp]),
     "oh_pcm_to_mel_device": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp]),
     "oh_encode_batch": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp]),

@@ -160,6 +160,8 @@ extern "C" {
                            sample_rate: c_int, n_frames: c_longlong, out: *mut f32, cap: c_longlong, out_n: *mut c_longlong) -> c_int;
     pub fn oh_load_pcm_16k_device(ctx: *mut oh_context, state: *mut oh_state, d_pcm: *const c_void, format: c_int, bits: c_int, channels: c_int,
                                   sample_rate: c_int, n_frames: c_longlong, d_out: *mut f32, cap: c_longlong, out_n: *mut c_longlong) -> c_int;
+    pub fn oh_chunk_rms_db(ctx: *mut oh_context, state: *mut oh_state, pcm: *const f32, n_samples: c_longlong, chunk: c_int, out: *mut f32,
+                           n_chunks: c_int) -> c_int;
     // ---- stage entry points
     pub fn oh_pcm_to_mel_batch(ctx: *mut oh_context, state: *mut oh_state, samples: *const *const f32, n_samples: *const c_int, batch: c_int,
                                out_mel: *const *mut f32, out_n_len: *mut c_int) -> c_int;
