@@ -6,6 +6,5 @@ echo "== baseline 256"; timeout 200 python scripts/bench_decode_step.py large-v3
 echo "== dual 256 + xattn stages 3"; OH_DUAL=256 OH_XATTN_STAGES=3 timeout 200 python scripts/bench_decode_step.py large-v3 256 100 quick
 echo "== dual 256 + xattn stages 2"; OH_DUAL=256 OH_XATTN_STAGES=2 timeout 200 python scripts/bench_decode_step.py large-v3 256 100 quick
 echo "== xattn stages 2 alone"; OH_XATTN_STAGES=2 timeout 200 python scripts/bench_decode_step.py large-v3 256 100 quick
-echo "== vad gpu test"; timeout 300 python -m pytest tests/test_vad.py tests/test_gpu_engine.py -m gpu -q --timeout 300 -p no:cacheprovider
 } > $o 2>&1
 tail -40 $o
