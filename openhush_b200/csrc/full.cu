@@ -361,19 +361,25 @@ struct Pump {
         for (const EncoderPass& p : sc.passes) n += (int)p.wins.size();
         return n;
     }
-    void poll_passes(bool block_on_oldest) {
+    // collect finished encoder passes (their windows become ready); a device fault surfaces here instead of spinning
+    int poll_passes(bool block_on_oldest) {
         while (!sc.passes.empty()) {
             EncoderPass& p = sc.passes.front();
             cudaError_t q = block_on_oldest ? cudaEventSynchronize(p.done) : cudaEventQuery(p.done);
             block_on_oldest = false;
-            if (q != cudaSuccess) {
-                if (q != cudaErrorNotReady) cudaGetLastError();
+            if (q == cudaErrorNotReady) {
+                cudaGetLastError();
                 break;
+            }
+            if (q != cudaSuccess) {
+                set_error(std::string("encoder pass failed: ") + cudaGetErrorString(q));
+                return OH_ERR_CUDA;
             }
             for (const WinRef& w : p.wins) sc.ready.push_back(w);
             sc.event_pool.push_back(p.done);
             sc.passes.pop_front();
         }
+        return OH_OK;
     }
     int launch_pass(int k) {
         const auto t0 = clk::now();
@@ -894,7 +900,7 @@ struct Pump {
         }
         if ((rc = ensure(st->beam_pairs, (size_t)R * sizeof(int4)))) return rc;
         while (target ? !target->finished() : true) {
-            poll_passes(false);
+            if ((rc = poll_passes(false))) return rc;
             if ((rc = launch_passes())) return rc;
             int n_busy = 0;
             for (int g = 0; g < NG; ++g) {
@@ -906,7 +912,7 @@ struct Pump {
                 n_busy += groups[g].busy ? 1 : 0;
             }
             if (n_busy > 0 && NG - n_busy >= std::max(1, st->starve_rows / nb) && sc.ready.empty() && !sc.passes.empty() && sc.parked.empty()) {
-                poll_passes(true);  // decode yields to the encoder pass in flight when groups run empty (see run())
+                if ((rc = poll_passes(true))) return rc;  // decode yields to the encoder pass in flight when groups run empty (see run())
                 continue;
             }
             if (n_busy == 0) {
@@ -917,7 +923,7 @@ struct Pump {
                 }
                 if (!sc.ready.empty()) continue;
                 if (!sc.passes.empty()) {
-                    poll_passes(true);
+                    if ((rc = poll_passes(true))) return rc;
                     continue;
                 }
                 if (!sc.need_window.empty()) {
@@ -1018,7 +1024,7 @@ struct Pump {
         for (auto& sb : sc.subs)
             if (!sb->finished() && sb->p.strategy == OH_SAMPLING_BEAM_SEARCH) return run_beam(target, std::max(1, sb->p.beam_size));
         while (target ? !target->finished() : true) {
-            poll_passes(false);
+            if ((rc = poll_passes(false))) return rc;
             if (sc.n_armed < R && sc.ready.empty() && sc.passes.empty() && (rc = launch_passes())) return rc;  // nothing encoded, nothing in flight
             if ((rc = arm_rows())) return rc;
             // Decode yields to the encoder when rows run empty.  An encoder pass issued next to the decode steps only gets
@@ -1026,7 +1032,7 @@ struct Pump {
             // every SM partly occupied), so without this the rows settle at ~60 % occupancy; with it the pass runs alone
             // for ~100 ms exactly when windows are short, and the look-ahead slots keep that rare in steady state.
             if (sc.n_armed > 0 && R - sc.n_armed >= st->starve_rows && sc.ready.empty() && !sc.passes.empty() && sc.parked.empty()) {
-                poll_passes(true);
+                if ((rc = poll_passes(true))) return rc;
                 if ((rc = launch_passes())) return rc;
                 if ((rc = arm_rows())) return rc;
             }
@@ -1037,7 +1043,7 @@ struct Pump {
                 }
                 if (!sc.ready.empty()) continue;  // arm_rows was held back by the ladder that just ran
                 if (!sc.passes.empty()) {
-                    poll_passes(true);
+                    if ((rc = poll_passes(true))) return rc;
                     continue;
                 }
                 if (!sc.need_window.empty()) {
