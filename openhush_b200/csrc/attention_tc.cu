@@ -3,25 +3,31 @@
 // accumulation, reached from /root/reference/src/engine/whisper.rs:266).  The 1500 x 1500 score matrix never leaves
 // the SM: S lives in TMEM, P goes through shared memory as the next MMA's operand, O partials come back through TMEM.
 //
-// One CTA = 128 query rows of one (window, head); 24 key blocks of 64; two CTAs per SM (96 KB of shared memory and
-// 256 TMEM columns each) so that one CTA's softmax hides the other's barrier and TMEM latencies.  192 threads:
+// One CTA = 128 query rows of one (window, head); 24 key blocks of 64; two CTAs per SM (100 KB of shared memory and
+// 256 TMEM columns each) so that one CTA's softmax hides the other's barrier and TMEM latencies.  320 threads:
 //   warp 0      TMA producer: Q tile once, then K_j and V_j boxes ([64 keys][64], 128-byte swizzle) through two rings,
 //               all straight out of the packed qkv activation [B*T][3d] (3-D tensor maps, rows past T zero-filled)
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer:
 //                 S_j = Q K_j^T      M128 N64 K64   (A, B K-major)            -> TMEM columns [64*(j%2), +64)
-//                 O_j = P_j V_j      M128 N64 K64   (A = P K-major, B = V MN-major: V is used as stored, no transpose)
+//                 O_j = P_j V_j      M128 N64 K64   (A = P from tensor memory (or K-major shared memory), B = V MN-major:
+//                                                    V is used as stored, no transpose)
 //                                                                              -> TMEM columns [128 + 64*(j%2), +64)
-//   warps 2..5  softmax, one query row per thread (TMEM lane = row): S_j row into registers, row max,
-//               p = exp2(s*c - m) with the running max / running sum of the online form, P_j rounded to the
-//               activation type and written to shared memory in the swizzled K-major operand layout; the O_j partials
-//               are folded into f32 registers one block later (o = (o + O_{j-1}) * exp2(m_{j-1} - m_j)), so the
-//               accumulator in TMEM is never rescaled and the MMAs of block j+1 overlap the softmax of block j.
+//   warps 2..9  softmax, TWO threads per query row (TMEM lane = row; warps w and w+4 share a lane group, each takes 32 of
+//               the block's 64 keys and 32 of the 64 output channels): half an S_j row into registers, row max (the two
+//               halves meet through shared memory and a 64-thread named barrier), p = exp2(s*c - m) with the running
+//               max / running sum of the online form, P_j rounded to the activation type and written to shared memory in
+//               the swizzled K-major operand layout; the O_j partials are folded into f32 registers one block later
+//               (o = (o + O_{j-1}) * exp2(m_{j-1} - m_j)), so the accumulator in TMEM is never rescaled and the MMAs of
+//               block j+1 overlap the softmax of block j.  Eight softmax warps per CTA (sixteen per SM) instead of four:
+//               the kernel is bound by the latency of the per-row exp / TMEM chains, not by their throughput.
 // Every mbarrier wait is bounded (trap after ~4 s) so a protocol bug cannot hang the GPU.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "../../include/oh_whisper.h"
@@ -35,19 +41,23 @@ namespace {
 using namespace tcx;
 
 constexpr int AT_BQ = 128, AT_BK = 64, AT_HD = 64;
-constexpr int AT_THREADS = 192;
+constexpr int AT_THREADS = 320;                        // TMA warp, MMA warp, 8 softmax warps
+constexpr int AT_SOFTMAX_THREADS = 256;
 constexpr int AT_SK = 3, AT_SV = 3;                    // K / V ring depths
 constexpr int AT_QBYTES = AT_BQ * AT_HD * 2;           // 16 KB
 constexpr int AT_TILE = AT_BK * AT_HD * 2;             // 8 KB: K_j box, V_j box
 constexpr int AT_PBYTES = AT_BQ * AT_BK * 2;           // 16 KB: P_j as one [128][64] K-major block
 constexpr int AT_OFF_Q = 0, AT_OFF_K = AT_QBYTES, AT_OFF_V = AT_OFF_K + AT_SK * AT_TILE, AT_OFF_P = AT_OFF_V + AT_SV * AT_TILE;
-constexpr int AT_OFF_BAR = AT_OFF_P + 2 * AT_PBYTES;
+constexpr int AT_OFF_MAX = AT_OFF_P + 2 * AT_PBYTES;   // row maxima of the two key halves, double-buffered: [2][2][128] f32
+constexpr int AT_OFF_SUM = AT_OFF_MAX + 2 * 2 * AT_BQ * 4;  // row sums of the two halves at the end: [2][128] f32
+constexpr int AT_OFF_BAR = AT_OFF_SUM + 2 * AT_BQ * 4;
 constexpr int AT_SMEM_BYTES = AT_OFF_BAR + 256 + 1024 /*align slack*/;
 constexpr int AT_TMEM_COLS = 256;
 static_assert(AT_BK == 64 && AT_HD == 64, "operand descriptors below assume one 128-byte swizzle atom per row");
 
 struct AtParams {
     int T, d, n_kb;
+    int p_tmem;  // 1: P_j goes to the MMA through tensor memory (over the S_j columns it was computed from) instead of shared memory
     uint32_t idesc_qk, idesc_pv;
     void* out;
 };
@@ -109,9 +119,9 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __g
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(s_full(i), 1);
-            mbar_init(p_ready(i), 128);
+            mbar_init(p_ready(i), AT_SOFTMAX_THREADS);
             mbar_init(o_full(i), 1);
-            mbar_init(o_empty(i), 128);
+            mbar_init(o_empty(i), AT_SOFTMAX_THREADS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -186,9 +196,11 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __g
                 const uint32_t tO = tmem_base + (uint32_t)(2 * AT_BK + i * AT_HD);
 #pragma unroll
                 for (int ks = 0; ks < AT_BK / 16; ++ks) {
-                    // A: P ([128][64] K-major), 32 B per k-step inside the swizzle atom
+                    // A: P ([128][64] K-major): in shared memory 32 B per k-step inside the swizzle atom; in tensor memory the 16
+                    //    keys of a k-step are 8 packed columns of the S buffer P_j replaced
                     // B: V is MN-major ([key][64 channels], one 128-byte swizzle row per key): 16 keys = 2048 B per k-step
-                    tc_mma_f16(tO, dp + (uint64_t)(ks * 2), dv + (uint64_t)(ks * (2048 >> 4)), p.idesc_pv, ks != 0 ? 1u : 0u);
+                    if (p.p_tmem) tc_mma_f16_ts(tO, tmem_base + (uint32_t)(i * AT_BK + ks * 8), dv + (uint64_t)(ks * (2048 >> 4)), p.idesc_pv, ks != 0 ? 1u : 0u);
+                    else tc_mma_f16(tO, dp + (uint64_t)(ks * 2), dv + (uint64_t)(ks * (2048 >> 4)), p.idesc_pv, ks != 0 ? 1u : 0u);
                 }
                 tc_commit(v_empty(sv));
                 tc_commit(o_full(i));
@@ -202,82 +214,89 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __g
         __syncwarp();
     } else {
         // ===================== softmax =====================
-        const int lane_grp = warp & 3;
-        const int row = lane_grp * 32 + lane;  // query row inside the tile = TMEM lane
+        const int lane_grp = warp & 3;            // TMEM lanes [32 * lane_grp, +32) are the ones this warp may read
+        const int half = (warp - 2) >> 2;         // which 32 keys of a block / which 32 output channels this thread owns
+        const int row = lane_grp * 32 + lane;     // query row inside the tile = TMEM lane
         const uint32_t lane_addr = (uint32_t)(lane_grp * 32) << 16;
+        const uint32_t pair_bar = 1u + (uint32_t)lane_grp;  // named barrier of the two warps that share these rows
         const float c = 0.125f * 1.44269504088896340736f;  // 1/sqrt(64) * log2(e): scores live in the exp2 domain
         float m_run = -1e30f, l_run = 0.0f;
-        float o[AT_HD];
+        float o[AT_HD / 2];
 #pragma unroll
-        for (int i = 0; i < AT_HD; ++i) o[i] = 0.0f;
+        for (int i = 0; i < AT_HD / 2; ++i) o[i] = 0.0f;
         uint8_t* Pgen = smem_gen + AT_OFF_P;
+        float* sm_max = reinterpret_cast<float*>(smem_gen + AT_OFF_MAX);
+        float* sm_sum = reinterpret_cast<float*>(smem_gen + AT_OFF_SUM);
+        const int c0 = half * 32;                 // first key (and first channel) of this thread's half
         for (int j = 0; j < n_kb; ++j) {
             const int i = j & 1;
             const uint32_t ph = (uint32_t)((j >> 1) & 1);
             const int valid = min(AT_BK, p.T - j * AT_BK);  // keys of this block that exist
             mbar_wait(s_full(i), ph);
             tc_fence_after();
-            const uint32_t tS = tmem_base + lane_addr + (uint32_t)(i * AT_BK);
-            uint32_t v0[32], v1[32];
-            tc_ld_32x32(tS, v0);
-            tc_ld_32x32(tS + 32, v1);
+            const uint32_t tS = tmem_base + lane_addr + (uint32_t)(i * AT_BK + c0);
+            uint32_t v[32];
+            tc_ld_32x32(tS, v);
             tc_wait_ld();
             float mx = -1e30f;
             if (valid == AT_BK) {
 #pragma unroll
-                for (int k = 0; k < 32; ++k) mx = fmaxf(mx, fmaxf(__uint_as_float(v0[k]), __uint_as_float(v1[k])));
+                for (int k = 0; k < 32; ++k) mx = fmaxf(mx, __uint_as_float(v[k]));
             } else {
 #pragma unroll
-                for (int k = 0; k < 32; ++k) {
-                    if (k < valid) mx = fmaxf(mx, __uint_as_float(v0[k]));
-                    if (32 + k < valid) mx = fmaxf(mx, __uint_as_float(v1[k]));
-                }
+                for (int k = 0; k < 32; ++k)
+                    if (c0 + k < valid) mx = fmaxf(mx, __uint_as_float(v[k]));
             }
+            // the two halves of the row agree on the block's maximum (double-buffered by block parity: a thread may be one
+            // block ahead of its partner, never two)
+            sm_max[(i * 2 + half) * AT_BQ + row] = mx;
+            asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+            mx = fmaxf(mx, sm_max[(i * 2 + (half ^ 1)) * AT_BQ + row]);
             const float m_new = fmaxf(m_run, mx * c);
             const float corr = ex2_approx(m_run - m_new);
             m_run = m_new;
-            // p, row sum, P_j (rounded to the activation type) into the swizzled K-major operand layout
+            // p, row sum, this half of P_j (rounded to the activation type) into the swizzled K-major operand layout
             float lsum = 0.0f;
             uint8_t* Prow = Pgen + i * AT_PBYTES + row * 128;
-            auto emit = [&](const uint32_t (&v)[32], int c0) {
-                uint32_t pk[16];
+            uint32_t pk[16];
 #pragma unroll
-                for (int k = 0; k < 32; k += 2) {
-                    float p0 = ex2_approx(fmaf(__uint_as_float(v[k]), c, -m_new));
-                    float p1 = ex2_approx(fmaf(__uint_as_float(v[k + 1]), c, -m_new));
-                    if (valid != AT_BK) {
-                        if (c0 + k >= valid) p0 = 0.0f;
-                        if (c0 + k + 1 >= valid) p1 = 0.0f;
-                    }
-                    lsum += p0 + p1;
-                    pk[k >> 1] = pack2<T>(p0, p1);
+            for (int k = 0; k < 32; k += 2) {
+                float p0 = ex2_approx(fmaf(__uint_as_float(v[k]), c, -m_new));
+                float p1 = ex2_approx(fmaf(__uint_as_float(v[k + 1]), c, -m_new));
+                if (valid != AT_BK) {
+                    if (c0 + k >= valid) p0 = 0.0f;
+                    if (c0 + k + 1 >= valid) p1 = 0.0f;
                 }
+                lsum += p0 + p1;
+                pk[k >> 1] = pack2<T>(p0, p1);
+            }
+            if (p.p_tmem) {
+                // both halves of the row hold their S values in registers (the pair barrier above came after the loads), so
+                // the first 32 columns of the S buffer can take the row's 64 packed P values: this thread's 32 keys = 16 columns
+                tc_st_32x16(tmem_base + lane_addr + (uint32_t)(i * AT_BK + half * 16), pk);
+                tc_wait_st();
+            } else {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int ch = (c0 >> 3) + q;  // 16-byte chunk (8 keys) inside the 128-byte row
                     *reinterpret_cast<uint4*>(Prow + ((ch ^ (row & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
                 }
-            };
-            emit(v0, 0);
-            emit(v1, 32);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // P_j (generic-proxy stores) -> visible to the MMA
+            }
             l_run = l_run * corr + lsum;
             tc_fence_before();
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // P_j (generic-proxy stores) -> visible to the MMA
             mbar_arrive(p_ready(i));
             // fold the previous block's partial output (same scale as o), then move both to the new maximum
             if (j >= 1) {
                 const int ip = (j - 1) & 1;
                 mbar_wait(o_full(ip), (uint32_t)(((j - 1) >> 1) & 1));
                 tc_fence_after();
-                const uint32_t tO = tmem_base + lane_addr + (uint32_t)(2 * AT_BK + ip * AT_HD);
+                const uint32_t tO = tmem_base + lane_addr + (uint32_t)(2 * AT_BK + ip * AT_HD + c0);
+                uint32_t w[32];
+                tc_ld_32x32(tO, w);
+                tc_wait_ld();
 #pragma unroll
-                for (int c0 = 0; c0 < AT_HD; c0 += 32) {
-                    uint32_t v[32];
-                    tc_ld_32x32(tO + c0, v);
-                    tc_wait_ld();
-#pragma unroll
-                    for (int k = 0; k < 32; ++k) o[c0 + k] = (o[c0 + k] + __uint_as_float(v[k])) * corr;
-                }
+                for (int k = 0; k < 32; ++k) o[k] = (o[k] + __uint_as_float(w[k])) * corr;
                 tc_fence_before();
                 mbar_arrive(o_empty(ip));
             }
@@ -286,28 +305,29 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __g
             const int ip = (n_kb - 1) & 1;
             mbar_wait(o_full(ip), (uint32_t)(((n_kb - 1) >> 1) & 1));
             tc_fence_after();
-            const uint32_t tO = tmem_base + lane_addr + (uint32_t)(2 * AT_BK + ip * AT_HD);
+            const uint32_t tO = tmem_base + lane_addr + (uint32_t)(2 * AT_BK + ip * AT_HD + c0);
+            uint32_t w[32];
+            tc_ld_32x32(tO, w);
+            tc_wait_ld();
 #pragma unroll
-            for (int c0 = 0; c0 < AT_HD; c0 += 32) {
-                uint32_t v[32];
-                tc_ld_32x32(tO + c0, v);
-                tc_wait_ld();
-#pragma unroll
-                for (int k = 0; k < 32; ++k) o[c0 + k] += __uint_as_float(v[k]);
-            }
+            for (int k = 0; k < 32; ++k) o[k] += __uint_as_float(w[k]);
         }
+        // the row's normaliser is the sum of the two halves' running sums (both carry the same running maximum)
+        sm_sum[half * AT_BQ + row] = l_run;
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        const float l_tot = l_run + sm_sum[(half ^ 1) * AT_BQ + row];
         const int t = q0 + row;
         if (t < p.T) {
-            const float inv = 1.0f / l_run;
-            T* orow = reinterpret_cast<T*>(p.out) + ((size_t)b * p.T + t) * p.d + h * AT_HD;
+            const float inv = 1.0f / l_tot;
+            T* orow = reinterpret_cast<T*>(p.out) + ((size_t)b * p.T + t) * p.d + h * AT_HD + c0;
 #pragma unroll
-            for (int c0 = 0; c0 < AT_HD; c0 += 8) {
+            for (int k = 0; k < 32; k += 8) {
                 uint4 u;
-                u.x = pack2<T>(o[c0] * inv, o[c0 + 1] * inv);
-                u.y = pack2<T>(o[c0 + 2] * inv, o[c0 + 3] * inv);
-                u.z = pack2<T>(o[c0 + 4] * inv, o[c0 + 5] * inv);
-                u.w = pack2<T>(o[c0 + 6] * inv, o[c0 + 7] * inv);
-                *reinterpret_cast<uint4*>(orow + c0) = u;
+                u.x = pack2<T>(o[k] * inv, o[k + 1] * inv);
+                u.y = pack2<T>(o[k + 2] * inv, o[k + 3] * inv);
+                u.z = pack2<T>(o[k + 4] * inv, o[k + 5] * inv);
+                u.w = pack2<T>(o[k + 6] * inv, o[k + 7] * inv);
+                *reinterpret_cast<uint4*>(orow + k) = u;
             }
         }
     }
@@ -348,6 +368,13 @@ int launch_encoder_attention_tc(const void* qkv, void* out, int type, int B, int
     p.idesc_qk = base | ((uint32_t)(AT_BK >> 3) << 17);
     p.idesc_pv = base | ((uint32_t)(AT_HD >> 3) << 17) | (1u << 16);  // bit 16: B operand is MN-major
     p.out = out;
+    // P_j reaches the second MMA through tensor memory (A operand in TMEM), written over the S_j columns it came from: 6x fewer
+    // shared-memory wavefronts than the shared-memory route and 4 % faster on B200; OH_ATTN_P=smem selects the latter
+    static const int p_tmem = [] {
+        const char* e = getenv("OH_ATTN_P");
+        return (e && strcmp(e, "smem") == 0) ? 0 : 1;
+    }();
+    p.p_tmem = p_tmem;
     dim3 grid((Tn + AT_BQ - 1) / AT_BQ, d / AT_HD, B);
     ProfScope ps(PC_ATTN_ENC, 4.0 * B * (double)Tn * Tn * d, st);
     if (type == DT_F16) OH_CUDA_CHECK(launch_k(encoder_attention_tc_kernel<__half>, grid, AT_THREADS, AT_SMEM_BYTES, st, map_q, map_kv, p));
