@@ -58,6 +58,7 @@ static_assert(AT_BK == 64 && AT_HD == 64, "operand descriptors below assume one 
 struct AtParams {
     int T, d, n_kb;
     int p_tmem;  // 1: P_j goes to the MMA through tensor memory (over the S_j columns it was computed from) instead of shared memory
+    int o_lazy;  // 1: O accumulates in tensor memory over all key blocks; a row's accumulator is rescaled only when its maximum grows by > 2^8
     uint32_t idesc_qk, idesc_pv;
     void* out;
 };
@@ -80,7 +81,7 @@ __device__ __forceinline__ float ex2_approx(float x) {  // arguments are <= 0 he
     return y;
 }
 
-template <typename T>
+template <typename T, bool kLazy>
 __global__ void __launch_bounds__(AT_THREADS, 2)
 encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv, const AtParams p) {
     extern __shared__ uint8_t at_smem_raw[];
@@ -189,18 +190,20 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __g
                 const uint32_t ph = (uint32_t)((j >> 1) & 1);
                 mbar_wait(p_ready(i), ph);  // P_j is in shared memory, S buffer i has been read out
                 mbar_wait(v_full(sv), pv);
-                if (j >= 2) mbar_wait(o_empty(i), ph ^ 1);  // O_{j-2} has been folded into registers
+                if (j >= 2 && !kLazy) mbar_wait(o_empty(i), ph ^ 1);  // O_{j-2} has been folded into registers
                 tc_fence_after();
                 const uint64_t dp = make_smem_desc(smem_base + AT_OFF_P + i * AT_PBYTES);
                 const uint64_t dv = make_smem_desc(smem_base + AT_OFF_V + sv * AT_TILE);
-                const uint32_t tO = tmem_base + (uint32_t)(2 * AT_BK + i * AT_HD);
+                // lazy mode: one accumulator for the whole row of key blocks (block 0 overwrites, the others add)
+                const uint32_t tO = tmem_base + (uint32_t)(2 * AT_BK + (kLazy ? 0 : i * AT_HD));
+                const uint32_t acc0 = (kLazy && j > 0) ? 1u : 0u;
 #pragma unroll
                 for (int ks = 0; ks < AT_BK / 16; ++ks) {
                     // A: P ([128][64] K-major): in shared memory 32 B per k-step inside the swizzle atom; in tensor memory the 16
                     //    keys of a k-step are 8 packed columns of the S buffer P_j replaced
                     // B: V is MN-major ([key][64 channels], one 128-byte swizzle row per key): 16 keys = 2048 B per k-step
-                    if (p.p_tmem) tc_mma_f16_ts(tO, tmem_base + (uint32_t)(i * AT_BK + ks * 8), dv + (uint64_t)(ks * (2048 >> 4)), p.idesc_pv, ks != 0 ? 1u : 0u);
-                    else tc_mma_f16(tO, dp + (uint64_t)(ks * 2), dv + (uint64_t)(ks * (2048 >> 4)), p.idesc_pv, ks != 0 ? 1u : 0u);
+                    if (p.p_tmem) tc_mma_f16_ts(tO, tmem_base + (uint32_t)(i * AT_BK + ks * 8), dv + (uint64_t)(ks * (2048 >> 4)), p.idesc_pv, ks != 0 ? 1u : acc0);
+                    else tc_mma_f16(tO, dp + (uint64_t)(ks * 2), dv + (uint64_t)(ks * (2048 >> 4)), p.idesc_pv, ks != 0 ? 1u : acc0);
                 }
                 tc_commit(v_empty(sv));
                 tc_commit(o_full(i));
@@ -252,8 +255,35 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __g
             sm_max[(i * 2 + half) * AT_BQ + row] = mx;
             asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
             mx = fmaxf(mx, sm_max[(i * 2 + (half ^ 1)) * AT_BQ + row]);
-            const float m_new = fmaxf(m_run, mx * c);
-            const float corr = ex2_approx(m_run - m_new);
+            float m_new = fmaxf(m_run, mx * c);
+            float corr = ex2_approx(m_run - m_new);
+            if (kLazy) {
+                // The accumulator stays in tensor memory.  P_j is computed against the maximum the row's accumulator is scaled
+                // to (m_run); only when the row's true maximum has grown by more than 8 (p would exceed 2^8) is the accumulator
+                // pulled, rescaled and put back — rows are independent TMEM lanes, P_{j-1} V_{j-1} has completed (o_full) and
+                // P_j V_j is not issued before this thread arrives on p_ready, so nobody else touches these columns meanwhile.
+                // tcgen05.ld/st are warp-wide, so the warp rescales if any of its rows has to (the others multiply by one).  Its
+                // partner warp sees the same maxima and takes the same decision for its 32 channels.
+                bool grow = j > 0 && m_new > m_run + 8.0f;
+                if (j > 0 && !grow) {
+                    m_new = m_run;  // keep the scale
+                    corr = 1.0f;
+                }
+                if (j == 0) corr = 1.0f;  // nothing accumulated yet
+                if (__any_sync(0xffffffffu, grow)) {
+                    const int ip = (j - 1) & 1;
+                    mbar_wait(o_full(ip), (uint32_t)(((j - 1) >> 1) & 1));
+                    tc_fence_after();
+                    const uint32_t tOl = tmem_base + lane_addr + (uint32_t)(2 * AT_BK + c0);
+                    uint32_t w[32];
+                    tc_ld_32x32(tOl, w);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) w[k] = __float_as_uint(__uint_as_float(w[k]) * corr);
+                    tc_st_32x32(tOl, w);
+                    tc_wait_st();
+                }
+            }
             m_run = m_new;
             // p, row sum, this half of P_j (rounded to the activation type) into the swizzled K-major operand layout
             float lsum = 0.0f;
@@ -287,7 +317,7 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __g
             tc_fence_before();
             mbar_arrive(p_ready(i));
             // fold the previous block's partial output (same scale as o), then move both to the new maximum
-            if (j >= 1) {
+            if (j >= 1 && !kLazy) {
                 const int ip = (j - 1) & 1;
                 mbar_wait(o_full(ip), (uint32_t)(((j - 1) >> 1) & 1));
                 tc_fence_after();
@@ -305,7 +335,7 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __g
             const int ip = (n_kb - 1) & 1;
             mbar_wait(o_full(ip), (uint32_t)(((n_kb - 1) >> 1) & 1));
             tc_fence_after();
-            const uint32_t tO = tmem_base + lane_addr + (uint32_t)(2 * AT_BK + ip * AT_HD + c0);
+            const uint32_t tO = tmem_base + lane_addr + (uint32_t)(2 * AT_BK + (kLazy ? 0 : ip * AT_HD) + c0);
             uint32_t w[32];
             tc_ld_32x32(tO, w);
             tc_wait_ld();
@@ -347,8 +377,10 @@ PerDeviceInit g_at_init;
 bool encoder_attention_tc_available() {
     return g_at_init.ensure([] {
         return gemm_tc_available() &&
-               cudaFuncSetAttribute(encoder_attention_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES) == cudaSuccess &&
-               cudaFuncSetAttribute(encoder_attention_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES) == cudaSuccess;
+               cudaFuncSetAttribute(encoder_attention_tc_kernel<__half, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES) == cudaSuccess &&
+               cudaFuncSetAttribute(encoder_attention_tc_kernel<__nv_bfloat16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES) == cudaSuccess &&
+               cudaFuncSetAttribute(encoder_attention_tc_kernel<__half, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES) == cudaSuccess &&
+               cudaFuncSetAttribute(encoder_attention_tc_kernel<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES) == cudaSuccess;
     });
 }
 
@@ -375,24 +407,37 @@ int launch_encoder_attention_tc(const void* qkv, void* out, int type, int B, int
         return (e && strcmp(e, "smem") == 0) ? 0 : 1;
     }();
     p.p_tmem = p_tmem;
+    static const int o_lazy = [] {  // OH_ATTN_O=lazy: the accumulator stays in tensor memory (rescaled on demand); default: folded into registers per block
+        const char* e = getenv("OH_ATTN_O");
+        return (e && strcmp(e, "lazy") == 0) ? 1 : 0;
+    }();
+    p.o_lazy = o_lazy;
     dim3 grid((Tn + AT_BQ - 1) / AT_BQ, d / AT_HD, B);
     ProfScope ps(PC_ATTN_ENC, 4.0 * B * (double)Tn * Tn * d, st);
-    if (type == DT_F16) OH_CUDA_CHECK(launch_k(encoder_attention_tc_kernel<__half>, grid, AT_THREADS, AT_SMEM_BYTES, st, map_q, map_kv, p));
-    else OH_CUDA_CHECK(launch_k(encoder_attention_tc_kernel<__nv_bfloat16>, grid, AT_THREADS, AT_SMEM_BYTES, st, map_q, map_kv, p));
+    if (p.o_lazy) {
+        if (type == DT_F16) OH_CUDA_CHECK(launch_k(encoder_attention_tc_kernel<__half, true>, grid, AT_THREADS, AT_SMEM_BYTES, st, map_q, map_kv, p));
+        else OH_CUDA_CHECK(launch_k(encoder_attention_tc_kernel<__nv_bfloat16, true>, grid, AT_THREADS, AT_SMEM_BYTES, st, map_q, map_kv, p));
+    } else {
+        if (type == DT_F16) OH_CUDA_CHECK(launch_k(encoder_attention_tc_kernel<__half, false>, grid, AT_THREADS, AT_SMEM_BYTES, st, map_q, map_kv, p));
+        else OH_CUDA_CHECK(launch_k(encoder_attention_tc_kernel<__nv_bfloat16, false>, grid, AT_THREADS, AT_SMEM_BYTES, st, map_q, map_kv, p));
+    }
     OH_COUNT_LAUNCH();
     return OH_OK;
 }
 
-// start-up check against the mma.sync flash kernel: T with a ragged last block, two heads, two windows
+// start-up check against the mma.sync flash kernel: T with a ragged last block, two heads, two windows; the keys grow with
+// time so that row maxima rise by far more than 2^8 from block to block (the on-demand rescale of the lazy accumulator runs)
 int encoder_attention_tc_selftest(cudaStream_t st, float* max_rel_err) {
     if (!encoder_attention_tc_available()) return OH_ERR_UNSUPPORTED;
     const int B = 2, Tn = 300, d = 128;
     const size_t n_qkv = (size_t)B * Tn * 3 * d, n_out = (size_t)B * Tn * d;
     std::vector<__half> h(n_qkv);
     uint32_t s = 99u;
-    for (auto& v : h) {
+    for (size_t i = 0; i < n_qkv; ++i) {
         s = s * 1664525u + 1013904223u;
-        v = __float2half_rn((((s >> 8) & 0xFFFF) / 32768.0f - 1.0f) * 2.0f);
+        const int t = (int)((i / (size_t)(3 * d)) % Tn), part = (int)((i / d) % 3);
+        const float gain = part == 1 ? 0.25f + (float)t / 40.0f : 2.0f;
+        h[i] = __float2half_rn((((s >> 8) & 0xFFFF) / 32768.0f - 1.0f) * gain);
     }
     void *dq = nullptr, *d0 = nullptr, *d1 = nullptr;
     OH_CUDA_CHECK(cudaMalloc(&dq, n_qkv * 2));
