@@ -284,9 +284,13 @@ __device__ __forceinline__ void raw8_to_f32<__nv_bfloat16>(const uint4& u, float
 }
 
 // ------------------------------------------------- K7+K8a (16-bit modes): self attention, one warp per (row, head)
-// The self cache is short (<= 448 keys, typically ~100) and L2-resident, so this kernel is latency-bound: one warp
-// per (row, head) with no block-level barrier, 4 groups of 8 lanes x 4 keys per sweep (8 independent 16-byte loads
-// per lane), per-group online softmax merged with shuffles at the end.  The step's k,v are appended first.
+// The self cache is short per (row, head) (<= 448 keys, typically ~100: 12.8 KB of K and of V, contiguous) but not
+// L2-resident at 256 rows (131 MB per layer at position 100, re-read one step = 4 GB of other traffic later), so the
+// kernel is a short HBM stream bound by latency chains: one warp per (row, head) with no block-level barrier, 4 groups
+// of 8 lanes x 4 keys per sweep (8 independent 16-byte loads per lane, the next sweep requested before this one is
+// consumed), per-group online softmax merged with shuffles at the end.  The step's k,v are appended first.
+// Measured at 256 rows, position 100: 34 us per launch for 136 MB = 4.0 TB/s (0.6 of the measured HBM peak); what is
+// left is the prologue's dependent loads (row state -> addresses -> first keys) and 2.2 waves of 16 warps per SM.
 template <typename T>
 __global__ void __launch_bounds__(128) self_attention_decode_warp_kernel(const T* __restrict__ qkv, T* kcache, T* vcache, DecodeSeqState s, int d,
                                                                          int n_ctx, int rows, T* __restrict__ out) {
