@@ -291,6 +291,8 @@ __device__ __forceinline__ void raw8_to_f32<__nv_bfloat16>(const uint4& u, float
 // consumed), per-group online softmax merged with shuffles at the end.  The step's k,v are appended first.
 // Measured at 256 rows, position 100: 34 us per launch for 136 MB = 4.0 TB/s (0.6 of the measured HBM peak); what is
 // left is the prologue's dependent loads (row state -> addresses -> first keys) and 2.2 waves of 16 warps per SM.
+// Holding the register allocation to 5 or 6 CTAs per SM (96 / 80 registers instead of 118) was measured and does not pay:
+// 1.02 ms per 256-row step at 4 CTAs, 1.11 at 5, 1.59 at 6 (spills).
 template <typename T>
 __global__ void __launch_bounds__(128) self_attention_decode_warp_kernel(const T* __restrict__ qkv, T* kcache, T* vcache, DecodeSeqState s, int d,
                                                                          int n_ctx, int rows, T* __restrict__ out) {

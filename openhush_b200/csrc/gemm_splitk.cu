@@ -7,12 +7,15 @@
 //   warp 0      TMA producer: k-blocks (64 wide) of this CTA's K-range, A box(es) [128][64] + W box [64][64], 4-stage ring
 //               (M > 128: two A boxes per stage share the W box, 2-stage ring — 256 rows cost one pass over W)
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (M128 N64 K16, f32 accumulator in TMEM)
-//   warps 2..5  tcgen05.ld the 128 x 64 partial tile into shared memory (aliases the drained ring)
+//   warps 2..9  tcgen05.ld the 128 x 64 partial tile(s) into shared memory (aliases the drained ring); two warps per TMEM
+//               lane group, 32 columns each
+//   all warps   request the residual values of the elements they will write (they do not depend on the partial sums)
 //   cluster.sync
 //   all warps   CTA r sums rows [r*128/CS, +128/CS) of the CS partial tiles in rank order (deterministic; no partial
-//               sum touches HBM) into its own copy, arrives on the cluster barrier, then runs the epilogue from local
-//               shared memory (bias / GELU / residual / type conversion, 16-byte coalesced stores) and only then
-//               waits on the barrier, so the barrier latency hides under the stores
+//               sum touches HBM) into its own copy — eight 16-byte loads in flight per thread, remote shared memory
+//               answers in ~215 cycles — arrives on the cluster barrier, then runs the epilogue from local shared memory
+//               (bias / GELU / residual / type conversion, 16-byte coalesced stores) and only then waits on the barrier,
+//               so the barrier latency hides under the stores
 //
 // The K-split depends on (N, K) only, never on M, and tensor-core rows are independent of each other, so a row's
 // result does not depend on which other rows share the batch.
@@ -41,7 +44,8 @@ namespace {
 using namespace tcx;
 
 constexpr int SPK_M = 128, SPK_N = 64, SPK_K = 64, SPK_UMMA_K = 16;
-constexpr int SPK_THREADS = 192;
+constexpr int SPK_THREADS = 320;  // producer warp, MMA warp, 8 warps that drain TMEM; all ten run the reduction and the epilogue
+constexpr int SPK_MAX_IT = 7;     // float4 items per thread in the epilogue for which the residual is prefetched (256 rows, CS >= 2)
 constexpr int SPK_A_BYTES = SPK_M * SPK_K * 2, SPK_B_BYTES = SPK_N * SPK_K * 2;
 constexpr int SPK_PS = SPK_N + 4;  // row stride (floats) of the partial tile: 16-byte aligned, spreads rows over banks
 // MT = 128-row tiles of X per CTA (1 for M <= 128, 2 for M <= 256): both tiles share every W box, so 256 rows cost one
@@ -67,6 +71,42 @@ struct SpkParams {
     int gelu, round_type;
     const uint16_t* lut;
 };
+
+// sums, for the rows this CTA owns, the CS partial tiles of the cluster in rank order; 8 / CS items per batch so that a
+// thread has eight 16-byte (mostly remote) loads in flight before the first add
+template <int CS>
+__device__ __forceinline__ void spk_reduce_rows(cg::cluster_group& cluster, float* Ps, int crank, int rows_per, int n_items, int m_lim, int n_blk, int N) {
+    constexpr int PER = 8 / CS;
+    const float* remote[CS];
+#pragma unroll
+    for (int c = 0; c < CS; ++c) remote[c] = cluster.map_shared_rank(Ps, c);
+    for (int i0 = threadIdx.x; i0 < n_items; i0 += SPK_THREADS * PER) {
+        float4 part[PER][CS];
+        bool ok[PER];
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            const int idx = i0 + j * SPK_THREADS;
+            const int rl = crank * rows_per + idx / (SPK_N / 4), c4 = (idx % (SPK_N / 4)) * 4;
+            ok[j] = idx < n_items && rl < m_lim && n_blk * SPK_N + c4 < N;
+            if (ok[j]) {
+#pragma unroll
+                for (int c = 0; c < CS; ++c) part[j][c] = *reinterpret_cast<const float4*>(remote[c] + (size_t)rl * SPK_PS + c4);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            if (!ok[j]) continue;
+            const int idx = i0 + j * SPK_THREADS;
+            const int rl = crank * rows_per + idx / (SPK_N / 4), c4 = (idx % (SPK_N / 4)) * 4;
+            float4 f = part[j][0];
+#pragma unroll
+            for (int c = 1; c < CS; ++c) {
+                f.x += part[j][c].x; f.y += part[j][c].y; f.z += part[j][c].z; f.w += part[j][c].w;
+            }
+            *reinterpret_cast<float4*>(Ps + (size_t)rl * SPK_PS + c4) = f;  // the same thread reads it back in phase 2
+        }
+    }
+}
 
 template <int MT>
 __global__ void __launch_bounds__(SPK_THREADS, 2)
@@ -173,8 +213,9 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         }
         __syncwarp();
     } else {
-        // partial tile TMEM -> shared memory; thread = one accumulator row
+        // partial tile TMEM -> shared memory; thread = one accumulator row, one half (32 columns) of the tile
         const int lane_grp = warp & 3;  // TMEM lanes [32*lane_grp, +32) are the only ones this warp may read
+        const int c0 = ((warp - 2) >> 2) * 32;
         const int row = lane_grp * 32 + lane;
         if (n_kb > 0) {
             mbar_wait(tfull_bar, 0);
@@ -184,60 +225,64 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         for (int t = 0; t < MT; ++t) {
             float* prow = Ps + (size_t)(t * SPK_M + row) * SPK_PS;
             if (n_kb > 0) {
+                uint32_t v[32];
+                tc_ld_32x32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(t * SPK_N + c0), v);
+                tc_wait_ld();
 #pragma unroll
-                for (int c0 = 0; c0 < SPK_N; c0 += 32) {
-                    uint32_t v[32];
-                    tc_ld_32x32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(t * SPK_N + c0), v);
-                    tc_wait_ld();
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4*>(prow + c0 + j) =
-                            make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-                }
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(prow + c0 + j) =
+                        make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
             } else {  // K-range empty (more ranks than k-blocks): contributes zeros
 #pragma unroll
-                for (int j = 0; j < SPK_N; j += 4) *reinterpret_cast<float4*>(prow + j) = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(prow + c0 + j) = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
     }
     tc_fence_before();
     pdl_wait();  // every thread orders itself after the preceding kernel before it reads the residual / writes C
     pdl_launch_dependents();
+
+    // this CTA's share of the output tile: rows [crank * rows_per, +rows_per), as float4 items
+    const int rows_per = SPK_ROWS / cs;
+    const int n_items = rows_per * (SPK_N / 4);
+    const int m_lim = min(p.M - m_blk * SPK_ROWS, SPK_ROWS);
+    // The residual does not depend on the partial sums: its loads go out before the cluster barrier and land while the
+    // partial tiles are being summed (each output element is read and written by the same thread, so an in-place
+    // residual update is not disturbed).
+    float4 rpre[SPK_MAX_IT];
+    const bool pre_ok = p.R != nullptr && n_items <= SPK_MAX_IT * SPK_THREADS;
+    if (pre_ok) {
+#pragma unroll
+        for (int it = 0; it < SPK_MAX_IT; ++it) {
+            const int idx = (int)threadIdx.x + it * SPK_THREADS;
+            const int rl = crank * rows_per + idx / (SPK_N / 4), n = n_blk * SPK_N + (idx % (SPK_N / 4)) * 4;
+            if (idx < n_items && rl < m_lim && n + 4 <= p.N)
+                rpre[it] = *reinterpret_cast<const float4*>(p.R + (size_t)(m_blk * SPK_ROWS + rl) * p.ldr + n);
+        }
+    }
     cluster.sync();  // every partial tile is complete and visible cluster-wide
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)SPK_TMEM_COLS) : "memory");
     }
 
-    // ---- fixed-order reduction of this CTA's rows across the cluster + epilogue
-    const int rows_per = SPK_ROWS / cs;
-    const float* remote[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) remote[c] = cluster.map_shared_rank(Ps, c < cs ? c : 0);
-    const int m_lim = min(p.M - m_blk * SPK_ROWS, SPK_ROWS);
-    // phase 1: sum the CS partials of this CTA's rows (rank order) and park the sums in its own copy of those rows —
-    // peers only ever read the rows THEY own, so the in-place update races with nobody
-    for (int idx = threadIdx.x; idx < rows_per * (SPK_N / 4); idx += SPK_THREADS) {
-        const int rl = crank * rows_per + idx / (SPK_N / 4), c4 = (idx % (SPK_N / 4)) * 4;
-        if (rl >= m_lim || n_blk * SPK_N + c4 >= p.N) continue;
-        float4 part[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-            if (c < cs) part[c] = *reinterpret_cast<const float4*>(remote[c] + (size_t)rl * SPK_PS + c4);
-        float4 f = part[0];
-#pragma unroll
-        for (int c = 1; c < 8; ++c)
-            if (c < cs) {
-                f.x += part[c].x; f.y += part[c].y; f.z += part[c].z; f.w += part[c].w;
-            }
-        *reinterpret_cast<float4*>(Ps + (size_t)rl * SPK_PS + c4) = f;  // same thread reads it back in phase 2
+    // ---- phase 1: sum the CS partials of this CTA's rows in rank order (deterministic) and park the sums in its own copy
+    // of those rows — peers only ever read the rows THEY own, so the in-place update races with nobody.  Eight 16-byte
+    // loads (8 / CS items x CS ranks) are in flight per thread before the first add: remote shared memory answers in
+    // ~215 cycles, and one item at a time would pay that once per item.
+    switch (cs) {
+        case 8: spk_reduce_rows<8>(cluster, Ps, crank, rows_per, n_items, m_lim, n_blk, p.N); break;
+        case 4: spk_reduce_rows<4>(cluster, Ps, crank, rows_per, n_items, m_lim, n_blk, p.N); break;
+        case 2: spk_reduce_rows<2>(cluster, Ps, crank, rows_per, n_items, m_lim, n_blk, p.N); break;
+        default: break;  // one rank: the partial tile is the sum
     }
     cluster.barrier_arrive();  // this CTA no longer reads remote shared memory; the matching wait is the last statement
-    // phase 2: epilogue from local shared memory (overlaps the cluster barrier)
-    for (int idx = threadIdx.x; idx < rows_per * (SPK_N / 4); idx += SPK_THREADS) {
+
+    // ---- phase 2: epilogue from local shared memory (overlaps the cluster barrier)
+    auto epilogue_item = [&](int idx, bool have_r, const float4& rr_pre) {
         const int rl = crank * rows_per + idx / (SPK_N / 4), c4 = (idx % (SPK_N / 4)) * 4;
         const int n = n_blk * SPK_N + c4;
-        if (rl >= m_lim || n >= p.N) continue;
+        if (rl >= m_lim || n >= p.N) return;
         const float4 f4 = *reinterpret_cast<const float4*>(Ps + (size_t)rl * SPK_PS + c4);
         float f[4] = {f4.x, f4.y, f4.z, f4.w};
         const int r = m_blk * SPK_ROWS + rl;
@@ -252,7 +297,7 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 for (int j = 0; j < 4; ++j) f[j] = epi_gelu(f[j], p.gelu, p.round_type, p.lut);
             }
             if (p.R) {
-                const float4 rr = *reinterpret_cast<const float4*>(p.R + (size_t)r * p.ldr + n);
+                const float4 rr = have_r ? rr_pre : *reinterpret_cast<const float4*>(p.R + (size_t)r * p.ldr + n);
                 f[0] += rr.x; f[1] += rr.y; f[2] += rr.z; f[3] += rr.w;
             }
             if (p.c_type == DT_F32) {
@@ -275,6 +320,16 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 else reinterpret_cast<__nv_bfloat16*>(p.C)[(size_t)r * p.ldc + n + j] = __float2bfloat16_rn(v);
             }
         }
+    };
+    if (pre_ok) {
+#pragma unroll
+        for (int it = 0; it < SPK_MAX_IT; ++it) {
+            const int idx = (int)threadIdx.x + it * SPK_THREADS;
+            if (idx < n_items) epilogue_item(idx, true, rpre[it]);
+        }
+    } else {
+        const float4 none = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int idx = threadIdx.x; idx < n_items; idx += SPK_THREADS) epilogue_item(idx, false, none);
     }
     cluster.barrier_wait();  // nobody leaves while a peer may still read its partial tile
 }
