@@ -220,6 +220,34 @@ OH_API int oh_load_pcm_16k(oh_context* ctx, oh_state* state, const void* pcm, in
 OH_API int oh_load_pcm_16k_device(oh_context* ctx, oh_state* state, const void* d_pcm, int format, int bits, int channels, int sample_rate,
                                   long long n_frames, float* d_out, long long cap, long long* out_n);
 
+/* ---- optional level processing of 16 kHz clips on the device: the worker's hook between capture and
+ * WhisperEngine::transcribe, src/queue/worker.rs:196-240 (preprocess_audio), in its order: AudioBuffer::normalize_rms
+ * (src/input/audio.rs:108-122), ::compress (:139-198), ::limit (:200-239).  Field defaults are the reference's
+ * (src/config.rs:1129-1159, 1239-1269); `preprocessing` itself is off by default there (config.rs:984), so nothing calls this
+ * unless the configuration asks for it.  RNNoise denoising (worker.rs:200-206) is a third-party model and not provided. */
+typedef struct oh_preprocess_params {
+    int normalize;          /* NormalizationConfig.enabled */
+    float target_db;        /* -18 */
+    int compress;           /* CompressionConfig.enabled */
+    float threshold_db;     /* -24 */
+    float ratio;            /* 4 */
+    float attack_ms;        /* 5 */
+    float release_ms;       /* 50 */
+    float makeup_gain_db;   /* 6 */
+    int limit;              /* LimiterConfig.enabled */
+    float ceiling_db;       /* -1 */
+    float limiter_release_ms; /* 50 */
+} oh_preprocess_params;
+OH_API oh_preprocess_params oh_preprocess_default_params(void);
+/* `batch` clips of host PCM (f32, 16 kHz), processed in place; rms_db (may be NULL) receives [batch][2] = RMS level in dB
+ * before and after (-inf for a silent or empty clip, as AudioBuffer::rms_db) */
+OH_API int oh_preprocess_pcm(oh_context* ctx, oh_state* state, float* const* pcm, const int* n_samples, int batch,
+                             const oh_preprocess_params* params, float* rms_db);
+/* same on device memory: d_pcm is one [batch][stride] array (the layout oh_full_batch_device / oh_stream_submit take), processed in
+ * place on the state's stream; n_samples and rms_db are host arrays */
+OH_API int oh_preprocess_pcm_device(oh_context* ctx, oh_state* state, float* d_pcm, long long stride, const int* n_samples, int batch,
+                                    const oh_preprocess_params* params, float* rms_db);
+
 /* RMS level in dB full scale of every `chunk`-sample block of a 16 kHz clip (host in, host out), one launch for the whole
  * clip: the per-chunk feature of the stand-in VAD engine behind the reference's VadEngine trait (src/vad/mod.rs:34-55; the
  * reference's own engine, Silero, is an ONNX model whose weights are not in its tree).  SURVEY.md section 8f N3. */

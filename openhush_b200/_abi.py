@@ -28,6 +28,13 @@ class Timings(C.Structure):
                 ("n_prompt_steps", C.c_longlong), ("n_row_steps", C.c_longlong), ("n_armed_row_steps", C.c_longlong)]
 
 
+class PreprocessParams(C.Structure):
+    _fields_ = [("normalize", C.c_int), ("target_db", C.c_float),
+                ("compress", C.c_int), ("threshold_db", C.c_float), ("ratio", C.c_float), ("attack_ms", C.c_float),
+                ("release_ms", C.c_float), ("makeup_gain_db", C.c_float),
+                ("limit", C.c_int), ("ceiling_db", C.c_float), ("limiter_release_ms", C.c_float)]
+
+
 class KernelStat(C.Structure):
     _fields_ = [("name", C.c_char * 32), ("launches", C.c_int), ("total_ms", C.c_float), ("work", C.c_double)]
 
@@ -58,3 +65,9 @@ def default_full_params(strategy: int = SAMPLING_GREEDY) -> FullParams:
     p.beam_patience = -1.0
     p.language = b"en"
     return p
+
+
+def default_preprocess_params() -> PreprocessParams:
+    """The reference's NormalizationConfig / CompressionConfig / LimiterConfig defaults (/root/reference/src/config.rs:
+    1129-1159 values, 1239-1269 `enabled: true` once `preprocessing` is on); oh_preprocess_default_params must agree."""
+    return PreprocessParams(1, -18.0, 1, -24.0, 4.0, 5.0, 50.0, 6.0, 1, -1.0, 50.0)

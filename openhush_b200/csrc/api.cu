@@ -425,6 +425,69 @@ OH_API int oh_chunk_rms_db(oh_context* ctx, oh_state* st, const float* pcm, long
     return OH_OK;
 }
 
+// ---- optional level processing (preprocess.cu)
+OH_API oh_preprocess_params oh_preprocess_default_params(void) {
+    oh_preprocess_params p;
+    p.normalize = 1; p.target_db = -18.0f;
+    p.compress = 1; p.threshold_db = -24.0f; p.ratio = 4.0f; p.attack_ms = 5.0f; p.release_ms = 50.0f; p.makeup_gain_db = 6.0f;
+    p.limit = 1; p.ceiling_db = -1.0f; p.limiter_release_ms = 50.0f;
+    return p;
+}
+
+namespace {
+// n (int) | gain (float) | rms (2 floats) per clip, one upload and one read-back per call
+int run_levels(oh_state* st, float* d_pcm, long long stride, const int* n_samples, int batch, const oh_preprocess_params& p, float* rms_db) {
+    int max_n = 0;
+    for (int i = 0; i < batch; ++i) {
+        if (n_samples[i] < 0 || n_samples[i] > stride) return OH_ERR_INVALID;
+        max_n = std::max(max_n, n_samples[i]);
+    }
+    if (p.compress && (!(p.attack_ms > 0.0f) || !(p.release_ms > 0.0f))) return OH_ERR_INVALID;
+    if (p.limit && !(p.limiter_release_ms > 0.0f)) return OH_ERR_INVALID;
+    int rc;
+    if ((rc = ensure(st->level_aux, (size_t)batch * 16))) return rc;
+    if ((rc = ensure(st->level_env, (size_t)batch * stride * 4))) return rc;
+    int* d_n = (int*)st->level_aux.p;
+    float* d_gain = (float*)st->level_aux.p + batch;
+    float* d_rms = (float*)st->level_aux.p + 2 * batch;
+    OH_CUDA_CHECK(cudaMemcpyAsync(d_n, n_samples, (size_t)batch * 4, cudaMemcpyHostToDevice, st->stream));
+    if ((rc = preprocess_levels_device(d_pcm, stride, d_n, batch, max_n, p, (float*)st->level_env.p, d_gain, d_rms, st->stream))) return rc;
+    if (rms_db) OH_CUDA_CHECK(cudaMemcpyAsync(rms_db, d_rms, (size_t)batch * 8, cudaMemcpyDeviceToHost, st->stream));
+    OH_CUDA_CHECK(cudaStreamSynchronize(st->stream));  // n_samples / rms_db are the caller's host arrays
+    return OH_OK;
+}
+}  // namespace
+
+OH_API int oh_preprocess_pcm_device(oh_context* ctx, oh_state* st, float* d_pcm, long long stride, const int* n_samples, int batch,
+                                    const oh_preprocess_params* params, float* rms_db) {
+    if (!ctx || !st || st->ctx != ctx || !d_pcm || !n_samples || !params || batch < 0 || stride < 0) return OH_ERR_INVALID;
+    if (select_device(ctx)) return OH_ERR_CUDA;
+    if (batch == 0) return OH_OK;
+    return run_levels(st, d_pcm, stride, n_samples, batch, *params, rms_db);
+}
+
+OH_API int oh_preprocess_pcm(oh_context* ctx, oh_state* st, float* const* pcm, const int* n_samples, int batch, const oh_preprocess_params* params,
+                             float* rms_db) {
+    if (!ctx || !st || st->ctx != ctx || !pcm || !n_samples || !params || batch < 0) return OH_ERR_INVALID;
+    if (select_device(ctx)) return OH_ERR_CUDA;
+    if (batch == 0) return OH_OK;
+    long long stride = 1;
+    for (int i = 0; i < batch; ++i) {
+        if (n_samples[i] < 0 || (n_samples[i] > 0 && !pcm[i])) return OH_ERR_INVALID;
+        stride = std::max<long long>(stride, n_samples[i]);
+    }
+    int rc;
+    if ((rc = ensure(st->level_pcm, (size_t)batch * stride * 4))) return rc;
+    float* d = (float*)st->level_pcm.p;
+    for (int i = 0; i < batch; ++i)
+        if (n_samples[i] > 0) OH_CUDA_CHECK(cudaMemcpyAsync(d + (size_t)i * stride, pcm[i], (size_t)n_samples[i] * 4, cudaMemcpyHostToDevice, st->stream));
+    if ((rc = run_levels(st, d, stride, n_samples, batch, *params, rms_db))) return rc;
+    for (int i = 0; i < batch; ++i)
+        if (n_samples[i] > 0) OH_CUDA_CHECK(cudaMemcpyAsync(pcm[i], d + (size_t)i * stride, (size_t)n_samples[i] * 4, cudaMemcpyDeviceToHost, st->stream));
+    OH_CUDA_CHECK(cudaStreamSynchronize(st->stream));
+    return OH_OK;
+}
+
 // ---- stage entry points
 OH_API int oh_pcm_to_mel_batch(oh_context* ctx, oh_state* st, const float* const* samples, const int* n_samples, int batch, float* const* out_mel,
                                int* out_n_len) {

@@ -243,7 +243,7 @@ void state_release(oh_state* st) {
     st->step_graphs.clear();
     DevBuf* all[] = {&st->pcm_stage, &st->mel_raw, &st->clip_meta, &st->xin, &st->x1, &st->x, &st->h, &st->qkv, &st->hid, &st->enc_f32,
                      &st->win_desc, &st->slot_ring, &st->xkv, &st->kself, &st->vself, &st->dx, &st->dh, &st->dqkv, &st->datt, &st->dq, &st->dhid, &st->logits,
-                     &st->dump_lp, &st->dump_p, &st->topk_dev, &st->beam_pairs, &st->resample_plan, &st->resample_in, &st->resample_out, &st->seq_dev, &st->rules_dev};
+                     &st->dump_lp, &st->dump_p, &st->topk_dev, &st->beam_pairs, &st->resample_plan, &st->resample_in, &st->resample_out, &st->level_pcm, &st->level_env, &st->level_aux, &st->seq_dev, &st->rules_dev};
     for (DevBuf* b : all) release(*b);
     if (st->pinned) cudaFreeHost(st->pinned);
     st->pinned = nullptr;

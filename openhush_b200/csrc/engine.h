@@ -180,6 +180,7 @@ struct oh_state {
     oh::DevBuf dx, dh, dqkv, datt, dq, dhid, logits, dump_lp, dump_p, topk_dev;
     int ld_logits = 0;
     oh::DevBuf resample_plan, resample_in, resample_out;  // pre-engine DSP (resample.cu): chunk plan, staging of the host entry point
+    oh::DevBuf level_pcm, level_env, level_aux;           // level processing (preprocess.cu): host-entry staging, envelope scratch, n / gain / rms
     oh::DevBuf beam_pairs;         // beam search: (src line, dst line, positions) of the step's cache-line copies
     oh::DevBuf seq_dev;            // DecodeSeqState arrays
     oh::DevBuf rules_dev;
@@ -243,6 +244,8 @@ int resample_to_16k_device(oh_state* st, const void* d_pcm, int format, int bits
                            long long* out_n, cudaStream_t stream);
 
 int chunk_rms_db_device(const float* d_pcm, int chunk, int n_chunks, float* d_out, cudaStream_t stream);
+int preprocess_levels_device(float* d_pcm, long long stride, const int* d_n, int batch, int max_n, const oh_preprocess_params& p, float* d_work, float* d_gain,
+                             float* d_rms, cudaStream_t stream);
 
 int ensure(DevBuf& b, size_t bytes);
 void release(DevBuf& b);

@@ -103,6 +103,13 @@ struct AudioBuffer {
     float duration_secs() const { return (float)samples.size() / (float)sample_rate; }
 };
 
+// The fields of AudioConfig the worker's preprocess_audio reads (config.rs:956-975; defaults config.rs:984, 1129-1159,
+// 1239-1269: preprocessing off, its three stages on).  RNNoise noise reduction is a third-party model and not provided.
+struct AudioConfig {
+    bool preprocessing = false;
+    oh_preprocess_params levels = oh_preprocess_default_params();
+};
+
 template <class T>
 using Result = std::variant<T, WhisperError>;
 
@@ -215,6 +222,18 @@ class WhisperEngine {
         return out;
     }
     int max_batch() const { return max_batch_; }
+    // worker.rs:196-240 for the buffers of the jobs a worker drained: normalise / compress / limit on the device, in place,
+    // one oh_preprocess_pcm call for all of them.  Nothing runs unless config.preprocessing.
+    bool preprocess_audio(const std::vector<AudioBuffer*>& buffers, const AudioConfig& config) const {
+        if (!config.preprocessing || buffers.empty()) return true;
+        std::vector<float*> ptrs;
+        std::vector<int> ns;
+        for (AudioBuffer* b : buffers) {
+            ptrs.push_back(b->samples.data());
+            ns.push_back((int)b->samples.size());
+        }
+        return oh_preprocess_pcm(ctx_, state_, ptrs.data(), ns.data(), (int)buffers.size(), &config.levels, nullptr) == OH_OK;
+    }
     // whisper.rs:334-387
     BenchmarkResult benchmark(float safety_margin) const {
         AudioBuffer a;
@@ -268,10 +287,15 @@ struct JobResult {
     bool is_final;
     float duration_secs;
 };
-inline JobResult process_job(const WhisperEngine* engine, const TranscriptionJob& job) {
+inline JobResult process_job(const WhisperEngine* engine, const TranscriptionJob& job, const AudioConfig* audio_config = nullptr) {
     JobResult r{"", job.sequence_id, job.chunk_id, job.is_final, job.buffer.duration_secs()};
-    if (!engine) return r;  // worker.rs:125-142: no engine -> empty result, the tracker never stalls
-    auto res = engine->transcribe(job.buffer);
+    if (!engine) {  // worker.rs:125-142: no engine -> empty result with duration 0 (:136), the tracker never stalls
+        r.duration_secs = 0.0f;
+        return r;
+    }
+    AudioBuffer buffer = job.buffer;  // worker.rs:150-154: the job's buffer goes through preprocess_audio first
+    if (audio_config && !engine->preprocess_audio({&buffer}, *audio_config)) return r;
+    auto res = engine->transcribe(buffer);
     if (auto* ok = std::get_if<TranscriptionResult>(&res)) r.text = ok->text;  // worker.rs:159-165: error -> logged + empty text
     return r;
 }
@@ -339,7 +363,7 @@ class WorkerPool {
                 }
             }
             std::vector<JobResult> res;
-            for (auto& j : batch) res.push_back(JobResult{"", j.sequence_id, j.chunk_id, j.is_final, j.buffer.duration_secs()});
+            for (auto& j : batch) res.push_back(JobResult{"", j.sequence_id, j.chunk_id, j.is_final, eng ? j.buffer.duration_secs() : 0.0f});
             if (eng) {
                 std::vector<const AudioBuffer*> bufs;
                 for (auto& j : batch) bufs.push_back(&j.buffer);

@@ -42,7 +42,7 @@ int main(int argc, char** argv) {
         job.buffer.samples.assign(16000, 0.f);
         job.sequence_id = 9;
         JobResult jr = process_job(nullptr, job);
-        CHECK(jr.text.empty() && jr.sequence_id == 9 && std::fabs(jr.duration_secs - 1.0f) < 1e-6f);
+        CHECK(jr.text.empty() && jr.sequence_id == 9 && jr.duration_secs == 0.0f);  // worker.rs:136
     }
     {  // the reference's tracker unit tests (queue/mod.rs:324-466), same inputs and expected values
         auto res = [](uint64_t seq, uint32_t chunk, const char* text, bool fin) { return JobResult{text, seq, chunk, fin, 1.0f}; };
@@ -96,6 +96,31 @@ int main(int argc, char** argv) {
         printf("TEXT_LEN %zu LANG %s MS %llu\n", ok->text.size(), ok->language.c_str(), (unsigned long long)ok->duration_ms);
         BenchmarkResult b = eng->benchmark(0.2f);
         CHECK(b.test_audio_secs == 2.0f && b.recommended_chunk_interval >= b.overhead_secs);
+        {   // the worker's level-processing hook (worker.rs:196-240) through the mirror: off by default, on -> the engine
+            // sees a normalised / compressed / limited buffer (peak under the -1 dB ceiling, level up from -26 dB to about -19.6 dB)
+            AudioBuffer q = a;
+            AudioConfig off, on;
+            on.preprocessing = true;
+            CHECK(eng->preprocess_audio({&q}, off) && q.samples == a.samples);
+            CHECK(eng->preprocess_audio({&q}, on));
+            double ss0 = 0.0, ss1 = 0.0;
+            float peak = 0.0f;
+            for (int i = 0; i < n; ++i) {
+                ss0 += (double)a.samples[i] * a.samples[i];
+                ss1 += (double)q.samples[i] * q.samples[i];
+                peak = std::max(peak, std::fabs(q.samples[i]));
+            }
+            CHECK(peak <= std::pow(10.0f, -1.0f / 20.0f) + 1e-6f && ss1 > 3.5 * ss0 && ss1 < 5.5 * ss0);  // -26.0 dB -> -19.6 dB (oracle: x 4.38)
+            // two fresh engines (a state's first call is what sampled fallback tokens are defined against, oh_whisper.h)
+            auto f1 = WhisperEngine::create(argv[1], "en", false, true), f2 = WhisperEngine::create(argv[1], "en", false, true);
+            CHECK(std::get_if<std::unique_ptr<WhisperEngine>>(&f1) && std::get_if<std::unique_ptr<WhisperEngine>>(&f2));
+            TranscriptionJob job;
+            job.buffer = a;
+            JobResult with = process_job(std::get<std::unique_ptr<WhisperEngine>>(f1).get(), job, &on);
+            auto direct = std::get<std::unique_ptr<WhisperEngine>>(f2)->transcribe(q);
+            CHECK(std::get_if<TranscriptionResult>(&direct) && with.text == std::get<TranscriptionResult>(direct).text);
+            printf("PREPROCESS_OK peak %.4f\n", peak);
+        }
         a.samples[5] = NAN;
         auto bad = eng->transcribe(a);
         CHECK(std::get_if<WhisperError>(&bad) && std::get<WhisperError>(bad).kind == WhisperError::ValidationFailed);

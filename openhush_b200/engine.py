@@ -113,6 +113,69 @@ class AudioBuffer:
         return len(self.samples) / float(self.sample_rate)
 
 
+# ---------------------------------------------------------------------------------------------- config.rs (audio preprocessing)
+@dataclass
+class NormalizationConfig:  # config.rs:1016-1023, 1239-1246
+    enabled: bool = True
+    target_db: float = -18.0
+
+
+@dataclass
+class CompressionConfig:  # config.rs:1025-1044, 1248-1259
+    enabled: bool = True
+    threshold_db: float = -24.0
+    ratio: float = 4.0
+    attack_ms: float = 5.0
+    release_ms: float = 50.0
+    makeup_gain_db: float = 6.0
+
+
+@dataclass
+class LimiterConfig:  # config.rs:1046-1056, 1261-1269
+    enabled: bool = True
+    ceiling_db: float = -1.0
+    release_ms: float = 50.0
+
+
+@dataclass
+class NoiseReductionConfig:  # config.rs:993-1010 (RNNoise: a third-party model, not provided here)
+    enabled: bool = False
+    strength: float = 1.0
+
+
+@dataclass
+class AudioConfig:
+    """The fields of config.rs:932-990 that the worker's preprocess_audio reads (worker.rs:196-240).  `preprocessing` is
+    off by default, exactly as in the reference; the three stages are enabled by default once it is on."""
+    preprocessing: bool = False
+    normalization: NormalizationConfig = field(default_factory=NormalizationConfig)
+    compression: CompressionConfig = field(default_factory=CompressionConfig)
+    limiter: LimiterConfig = field(default_factory=LimiterConfig)
+    noise_reduction: NoiseReductionConfig = field(default_factory=NoiseReductionConfig)
+
+    def to_params(self):
+        """The C-ABI struct of oh_preprocess_pcm for this configuration."""
+        from ._abi import PreprocessParams
+        n, c, l = self.normalization, self.compression, self.limiter
+        return PreprocessParams(int(n.enabled), n.target_db, int(c.enabled), c.threshold_db, c.ratio, c.attack_ms, c.release_ms,
+                                c.makeup_gain_db, int(l.enabled), l.ceiling_db, l.release_ms)
+
+
+def preprocess_audio(state, buffers, config: AudioConfig):
+    """worker.rs:196-240 for a batch of AudioBuffers, in place, on the device: RMS normalisation, compression and the
+    limiter run as one call of oh_preprocess_pcm over all buffers (stages the configuration leaves disabled are skipped;
+    nothing runs at all unless `config.preprocessing`).  Returns the [n, 2] RMS levels (dB) before / after, or None.
+    Noise reduction (worker.rs:200-206) is the reference's RNNoise dependency and is not provided: asking for it raises."""
+    if config.noise_reduction.enabled:
+        raise NotImplementedError("noise_reduction (RNNoise) is not part of this library")
+    if not config.preprocessing or not buffers:
+        return None
+    clips, rms = state.preprocess([b.samples for b in buffers], config.to_params())
+    for b, c in zip(buffers, clips):
+        b.samples = c
+    return rms
+
+
 # ---------------------------------------------------------------------------------------------- engine/whisper.rs
 class WhisperError(Exception):
     pass
@@ -325,8 +388,15 @@ class TranscriptionWorker:
     """queue/worker.rs:85-193 reduced to the hot-path caller: one engine, jobs in, one result per job out — always,
     so the tracker never stalls (engine missing → empty text, engine error → logged + empty text)."""
 
-    def __init__(self, engine: WhisperEngine | None):
+    def __init__(self, engine: WhisperEngine | None, audio_config: AudioConfig | None = None):
         self.engine = engine
+        self.audio_config = audio_config or AudioConfig()  # worker.rs:52-53
+
+    def _preprocess(self, jobs):
+        """worker.rs:150-154: the buffers of the drained jobs go through preprocess_audio before the engine sees them (one
+        device call for all of them); a failure here is an engine-side error like any other: logged, empty text."""
+        if self.audio_config.preprocessing or self.audio_config.noise_reduction.enabled:
+            preprocess_audio(self.engine.state, [j.buffer for j in jobs], self.audio_config)
 
     def load_engine(self, engine: WhisperEngine):  # WorkerCommand::LoadEngine, worker.rs:100-103
         self.engine = engine
@@ -337,10 +407,11 @@ class TranscriptionWorker:
         self.engine = None
 
     def process_job(self, job: TranscriptionJob) -> JobResult:
-        dur = job.buffer.duration_secs()
+        dur = job.buffer.duration_secs() if self.engine is not None else 0.0  # worker.rs:136: no engine -> duration 0
         text, segs = "", []
         if self.engine is not None:
             try:
+                self._preprocess([job])
                 res = self.engine.transcribe(job.buffer)
                 text, segs = res.text, res.segments
             except Exception:  # worker.rs:161-164: any engine error is logged and answered with an empty text
@@ -353,6 +424,7 @@ class TranscriptionWorker:
         if self.engine is None or len(jobs) == 1 or not hasattr(self.engine, "transcribe_batch"):
             return [self.process_job(j) for j in jobs]
         try:
+            self._preprocess(jobs)
             res = self.engine.transcribe_batch([j.buffer for j in jobs])
         except Exception:
             res = [None] * len(jobs)

@@ -11,6 +11,7 @@ import subprocess
 
 import numpy as np
 
+from . import _abi
 from ._abi import ContextParams, FullParams, Timings
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -73,6 +74,9 @@ SYMBOLS = {
     "oh_load_pcm_16k": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong, _vp, C.c_longlong, C.POINTER(C.c_longlong)]),
     "oh_load_pcm_16k_device": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong, _vp, C.c_longlong, C.POINTER(C.c_longlong)]),
     "oh_chunk_rms_db": (C.c_int, [_vp, _vp, _vp, C.c_longlong, C.c_int, _vp, C.c_int]),
+    "oh_preprocess_default_params": (_abi.PreprocessParams, []),
+    "oh_preprocess_pcm": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.POINTER(_abi.PreprocessParams), _vp]),
+    "oh_preprocess_pcm_device": (C.c_int, [_vp, _vp, _vp, C.c_longlong, _vp, C.c_int, C.POINTER(_abi.PreprocessParams), _vp]),
     "oh_pcm_to_mel_batch": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp, _vp]),
     "oh_pcm_to_mel_device": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp]),
     "oh_encode_batch": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp]),
@@ -254,6 +258,29 @@ class State:
         if rc != 0:
             raise OhError(f"oh_load_pcm_16k rc={rc}: " + self.lib.oh_last_error().decode(errors="replace"))
         return out[:got.value]
+
+    def preprocess(self, clips, params=None):
+        """Level processing of 16 kHz f32 clips on the device (the worker's preprocess_audio hook: RMS normalisation,
+        compression, limiter — each if enabled in `params`).  Returns (processed clips, [batch, 2] RMS dB before / after)."""
+        params = params or _abi.default_preprocess_params()
+        clips = [np.array(c, dtype=np.float32, copy=True) for c in clips]
+        ptrs = (C.c_void_p * len(clips))(*[c.ctypes.data for c in clips])
+        ns = (C.c_int * len(clips))(*[len(c) for c in clips])
+        rms = np.zeros((len(clips), 2), dtype=np.float32)
+        rc = self.lib.oh_preprocess_pcm(self.ctx.h, self.h, ptrs, ns, len(clips), C.byref(params), rms.ctypes.data)
+        if rc != 0:
+            raise OhError(f"oh_preprocess_pcm rc={rc}: " + self.lib.oh_last_error().decode(errors="replace"))
+        return clips, rms
+
+    def preprocess_device(self, d_pcm_ptr: int, stride: int, n_samples, params=None):
+        """Same on a device-resident [batch][stride] f32 array (in place, on the state's stream)."""
+        params = params or _abi.default_preprocess_params()
+        ns = (C.c_int * len(n_samples))(*[int(n) for n in n_samples])
+        rms = np.zeros((len(n_samples), 2), dtype=np.float32)
+        rc = self.lib.oh_preprocess_pcm_device(self.ctx.h, self.h, C.c_void_p(d_pcm_ptr), stride, ns, len(n_samples), C.byref(params), rms.ctypes.data)
+        if rc != 0:
+            raise OhError(f"oh_preprocess_pcm_device rc={rc}: " + self.lib.oh_last_error().decode(errors="replace"))
+        return rms
 
     # ---- stages
     def pcm_to_mel(self, clips):

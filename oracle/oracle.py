@@ -75,6 +75,12 @@ def lib():
             "orc_mono_mix": (None, [vp, C.c_int, C.c_int, C.c_int, C.c_longlong, vp]),
             "orc_resample_sinc": (C.c_longlong, [vp, C.c_longlong, C.c_int, C.c_int, vp, C.c_longlong]),
             "orc_min_duration_padding": (C.c_longlong, [C.c_longlong]),
+            "orc_rms_db": (C.c_float, [vp, C.c_longlong]),
+            "orc_apply_gain": (None, [vp, C.c_longlong, C.c_float]),
+            "orc_normalize_rms": (None, [vp, C.c_longlong, C.c_float]),
+            "orc_compress": (None, [vp, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float]),
+            "orc_limit": (None, [vp, C.c_longlong, C.c_float, C.c_float]),
+            "orc_preprocess_audio": (None, [vp, C.c_longlong, vp, vp, vp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -100,6 +106,47 @@ def load_pcm_16k(frames: np.ndarray, sample_rate: int, bits: int = 0, pad: bool 
     if pad:
         out = np.concatenate([out, np.zeros(int(L.orc_min_duration_padding(len(out))), np.float32)])
     return out
+
+
+# ---- the worker's optional level processing (orc_preprocess.cpp; src/input/audio.rs:89-239, src/queue/worker.rs:196-240)
+def rms_db(x) -> float:
+    a = np.ascontiguousarray(x, dtype=np.float32)
+    return float(lib().orc_rms_db(a.ctypes.data, len(a)))
+
+
+def apply_gain(x, gain_db: float) -> np.ndarray:
+    a = np.array(x, dtype=np.float32, copy=True)
+    lib().orc_apply_gain(a.ctypes.data, len(a), gain_db)
+    return a
+
+
+def normalize_rms(x, target_db: float) -> np.ndarray:
+    a = np.array(x, dtype=np.float32, copy=True)
+    lib().orc_normalize_rms(a.ctypes.data, len(a), target_db)
+    return a
+
+
+def compress(x, threshold_db: float, ratio: float, attack_ms: float, release_ms: float, makeup_gain_db: float) -> np.ndarray:
+    a = np.array(x, dtype=np.float32, copy=True)
+    lib().orc_compress(a.ctypes.data, len(a), threshold_db, ratio, attack_ms, release_ms, makeup_gain_db)
+    return a
+
+
+def limit(x, ceiling_db: float, release_ms: float) -> np.ndarray:
+    a = np.array(x, dtype=np.float32, copy=True)
+    lib().orc_limit(a.ctypes.data, len(a), ceiling_db, release_ms)
+    return a
+
+
+def preprocess_audio(x, params):
+    """params: any object with the fields of oh_preprocess_params.  Returns (processed clip, (rms_db before, after))."""
+    a = np.array(x, dtype=np.float32, copy=True)
+    flags = np.array([params.normalize, params.compress, params.limit], dtype=np.int32)
+    v = np.array([params.target_db, params.threshold_db, params.ratio, params.attack_ms, params.release_ms, params.makeup_gain_db,
+                  params.ceiling_db, params.limiter_release_ms], dtype=np.float32)
+    rms = np.zeros(2, dtype=np.float32)
+    lib().orc_preprocess_audio(a.ctypes.data, len(a), flags.ctypes.data, v.ctypes.data, rms.ctypes.data)
+    return a, (float(rms[0]), float(rms[1]))
 
 
 class OracleModel:

@@ -98,6 +98,24 @@ pub struct oh_kernel_stat {
     pub work: f64,
 }
 
+/// Level processing between capture and the engine (`preprocess_audio`, src/queue/worker.rs:196-240); defaults are the
+/// reference's `NormalizationConfig` / `CompressionConfig` / `LimiterConfig` (src/config.rs:1129-1159, 1239-1269).
+#[repr(C)]
+#[derive(Debug, Clone, Copy)]
+pub struct oh_preprocess_params {
+    pub normalize: c_int,
+    pub target_db: c_float,
+    pub compress: c_int,
+    pub threshold_db: c_float,
+    pub ratio: c_float,
+    pub attack_ms: c_float,
+    pub release_ms: c_float,
+    pub makeup_gain_db: c_float,
+    pub limit: c_int,
+    pub ceiling_db: c_float,
+    pub limiter_release_ms: c_float,
+}
+
 extern "C" {
     // ---- lifecycle
     pub fn oh_context_default_params() -> oh_context_params;
@@ -162,6 +180,11 @@ extern "C" {
                                   sample_rate: c_int, n_frames: c_longlong, d_out: *mut f32, cap: c_longlong, out_n: *mut c_longlong) -> c_int;
     pub fn oh_chunk_rms_db(ctx: *mut oh_context, state: *mut oh_state, pcm: *const f32, n_samples: c_longlong, chunk: c_int, out: *mut f32,
                            n_chunks: c_int) -> c_int;
+    pub fn oh_preprocess_default_params() -> oh_preprocess_params;
+    pub fn oh_preprocess_pcm(ctx: *mut oh_context, state: *mut oh_state, pcm: *const *mut f32, n_samples: *const c_int, batch: c_int,
+                             params: *const oh_preprocess_params, rms_db: *mut f32) -> c_int;
+    pub fn oh_preprocess_pcm_device(ctx: *mut oh_context, state: *mut oh_state, d_pcm: *mut f32, stride: c_longlong, n_samples: *const c_int,
+                                    batch: c_int, params: *const oh_preprocess_params, rms_db: *mut f32) -> c_int;
     // ---- stage entry points
     pub fn oh_pcm_to_mel_batch(ctx: *mut oh_context, state: *mut oh_state, samples: *const *const f32, n_samples: *const c_int, batch: c_int,
                                out_mel: *const *mut f32, out_n_len: *mut c_int) -> c_int;

@@ -84,6 +84,7 @@ def test_rust_sys_crate_declares_every_symbol():
     assert rust_fields("oh_context_params") == [n for n, _ in _abi.ContextParams._fields_]
     assert rust_fields("oh_timings") == [n for n, _ in _abi.Timings._fields_]
     assert rust_fields("oh_kernel_stat") == [n for n, _ in _abi.KernelStat._fields_]
+    assert rust_fields("oh_preprocess_params") == [n for n, _ in _abi.PreprocessParams._fields_]
     hdr = open(os.path.join(ROOT, "include", "oh_whisper.h")).read()
     body = re.search(r"typedef struct oh_timings \{(.*?)\} oh_timings;", hdr, flags=re.S).group(1)
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)

@@ -76,7 +76,7 @@ def test_cpp_host_mirror_gpu(micro_path):
     import torch
     n_dev = min(torch.cuda.device_count(), 2)
     r = subprocess.run([exe, micro_path, "200000", "1", str(n_dev)], capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0 and "HOST_TEST_OK" in r.stdout and "TEXT_LEN" in r.stdout and f"POOL_OK workers={n_dev}" in r.stdout, r.stdout + r.stderr
+    assert r.returncode == 0 and "HOST_TEST_OK" in r.stdout and "TEXT_LEN" in r.stdout and "PREPROCESS_OK" in r.stdout and f"POOL_OK workers={n_dev}" in r.stdout, r.stdout + r.stderr
 
 
 def test_worker_pool_on_gpus_batches_jobs(micro_path):
