@@ -5,8 +5,12 @@
 //   2. AudioBuffer::compress        audio.rs:139-198   attack / release envelope follower, gain above the threshold, make-up gain
 //   3. AudioBuffer::limit           audio.rs:200-239   instant attack, smoothed release towards 1
 // Two of the three carry a recurrence over the samples whose coefficient depends on the data (|x| > envelope picks attack or
-// release; target < gain picks the instant attack), so they do not reduce to a scan: they run one thread per clip, 32 clips
-// per warp, every lane walking its own clip (a lane's 32-byte sectors are re-used by its next seven samples out of L1).
+// release; target < gain picks the instant attack), so they do not reduce to a scan: a clip is walked sample by sample by ONE
+// lane, and the cost of a pass is the length of that dependent chain (about a dozen cycles per sample).  A warp owns a clip:
+// all 32 lanes move the data (the next 1024-sample tile is in flight in registers while the current one is worked on,
+// finished tiles are stored coalesced) and compute the per-sample terms that do not depend on the recurrence's state (the
+// limiter's division among them); lane 0 then runs the recurrence over the tile out of shared memory — so little besides
+// the chain itself is serial, and clips run side by side on as many warps as there are clips.
 // Everything that is not on a recurrence — the compressor's log10 / pow gain curve, the gain products — is a plain
 // element-wise kernel in between; the three passes alternate between the clip and one scratch array, so each reads one buffer
 // (read-only path) and writes the other.  Arithmetic follows the reference operation by operation in f32 (separate multiplies and
@@ -35,32 +39,103 @@ __device__ __forceinline__ float rms_db_of(float sum_squares, int n) {
     return rms > 0.0f ? __fmul_rn(20.0f, log10f(rms)) : -INFINITY;
 }
 
-// pass A, one thread per clip: RMS before, the normalisation gain, the compressor's envelope (written to `env`)
-__global__ void __launch_bounds__(32) level_envelope_kernel(const float* __restrict__ pcm, long long stride, const int* __restrict__ n_samples, int batch,
-                                                            LevelCoeffs c, float* __restrict__ env, float* __restrict__ gain_out,
-                                                            float* __restrict__ rms_out) {
-    const int b = blockIdx.x * 32 + threadIdx.x;
+constexpr int LV_TILE = 1024, LV_WARPS = 4;
+
+// One warp sweeps one clip.  Per sample, `prep(v)` computes what does not depend on the recurrence's state — all 32 lanes
+// do that for a whole tile at once (the limiter's division lives here) — and `step(v, aux)` advances the state and returns
+// the value to store (kStore); lane 0 calls it in sample order, so a tile's only serial part is the chain itself.  The
+// tile buffer is updated in place.
+template <bool kStore, class P, class F>
+__device__ __forceinline__ void warp_sweep(const float* __restrict__ src, float* __restrict__ dst, int n, float* s_buf, float* s_aux, int lane, P&& prep,
+                                           F&& step) {
+    float nxt[LV_TILE / 32];
+    auto fetch = [&](int t0) {
+#pragma unroll
+        for (int k = 0; k < LV_TILE / 32; ++k) {
+            const int idx = t0 + k * 32 + lane;
+            nxt[k] = idx < n ? src[idx] : 0.0f;
+        }
+    };
+    fetch(0);
+    for (int t0 = 0; t0 < n; t0 += LV_TILE) {
+#pragma unroll
+        for (int k = 0; k < LV_TILE / 32; ++k) {
+            s_buf[k * 32 + lane] = nxt[k];
+            s_aux[k * 32 + lane] = prep(nxt[k]);
+        }
+        __syncwarp();
+        if (t0 + LV_TILE < n) fetch(t0 + LV_TILE);  // lands while lane 0 walks the current tile
+        if (lane == 0) {
+            const int m = min(LV_TILE, n - t0);
+            int i0 = 0;
+            for (; i0 + 8 <= m; i0 += 8) {  // full groups: straight-line code
+                float v[8], a[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    v[k] = s_buf[i0 + k];
+                    a[k] = s_aux[i0 + k];
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = step(v[k], a[k]);
+                if (kStore) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) s_buf[i0 + k] = v[k];
+                }
+            }
+            for (; i0 < m; ++i0) {  // the clip's last few samples
+                const float o = step(s_buf[i0], s_aux[i0]);
+                if (kStore) s_buf[i0] = o;
+            }
+        }
+        __syncwarp();
+        if (kStore) {
+#pragma unroll
+            for (int k = 0; k < LV_TILE / 32; ++k) {
+                const int idx = t0 + k * 32 + lane;
+                if (idx < n) dst[idx] = s_buf[k * 32 + lane];
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// pass A, one warp per clip: RMS before, the normalisation gain, the compressor's envelope (written to `env`)
+__global__ void __launch_bounds__(32 * LV_WARPS) level_envelope_kernel(const float* __restrict__ pcm, long long stride, const int* __restrict__ n_samples,
+                                                                       int batch, LevelCoeffs c, float* __restrict__ env, float* __restrict__ gain_out,
+                                                                       float* __restrict__ rms_out) {
+    __shared__ float s_tile[LV_WARPS][LV_TILE], s_aux[LV_WARPS][LV_TILE];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * LV_WARPS + warp;
     if (b >= batch) return;
     const int n = n_samples[b];
     const float* x = pcm + (size_t)b * stride;
     float sum = 0.0f;
-    for (int i = 0; i < n; ++i) sum = __fadd_rn(sum, __fmul_rn(x[i], x[i]));
-    const float before = rms_db_of(sum, n);
+    warp_sweep<false>(
+        x, nullptr, n, s_tile[warp], s_aux[warp], lane, [&](float v) { return __fmul_rn(v, v); },
+        [&](float, float sq) {
+            sum = __fadd_rn(sum, sq);
+            return 0.0f;
+        });
     float gain = 1.0f;
-    if (c.normalize && isfinite(before)) gain = powf(10.0f, __fdiv_rn(__fsub_rn(c.target_db, before), 20.0f));  // audio.rs:112-113, 125
-    gain_out[b] = gain;
-    if (rms_out) rms_out[2 * b] = before;
+    if (lane == 0) {  // lane 0's sum is the clip's
+        const float before = rms_db_of(sum, n);
+        if (c.normalize && isfinite(before)) gain = powf(10.0f, __fdiv_rn(__fsub_rn(c.target_db, before), 20.0f));  // audio.rs:112-113, 125
+        gain_out[b] = gain;
+        if (rms_out) rms_out[2 * b] = before;
+    }
     if (!c.compress) return;
-    float* e = env + (size_t)b * stride;
+    gain = __shfl_sync(0xffffffffu, gain, 0);
     float envelope = 0.0f;
     const float a1 = __fsub_rn(1.0f, c.attack_coeff), r1 = __fsub_rn(1.0f, c.release_coeff);
-    for (int i = 0; i < n; ++i) {
-        const float in = fabsf(__fmul_rn(x[i], gain));  // the compressor sees the normalised sample
-        const float up = __fadd_rn(__fmul_rn(c.attack_coeff, envelope), __fmul_rn(a1, in));
-        const float down = __fadd_rn(__fmul_rn(c.release_coeff, envelope), __fmul_rn(r1, in));
-        envelope = in > envelope ? up : down;  // audio.rs:166-170
-        e[i] = envelope;
-    }
+    warp_sweep<true>(
+        x, env + (size_t)b * stride, n, s_tile[warp], s_aux[warp], lane,
+        [&](float v) { return fabsf(__fmul_rn(v, gain)); },  // the compressor sees the normalised sample
+        [&](float, float in) {
+            const float up = __fadd_rn(__fmul_rn(c.attack_coeff, envelope), __fmul_rn(a1, in));
+            const float down = __fadd_rn(__fmul_rn(c.release_coeff, envelope), __fmul_rn(r1, in));
+            envelope = in > envelope ? up : down;  // audio.rs:166-170
+            return envelope;
+        });
 }
 
 // pass B, element-wise: normalisation gain, compressor gain curve (audio.rs:173-182), make-up gain (audio.rs:186-188).
@@ -92,36 +167,33 @@ __global__ void __launch_bounds__(256) level_gain_kernel(const float* __restrict
     }
 }
 
-// pass C, one thread per clip: the limiter's gain recurrence (audio.rs:211-229) and the RMS after; `work` -> clip.
-// Eight samples are in registers before the recurrence touches the first, so the loads do not sit on its chain.
-__global__ void __launch_bounds__(32) level_limit_kernel(const float* __restrict__ work, float* __restrict__ pcm, long long stride,
-                                                         const int* __restrict__ n_samples, int batch, LevelCoeffs c, float* __restrict__ rms_out) {
-    const int b = blockIdx.x * 32 + threadIdx.x;
+// pass C, one warp per clip: the limiter's gain recurrence (audio.rs:211-229) and the RMS after; `work` -> clip
+__global__ void __launch_bounds__(32 * LV_WARPS) level_limit_kernel(const float* __restrict__ work, float* __restrict__ pcm, long long stride,
+                                                                    const int* __restrict__ n_samples, int batch, LevelCoeffs c,
+                                                                    float* __restrict__ rms_out) {
+    __shared__ float s_tile[LV_WARPS][LV_TILE], s_aux[LV_WARPS][LV_TILE];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * LV_WARPS + warp;
     if (b >= batch) return;
     const int n = n_samples[b];
-    const float* src = work + (size_t)b * stride;
-    float* x = pcm + (size_t)b * stride;
     float gain_reduction = 1.0f, sum = 0.0f;
     const float r1 = __fsub_rn(1.0f, c.limiter_release_coeff);
-    for (int i0 = 0; i0 < n; i0 += 8) {
-        float v[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = i0 + k < n ? src[i0 + k] : 0.0f;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            if (i0 + k >= n) break;
+    warp_sweep<true>(
+        work + (size_t)b * stride, pcm + (size_t)b * stride, n, s_tile[warp], s_aux[warp], lane,
+        [&](float v) {  // the gain this sample asks for
+            const float in = fabsf(v);
+            return in > c.ceiling_linear ? __fdiv_rn(c.ceiling_linear, in) : 1.0f;
+        },
+        [&](float v, float target) {
             if (c.limit) {
-                const float in = fabsf(v[k]);
-                const float target = in > c.ceiling_linear ? __fdiv_rn(c.ceiling_linear, in) : 1.0f;
                 const float rel = __fadd_rn(__fmul_rn(c.limiter_release_coeff, gain_reduction), __fmul_rn(r1, target));
                 gain_reduction = target < gain_reduction ? target : rel;
-                v[k] = __fmul_rn(v[k], gain_reduction);
+                v = __fmul_rn(v, gain_reduction);
             }
-            x[i0 + k] = v[k];
-            sum = __fadd_rn(sum, __fmul_rn(v[k], v[k]));
-        }
-    }
-    if (rms_out) rms_out[2 * b + 1] = rms_db_of(sum, n);
+            sum = __fadd_rn(sum, __fmul_rn(v, v));
+            return v;
+        });
+    if (lane == 0 && rms_out) rms_out[2 * b + 1] = rms_db_of(sum, n);
 }
 
 }  // namespace
@@ -146,12 +218,12 @@ int preprocess_levels_device(float* d_pcm, long long stride, const int* d_n, int
     c.ceiling_linear = std::pow(10.0f, p.ceiling_db / 20.0f);
     c.limiter_release_coeff = std::exp(-1.0f / (p.limiter_release_ms * sr / 1000.0f));
     ProfScope ps(PC_RESAMPLE, 0.0, stream);
-    level_envelope_kernel<<<(batch + 31) / 32, 32, 0, stream>>>(d_pcm, stride, d_n, batch, c, d_work, d_gain, d_rms);
+    level_envelope_kernel<<<(batch + LV_WARPS - 1) / LV_WARPS, 32 * LV_WARPS, 0, stream>>>(d_pcm, stride, d_n, batch, c, d_work, d_gain, d_rms);
     OH_COUNT_LAUNCH();
     const int gx = std::max(1, std::min((max_n + 255) / 256, 1184 / std::max(batch, 1) + 1));  // about eight CTAs per SM over the batch
     level_gain_kernel<<<dim3(gx, batch), 256, 0, stream>>>(d_pcm, stride, d_n, c, d_work, d_gain);
     OH_COUNT_LAUNCH();
-    level_limit_kernel<<<(batch + 31) / 32, 32, 0, stream>>>(d_work, d_pcm, stride, d_n, batch, c, d_rms);
+    level_limit_kernel<<<(batch + LV_WARPS - 1) / LV_WARPS, 32 * LV_WARPS, 0, stream>>>(d_work, d_pcm, stride, d_n, batch, c, d_rms);
     OH_COUNT_LAUNCH();
     OH_CUDA_CHECK(cudaGetLastError());
     return OH_OK;

@@ -295,3 +295,32 @@ impl BatchExt for WhisperState {
         Ok(self.collect(n_jobs))
     }
 }
+
+// ------------------------------------------------------------------------------------------------ additive: level processing
+/// The worker's `preprocess_audio` hook (/root/reference/src/queue/worker.rs:196-240) on the GPU: RMS normalisation,
+/// compression and the limiter of `AudioBuffer` (/root/reference/src/input/audio.rs:108-239) over the buffers of the jobs a
+/// worker drained, in place, in one call.  `params` is filled from the reference's `AudioConfig`
+/// (`normalization` / `compression` / `limiter`; see `LevelParams::from_config` in INTEGRATION.md); the caller keeps the
+/// `if !config.preprocessing { return; }` of the reference.  RNNoise noise reduction stays where it is (host side).
+pub type LevelParams = sys::oh_preprocess_params;
+
+pub trait PreprocessExt {
+    /// Returns the RMS level in dB before and after, per buffer (what the reference logs at worker.rs:210 and :236).
+    fn preprocess_audio(&mut self, buffers: &mut [&mut [f32]], params: &LevelParams) -> Result<Vec<(f32, f32)>, WhisperError>;
+}
+impl PreprocessExt for WhisperState {
+    fn preprocess_audio(&mut self, buffers: &mut [&mut [f32]], params: &LevelParams) -> Result<Vec<(f32, f32)>, WhisperError> {
+        let ptrs: Vec<*mut f32> = buffers.iter_mut().map(|b| b.as_mut_ptr()).collect();
+        let lens: Vec<c_int> = buffers.iter().map(|b| b.len() as c_int).collect();
+        let mut rms = vec![0.0f32; 2 * buffers.len()];
+        map_rc(unsafe {
+            sys::oh_preprocess_pcm(self.ctx.0, self.state, ptrs.as_ptr(), lens.as_ptr(), buffers.len() as c_int, params, rms.as_mut_ptr())
+        })?;
+        Ok(rms.chunks(2).map(|c| (c[0], c[1])).collect())
+    }
+}
+
+/// Defaults of the reference's configuration (src/config.rs:1129-1159, 1239-1269).
+pub fn default_level_params() -> LevelParams {
+    unsafe { sys::oh_preprocess_default_params() }
+}
