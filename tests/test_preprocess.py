@@ -76,6 +76,19 @@ def test_oracle_stage_details():
     assert np.abs(got).max() <= 10.0 ** (-1.0 / 20.0) + 1e-6
 
 
+def _golden():
+    return np.load(os.path.join(ROOT, "tests", "golden", "oracle_levels.npz"))
+
+
+def test_oracle_reproduces_its_frozen_outputs():
+    g, p = _golden(), _abi.default_preprocess_params()
+    for name in ("speech", "tone"):
+        y, rms = O.preprocess_audio(g[name + "_in"], p)
+        np.testing.assert_allclose(y, g[name + "_out"], rtol=1e-6, atol=1e-8)  # libm's last bits may differ between hosts
+        np.testing.assert_allclose(np.array(rms, np.float32), g[name + "_rms"], atol=1e-4)
+    assert np.abs(g["tone_out"]).max() <= 10.0 ** (-1.0 / 20.0) + 1e-6 < np.abs(g["tone_in"]).max()
+
+
 def test_params_mirror_the_reference_defaults_and_the_header():
     from openhush_b200 import lib
     p, q = lib.load().oh_preprocess_default_params(), _abi.default_preprocess_params()
@@ -144,6 +157,15 @@ def test_device_level_processing_matches_oracle(st):
     q = _abi.default_preprocess_params()
     q.normalize, q.limit, q.ratio = 0, 0, 1.0
     assert np.array_equal(st.preprocess(clips[:1], q)[0][0], clips[0])
+
+
+@pytest.mark.gpu
+def test_device_level_processing_matches_golden(st):
+    g, p = _golden(), _abi.default_preprocess_params()
+    got, rms = st.preprocess([g["speech_in"], g["tone_in"]], p)
+    for i, name in enumerate(("speech", "tone")):
+        _close(got[i], g[name + "_out"])
+        np.testing.assert_allclose(rms[i], g[name + "_rms"], atol=1e-3)
 
 
 @pytest.mark.gpu
