@@ -334,6 +334,33 @@ class WhisperEngine:
             out[i] = TranscriptionFailed(_FULL_ERRORS.get(item_rc, f"GenericError({item_rc})")) if item_rc != 0 else self._result_of_item(k, t0)
         return out
 
+    def submit_batch(self, audios):
+        """Stream form of transcribe_batch (oh_stream_submit): registers the jobs and returns a handle at once; the jobs
+        start sharing the decoder rows with those of earlier handles.  collect(handle) waits for them (oh_stream_wait) and
+        returns what transcribe_batch would have.  Handles are collected in the order they were submitted."""
+        out = [None] * len(audios)
+        clips, idx = [], []
+        for i, a in enumerate(audios):
+            try:
+                validate_audio(a.samples, a.sample_rate)
+            except AudioValidationError as e:
+                out[i] = ValidationFailed(e)
+                continue
+            clips.append(np.ascontiguousarray(a.samples, dtype=np.float32))
+            idx.append(i)
+        params = self._params()
+        ticket = self.state.stream_submit_clips(clips, params) if clips else None
+        return dict(ticket=ticket, out=out, idx=idx, params=params, t0=time.perf_counter())
+
+    def collect(self, handle) -> list:
+        out, idx = handle["out"], handle["idx"]
+        if handle["ticket"] is not None:
+            rc = self.state.stream_wait(handle["ticket"])
+            for k, i in enumerate(idx):
+                item_rc = rc if rc != 0 else self.state.item_rc(k)
+                out[i] = TranscriptionFailed(_FULL_ERRORS.get(item_rc, f"GenericError({item_rc})")) if item_rc != 0 else self._result_of_item(k, handle["t0"])
+        return out
+
     def benchmark(self, safety_margin: float) -> BenchmarkResult:
         """whisper.rs:334-387: 1 warm-up + 3 timed transcriptions of 2 s of silence."""
         audio = AudioBuffer(np.zeros(32000, np.float32), 16000)
@@ -418,6 +445,31 @@ class TranscriptionWorker:
                 text, segs = "", []
         return JobResult(text, job.sequence_id, job.chunk_id, job.is_final, dur, segs)
 
+    def _results(self, jobs, res) -> list:
+        out = []
+        for j, r in zip(jobs, res):
+            ok = isinstance(r, TranscriptionResult)
+            out.append(JobResult(r.text if ok else "", j.sequence_id, j.chunk_id, j.is_final, j.buffer.duration_secs(), r.segments if ok else []))
+        return out
+
+    def submit_jobs(self, jobs):
+        """Additive: process_jobs split in two for continuous batching across drains — the jobs are preprocessed and handed
+        to the engine's stream (oh_stream_submit) and the worker is free to drain and submit the next ones before it calls
+        collect_jobs for these, so the decoder rows do not run empty between drains.  Never raises: a failure becomes empty
+        texts at collect time (worker.rs:161-164)."""
+        try:
+            self._preprocess(jobs)
+            return self.engine.submit_batch([j.buffer for j in jobs])
+        except Exception:
+            return None
+
+    def collect_jobs(self, jobs, handle) -> list:
+        try:
+            res = self.engine.collect(handle) if handle is not None else [None] * len(jobs)
+        except Exception:
+            res = [None] * len(jobs)
+        return self._results(jobs, res)
+
     def process_jobs(self, jobs) -> list:
         """Additive: the jobs a worker drained from the queue (up to the engine's max_batch) as one batched engine call.
         One JobResult per job, always, in the order given."""
@@ -428,11 +480,7 @@ class TranscriptionWorker:
             res = self.engine.transcribe_batch([j.buffer for j in jobs])
         except Exception:
             res = [None] * len(jobs)
-        out = []
-        for j, r in zip(jobs, res):
-            ok = isinstance(r, TranscriptionResult)
-            out.append(JobResult(r.text if ok else "", j.sequence_id, j.chunk_id, j.is_final, j.buffer.duration_secs(), r.segments if ok else []))
-        return out
+        return self._results(jobs, res)
 
 
 def shard_jobs(n_jobs: int, rank: int, world: int):
@@ -474,7 +522,7 @@ class WorkerPool:
     thread answer every job with an empty text, which is the reference's rule for its single worker (worker.rs:125-142:
     the tracker must never stall)."""
 
-    def __init__(self, engines, max_batch: int | None = None):
+    def __init__(self, engines, max_batch: int | None = None, depth: int = 1):
         import queue
         import threading
         self.jobs: "queue.Queue" = queue.Queue()
@@ -483,6 +531,7 @@ class WorkerPool:
         self.jobs_done = [0] * len(engines)
         self.batches_done = [0] * len(engines)
         self._max_batch = max_batch
+        self._depth = max(0, depth)  # drains a worker may have in flight on its engine's stream beyond the one it collects next
         live = [i for i, e in enumerate(engines) if e is not None]
         consumers = live if live else list(range(min(1, len(engines))))
         self._threads = [threading.Thread(target=self._run, args=(i,), daemon=True) for i in consumers]
@@ -496,30 +545,65 @@ class WorkerPool:
         return max(1, getattr(ctx, "max_batch", 1))
 
     def _run(self, i: int):
+        """Drain up to `limit` jobs, hand them to the engine, answer.  With an engine that has the stream pair
+        (submit_batch / collect) the worker keeps `depth` drains in flight: it submits the next drain before it collects
+        the previous one (oh_stream_submit / oh_stream_wait), so the decoder rows stay busy across drains; it blocks on the
+        queue only when nothing is in flight."""
+        import collections
         import queue
         limit = self._batch_limit(i)
-        while True:
-            job = self.jobs.get()
-            if job is None:  # WorkerCommand::Shutdown
-                return
-            batch, stop = [job], False
-            while len(batch) < limit:
-                try:
-                    nxt = self.jobs.get_nowait()
-                except queue.Empty:
-                    break
-                if nxt is None:
-                    stop = True
-                    break
-                batch.append(nxt)
-            try:
-                results = self.workers[i].process_jobs(batch)
-            except Exception:  # a result per job, whatever happens: the tracker must never stall
-                results = [JobResult("", j.sequence_id, j.chunk_id, j.is_final, j.buffer.duration_secs(), []) for j in batch]
+        w = self.workers[i]
+        pipelined = self._depth > 0 and hasattr(w.engine, "submit_batch") and hasattr(w.engine, "collect")
+        inflight = collections.deque()
+        stop = False
+
+        def answer(batch, results):
             for r in results:
                 self.results.put(r)
             self.jobs_done[i] += len(batch)
             self.batches_done[i] += 1
+
+        def empty(batch):  # a result per job, whatever happens: the tracker must never stall
+            return [JobResult("", j.sequence_id, j.chunk_id, j.is_final, j.buffer.duration_secs(), []) for j in batch]
+
+        while True:
+            batch = []
+            if not stop and len(inflight) <= self._depth:
+                try:
+                    job = self.jobs.get(block=not inflight)
+                except queue.Empty:
+                    job = False
+                if job is None:  # WorkerCommand::Shutdown
+                    stop = True
+                elif job is not False:
+                    batch = [job]
+                    while len(batch) < limit:
+                        try:
+                            nxt = self.jobs.get_nowait()
+                        except queue.Empty:
+                            break
+                        if nxt is None:
+                            stop = True
+                            break
+                        batch.append(nxt)
+            if batch:
+                if pipelined:
+                    inflight.append((batch, w.submit_jobs(batch)))
+                else:
+                    try:
+                        results = w.process_jobs(batch)
+                    except Exception:
+                        results = empty(batch)
+                    answer(batch, results)
+                continue
+            if inflight:
+                batch, handle = inflight.popleft()
+                try:
+                    results = w.collect_jobs(batch, handle)
+                except Exception:
+                    results = empty(batch)
+                answer(batch, results)
+                continue
             if stop:
                 return
 

@@ -172,6 +172,60 @@ def test_worker_pool_shared_queue_and_ordered_handout():
     assert threading.active_count() < 20
 
 
+def test_worker_pool_keeps_drains_in_flight_on_a_stream_engine():
+    """An engine with the stream pair (submit_batch / collect over oh_stream_submit / oh_stream_wait) gets the next drain
+    submitted before the previous one is collected — at most `depth` beyond the one collected next — handles are collected
+    in submission order, a failing submit or collect costs only that drain's texts, and shutdown collects what is in flight."""
+    import numpy as np
+
+    from openhush_b200.engine import AudioBuffer, TranscriptionJob, TranscriptionResult, WorkerPool
+
+    class StreamEngine:
+        def __init__(self):
+            self.log, self.live, self.max_live, self.next_ticket = [], 0, 0, 0
+
+        def transcribe(self, audio):  # the single-job form must not be used by the pipelined worker
+            raise AssertionError("blocking path used")
+
+        def submit_batch(self, audios):
+            t = self.next_ticket
+            self.next_ticket += 1
+            self.live += 1
+            self.max_live = max(self.max_live, self.live)
+            self.log.append(("submit", t, len(audios)))
+            if any(len(a.samples) == 16000 + 9 for a in audios):
+                self.live -= 1
+                raise RuntimeError("submit failed")
+            return dict(ticket=t, audios=audios)
+
+        def collect(self, handle):
+            self.log.append(("collect", handle["ticket"]))
+            self.live -= 1
+            if any(len(a.samples) == 16000 + 17 for a in handle["audios"]):
+                raise RuntimeError("collect failed")
+            return [TranscriptionResult(f"n={len(a.samples)}", "en", 1, []) for a in handle["audios"]]
+
+    for depth in (1, 2):
+        eng = StreamEngine()
+        pool = WorkerPool([eng], max_batch=4, depth=depth)
+        tracker = TranscriptionTracker.new_ordered()
+        n = 26
+        for seq in range(n):
+            tracker.add_pending_with_config(seq, 0, 0, 0, BackpressureStrategy.WARN)
+            pool.submit(TranscriptionJob(AudioBuffer(np.zeros(16000 + seq, np.float32), 16000), seq))
+        got = pool.drain(n, tracker, timeout=30.0)
+        pool.shutdown()
+        assert [r.sequence_id for r in got] == list(range(n)) and sum(pool.jobs_done) == n
+        bad = {r.sequence_id for r in got if r.text == ""}
+        assert {9, 17} <= bad and len(bad) <= 8                          # only the drains holding job 9 / job 17 lose their texts
+        assert all(r.text == f"n={16000 + r.sequence_id}" for r in got if r.sequence_id not in bad)
+        assert eng.max_live <= depth + 1 and eng.live == 0
+        collected = [e[1] for e in eng.log if e[0] == "collect"]
+        assert collected == sorted(collected)                            # oldest handle first
+        if len([e for e in eng.log if e[0] == "submit"]) > 2:
+            assert eng.max_live >= 2                                     # a drain was submitted while another was in flight
+
+
 def test_worker_without_any_engine_still_answers_every_job():
     """The reference's single-worker rule (worker.rs:125-142): with no engine at all the tracker must not stall."""
     import numpy as np
