@@ -199,27 +199,53 @@ class WhisperEngine {
         if (language_ != "auto") p.language = language_.c_str();
         p.translate = translate_ ? 0 : 1;
         const int rc = oh_full_batch(ctx_, state_, p, ptrs.data(), lens.data(), (int)ptrs.size());
-        const uint64_t ms = (uint64_t)std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count();
-        for (size_t k = 0; k < idx.size(); ++k) {
-            const int item_rc = rc != 0 ? rc : oh_full_item_rc(state_, (int)k);
-            if (item_rc != 0) {
-                const char* name = item_rc == OH_ERR_MEL ? "UnableToCalculateSpectrogram" : item_rc == OH_ERR_ENCODE ? "FailedToEncode" : item_rc == OH_ERR_DECODE ? "FailedToDecode" : nullptr;
-                out[idx[k]] = WhisperError{WhisperError::TranscriptionFailed, name ? std::string(name) : "GenericError(" + std::to_string(item_rc) + ")"};
+        fill_results(out, idx, rc, t0);
+        return out;
+    }
+    // Stream form of transcribe_batch (oh_stream_submit / oh_stream_wait): submit_batch registers the jobs and returns at
+    // once — they start sharing the decoder rows with the jobs of earlier tickets — and collect() waits for them and gives
+    // what transcribe_batch would have.  Tickets are collected in the order they were submitted.
+    struct Pending {
+        int ticket = -1;
+        std::vector<Result<TranscriptionResult>> out;
+        std::vector<size_t> idx;
+        std::chrono::steady_clock::time_point t0;
+    };
+    Pending submit_batch(const std::vector<const AudioBuffer*>& audios) const {
+        Pending pd;
+        pd.out.resize(audios.size());
+        std::vector<const float*> ptrs;
+        std::vector<int> lens;
+        for (size_t i = 0; i < audios.size(); ++i) {
+            auto v = validate_audio(audios[i]->samples.data(), audios[i]->samples.size(), audios[i]->sample_rate);
+            if (auto* err = std::get_if<AudioValidationError>(&v)) {
+                pd.out[i] = WhisperError{WhisperError::ValidationFailed, err->message()};
                 continue;
             }
-            std::string text;
-            const int n = oh_full_n_segments_item(state_, (int)k);
-            for (int i = 0; i < n; ++i) {
-                const char* s = oh_full_get_segment_text_item(state_, (int)k, i);
-                if (s && valid_utf8(s)) text += s;
-            }
-            TranscriptionResult r;
-            r.text = trim(text);
-            r.language = language_ == "auto" ? "en" : language_;
-            r.duration_ms = ms;
-            out[idx[k]] = r;
+            ptrs.push_back(audios[i]->samples.data());
+            lens.push_back((int)audios[i]->samples.size());
+            pd.idx.push_back(i);
         }
-        return out;
+        pd.t0 = std::chrono::steady_clock::now();
+        if (ptrs.empty()) return pd;
+        oh_full_params p = oh_full_default_params(OH_SAMPLING_GREEDY);
+        p.greedy_best_of = 1;
+        if (language_ != "auto") p.language = language_.c_str();
+        p.translate = translate_ ? 0 : 1;
+        int ticket = -1;
+        const int rc = oh_stream_submit(ctx_, state_, p, ptrs.data(), lens.data(), (int)ptrs.size(), 0, &ticket);
+        if (rc != 0) {
+            for (size_t k : pd.idx) pd.out[k] = WhisperError{WhisperError::TranscriptionFailed, "GenericError(" + std::to_string(rc) + ")"};
+            pd.idx.clear();
+            return pd;
+        }
+        pd.ticket = ticket;
+        return pd;
+    }
+    std::vector<Result<TranscriptionResult>> collect(Pending& pd) const {
+        if (pd.ticket >= 0) fill_results(pd.out, pd.idx, oh_stream_wait(ctx_, state_, pd.ticket), pd.t0);
+        pd.ticket = -1;
+        return std::move(pd.out);
     }
     int max_batch() const { return max_batch_; }
     // worker.rs:196-240 for the buffers of the jobs a worker drained: normalise / compress / limit on the device, in place,
@@ -265,6 +291,30 @@ class WhisperEngine {
     static std::string trim(const std::string& s) {
         size_t a = s.find_first_not_of(" \t\r\n"), b = s.find_last_not_of(" \t\r\n");
         return a == std::string::npos ? std::string() : s.substr(a, b - a + 1);
+    }
+    // per-job results of the batched call that just completed on the state (rc: the call's own return code)
+    void fill_results(std::vector<Result<TranscriptionResult>>& out, const std::vector<size_t>& idx, int rc,
+                      std::chrono::steady_clock::time_point t0) const {
+        const uint64_t ms = (uint64_t)std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count();
+        for (size_t k = 0; k < idx.size(); ++k) {
+            const int item_rc = rc != 0 ? rc : oh_full_item_rc(state_, (int)k);
+            if (item_rc != 0) {
+                const char* name = item_rc == OH_ERR_MEL ? "UnableToCalculateSpectrogram" : item_rc == OH_ERR_ENCODE ? "FailedToEncode" : item_rc == OH_ERR_DECODE ? "FailedToDecode" : nullptr;
+                out[idx[k]] = WhisperError{WhisperError::TranscriptionFailed, name ? std::string(name) : "GenericError(" + std::to_string(item_rc) + ")"};
+                continue;
+            }
+            std::string text;
+            const int n = oh_full_n_segments_item(state_, (int)k);
+            for (int i = 0; i < n; ++i) {
+                const char* sgm = oh_full_get_segment_text_item(state_, (int)k, i);
+                if (sgm && valid_utf8(sgm)) text += sgm;
+            }
+            TranscriptionResult r;
+            r.text = trim(text);
+            r.language = language_ == "auto" ? "en" : language_;
+            r.duration_ms = ms;
+            out[idx[k]] = r;
+        }
     }
     oh_context* ctx_ = nullptr;
     oh_state* state_ = nullptr;
@@ -348,35 +398,57 @@ class WorkerPool {
     const std::vector<size_t>& jobs_done() const { return jobs_done_; }
 
   private:
+    // Drain up to max_batch jobs, hand them to the engine's stream, answer.  A worker keeps one drain in flight while it
+    // collects the previous one (oh_stream_submit / oh_stream_wait), so its decoder rows stay busy across drains; it blocks
+    // on the queue only when nothing is in flight.
     void run(size_t i) {
         const WhisperEngine* eng = engines_[i].get();
-        const size_t limit = eng ? (size_t)eng->max_batch() : 1;
-        while (true) {
-            std::vector<TranscriptionJob> batch;
-            {
-                std::unique_lock<std::mutex> lk(mu_);
-                cv_jobs_.wait(lk, [&] { return stop_ || !jobs_.empty(); });
-                if (jobs_.empty()) return;  // stop requested and nothing left
-                while (!jobs_.empty() && batch.size() < limit) {
-                    batch.push_back(std::move(jobs_.front()));
-                    jobs_.pop_front();
-                }
-            }
+        const size_t limit = eng ? (size_t)eng->max_batch() : 1, depth = 1;
+        std::deque<std::pair<std::vector<TranscriptionJob>, WhisperEngine::Pending>> inflight;
+        auto answer = [&](std::vector<TranscriptionJob>& batch, const std::vector<Result<TranscriptionResult>>* out) {
             std::vector<JobResult> res;
             for (auto& j : batch) res.push_back(JobResult{"", j.sequence_id, j.chunk_id, j.is_final, eng ? j.buffer.duration_secs() : 0.0f});
-            if (eng) {
-                std::vector<const AudioBuffer*> bufs;
-                for (auto& j : batch) bufs.push_back(&j.buffer);
-                auto out = eng->transcribe_batch(bufs);
-                for (size_t k = 0; k < out.size(); ++k)
-                    if (auto* ok = std::get_if<TranscriptionResult>(&out[k])) res[k].text = ok->text;  // error -> empty text (worker.rs:159-165)
-            }
+            if (out)
+                for (size_t k = 0; k < out->size() && k < res.size(); ++k)
+                    if (auto* ok = std::get_if<TranscriptionResult>(&(*out)[k])) res[k].text = ok->text;  // error -> empty text (worker.rs:159-165)
             {
                 std::lock_guard<std::mutex> lk(mu_);
                 for (auto& r : res) results_.push_back(std::move(r));
                 jobs_done_[i] += batch.size();
             }
             cv_results_.notify_all();
+        };
+        while (true) {
+            std::vector<TranscriptionJob> batch;
+            bool stopping = false;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                if (inflight.empty()) cv_jobs_.wait(lk, [&] { return stop_ || !jobs_.empty(); });
+                if (inflight.size() <= depth)
+                    while (!jobs_.empty() && batch.size() < limit) {
+                        batch.push_back(std::move(jobs_.front()));
+                        jobs_.pop_front();
+                    }
+                stopping = stop_ && jobs_.empty();
+            }
+            if (!batch.empty()) {
+                if (!eng) {
+                    answer(batch, nullptr);
+                    continue;
+                }
+                inflight.emplace_back(std::move(batch), WhisperEngine::Pending{});
+                std::vector<const AudioBuffer*> bufs;
+                for (auto& j : inflight.back().first) bufs.push_back(&j.buffer);
+                inflight.back().second = eng->submit_batch(bufs);
+                continue;
+            }
+            if (!inflight.empty()) {
+                auto out = eng->collect(inflight.front().second);
+                answer(inflight.front().first, &out);
+                inflight.pop_front();
+                continue;
+            }
+            if (stopping) return;
         }
     }
     std::vector<std::unique_ptr<WhisperEngine>> engines_;
