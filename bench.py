@@ -268,10 +268,17 @@ def main():
     host = torch.empty((n_sets * B, N_SAMPLES), dtype=torch.float32, pin_memory=True)
     hv = host.numpy()
     gen = synth._lib()
-    for q in range(n_sets):
-        for i in range(B):
-            w = (q * world + rank) * B + i
-            gen.ohgen_audio(w + 1, N_SAMPLES, hv[q * B + i].ctypes.data)
+
+    def fill_clips(rows, seeds):
+        """Synthetic windows into the rows of a pinned array; the generator is a C function (ctypes drops the GIL), one
+        clip per call, so the host cores of this rank work side by side — set-up time, not part of any timed region."""
+        from concurrent.futures import ThreadPoolExecutor
+        n_thr = max(1, min(16, (os.cpu_count() or 1) // max(world, 1)))
+        with ThreadPoolExecutor(n_thr) as ex:
+            list(ex.map(lambda rs: gen.ohgen_audio(int(rs[1]), N_SAMPLES, rs[0].ctypes.data), zip(rows, seeds)))
+
+    fill_clips([hv[q * B + i] for q in range(n_sets) for i in range(B)],
+               [(q * world + rank) * B + i + 1 for q in range(n_sets) for i in range(B)])
     dev = host.cuda(non_blocking=False)
     ns = [N_SAMPLES] * B
 
@@ -394,8 +401,7 @@ def main():
             mine = list(range(r, n_rec, n_ranks))
             buf = torch.empty((len(mine), N_SAMPLES), dtype=torch.float32, pin_memory=True)
             bv = buf.numpy()
-            for i, w in enumerate(mine):
-                gen.ohgen_audio(100000 + w + 1, N_SAMPLES, bv[i].ctypes.data)
+            fill_clips([bv[i] for i in range(len(mine))], [100000 + w + 1 for w in mine])
             dbuf = buf.cuda()
             pp = [dbuf.data_ptr() + i * N_SAMPLES * 4 for i in range(len(mine))]
             barrier()
