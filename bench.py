@@ -498,6 +498,18 @@ def main():
                         traffic_source=traffic_src, algorithmic_bytes_per_launch=src["work"] / src["launches"],
                         peak_source=pk["src"], share_of_step=top["total_ms"] / tot_ms, avg_launch_ms=src["total_ms"] / src["launches"],
                         launches=src["launches"], measured_on="decode steps with every row active (stage API), CUDA events on the launching stream")
+        if roof.get("bound") == "hbm" and roof.get("kernel") == "cross_attention_decode":
+            # Share of the TIMED region (graph replays, no per-launch events possible): the bytes the kernel had to move there —
+            # every armed row-step streams its window's K and V once per layer — at the rate measured above, over the wall
+            # time.  share_of_step comes from the event-bracketed step, where the small kernels are launch-bound and inflate
+            # the denominator; the ncu launch list in profiles/ is the third view (decode phase only, every row armed).
+            try:
+                row_layer_bytes = 2 * ctx.n_audio_ctx * ctx.n_text_state * 2
+                moved = float(cnt["asteps"]) * ctx.n_text_layer * row_layer_bytes
+                roof["bytes_moved_in_timed_region"] = moved
+                roof["share_of_timed_region"] = (moved / (roof["achieved"] * 1e9)) / (world * ms / 1e3)
+            except Exception:  # reporting only: never lose the line over it
+                pass
         kernels = {r["name"]: dict(ms=round(r["total_ms"], 3), launches=r["launches"], share=round(r["total_ms"] / tot_ms, 4),
                                    rate=(None if not r["work"] else
                                          round(r["work"] / (r["total_ms"] / 1e3) / 1e12, 2) if r["name"].startswith("gemm") or r["name"] == "attention_encoder"
