@@ -146,3 +146,94 @@ def merge_timed_segments(results, chunk_offsets_cs=None):
         clock = base + int(round(r.duration_secs * 100.0))
     out.sort(key=lambda s: (s[0], s[1]))
     return out
+
+
+# ---------------------------------------------------------------------------------------------- recording.rs: timed output
+def _ms_u32(secs: float) -> int:
+    """`(secs * 1000.0) as u32` on an f32 (recording.rs:178, :188): f32 product, truncation towards zero, saturating."""
+    import numpy as np
+    v = float(np.float32(secs) * np.float32(1000.0))
+    return 0 if not v > 0.0 else min(int(v), 0xFFFFFFFF)
+
+
+def format_timestamp(secs: float) -> str:  # recording.rs:167-173, HH:MM:SS
+    import numpy as np
+    v = float(np.float32(secs))
+    total = 0 if not v > 0.0 else min(int(v), 0xFFFFFFFF)
+    return f"{total // 3600:02d}:{(total % 3600) // 60:02d}:{total % 60:02d}"
+
+
+def format_srt_timestamp(secs: float) -> str:  # recording.rs:176-184, HH:MM:SS,mmm
+    ms = _ms_u32(secs)
+    return f"{ms // 3600000:02d}:{(ms % 3600000) // 60000:02d}:{(ms % 60000) // 1000:02d},{ms % 1000:03d}"
+
+
+def format_vtt_timestamp(secs: float) -> str:  # recording.rs:186-194, HH:MM:SS.mmm
+    ms = _ms_u32(secs)
+    return f"{ms // 3600000:02d}:{(ms % 3600000) // 60000:02d}:{(ms % 60000) // 1000:02d}.{ms % 1000:03d}"
+
+
+@dataclass
+class TranscribedSegment:
+    """recording.rs:117-165.  The reference fills start / end from the wall clock of the capture loop; here they come from
+    the model's own timestamps (oh_full_get_segment_t0 / t1 through merge_timed_segments) — SURVEY.md section 8f N1."""
+    start_secs: float
+    end_secs: float
+    text: str
+    speaker_id: int | None = None
+
+    def _spoken(self) -> str:
+        return f"<v Speaker {self.speaker_id}>{self.text}" if self.speaker_id is not None else self.text
+
+    def format_timestamped(self) -> str:
+        start = format_timestamp(self.start_secs)
+        return f"[{start}] Speaker {self.speaker_id}: {self.text}" if self.speaker_id is not None else f"[{start}] {self.text}"
+
+    def format_srt(self, index: int) -> str:
+        return f"{index}\n{format_srt_timestamp(self.start_secs)} --> {format_srt_timestamp(self.end_secs)}\n{self._spoken()}\n"
+
+    def format_vtt(self) -> str:
+        return f"{format_vtt_timestamp(self.start_secs)} --> {format_vtt_timestamp(self.end_secs)}\n{self._spoken()}\n"
+
+
+def transcribed_segments(merged) -> list:
+    """[(t0, t1, text)] in 10 ms units on the recording's clock (merge_timed_segments) -> TranscribedSegment list; empty
+    pieces are dropped and texts stripped, as the capture loop does before it stores a segment."""
+    out = []
+    for t0, t1, text in merged:
+        t = text.strip()
+        if t:
+            out.append(TranscribedSegment(t0 / 100.0, t1 / 100.0, t))
+    return out
+
+
+class OutputFormat(enum.Enum):  # recording.rs:72-101
+    TEXT = "text"
+    TIMESTAMPED = "timestamped"
+    SRT = "srt"
+    VTT = "vtt"
+
+    @staticmethod
+    def from_str(s: str) -> "OutputFormat":
+        key = s.lower()
+        for names, fmt in ((("text", "txt"), OutputFormat.TEXT), (("timestamped", "ts"), OutputFormat.TIMESTAMPED),
+                           (("srt", "subrip"), OutputFormat.SRT), (("vtt", "webvtt"), OutputFormat.VTT)):
+            if key in names:
+                return fmt
+        raise ValueError(f"Unknown format '{s}'. Use: text, timestamped, srt, vtt")
+
+
+def render_transcript(segments, output_format: OutputFormat = OutputFormat.TEXT) -> str:
+    """What RecordingSession::save_to_file writes (recording.rs:505-524) for a list of TranscribedSegments: plain text one
+    line per segment, timestamped lines, SRT entries numbered from 1, or WebVTT cues under the "WEBVTT" header."""
+    out = "WEBVTT\n\n" if output_format is OutputFormat.VTT else ""
+    for i, seg in enumerate(segments):
+        if output_format is OutputFormat.TEXT:
+            out += f"{seg.text}\n"
+        elif output_format is OutputFormat.TIMESTAMPED:
+            out += f"{seg.format_timestamped()}\n"
+        elif output_format is OutputFormat.SRT:
+            out += seg.format_srt(i + 1)
+        else:
+            out += seg.format_vtt()
+    return out

@@ -242,3 +242,35 @@ def test_worker_without_any_engine_still_answers_every_job():
     got = pool.drain(5, timeout=10.0)
     pool.shutdown()
     assert sorted(r.sequence_id for r in got) == list(range(5)) and all(r.text == "" for r in got)
+
+
+def test_timed_output_formats_from_model_timestamps():
+    """recording.rs:528-590 (the reference's own tests for the timestamp / segment formatters, same inputs and strings) and
+    the N1 extension: segments carry the model's (t0, t1) instead of the capture loop's wall clock."""
+    from types import SimpleNamespace
+
+    import pytest
+
+    from openhush_b200.tracker import (OutputFormat, TranscribedSegment, format_srt_timestamp, format_timestamp, format_vtt_timestamp,
+                                       render_transcript, transcribed_segments)
+    assert format_timestamp(0.0) == "00:00:00" and format_timestamp(61.0) == "00:01:01" and format_timestamp(3661.0) == "01:01:01"
+    assert format_srt_timestamp(0.0) == "00:00:00,000" and format_srt_timestamp(1.5) == "00:00:01,500"
+    assert format_srt_timestamp(3661.123) == "01:01:01,123"
+    assert format_vtt_timestamp(0.0) == "00:00:00.000" and format_vtt_timestamp(1.5) == "00:00:01.500"
+    assert OutputFormat.from_str("text") is OutputFormat.TEXT and OutputFormat.from_str("srt") is OutputFormat.SRT
+    assert OutputFormat.from_str("VTT") is OutputFormat.VTT and OutputFormat.from_str("ts") is OutputFormat.TIMESTAMPED
+    with pytest.raises(ValueError):
+        OutputFormat.from_str("invalid")
+    seg = TranscribedSegment(0.0, 5.0, "Hello world")
+    assert "[00:00:00]" in seg.format_timestamped()
+    assert "00:00:00,000 --> 00:00:05,000" in seg.format_srt(1) and "00:00:00.000 --> 00:00:05.000" in seg.format_vtt()
+    assert TranscribedSegment(1.0, 2.0, "hi", speaker_id=3).format_srt(2) == "2\n00:00:01,000 --> 00:00:02,000\n<v Speaker 3>hi\n"
+    # model timestamps (10 ms units, per chunk) -> recording clock -> subtitles
+    a = SimpleNamespace(chunk_id=0, duration_secs=30.0, segments=[(0, 250, " first words"), (250, 2900, " and more")])
+    b = SimpleNamespace(chunk_id=1, duration_secs=30.0, segments=[(10, 400, " next window"), (400, 400, "  ")])
+    segs = transcribed_segments(merge_timed_segments([b, a]))
+    assert [(s.start_secs, s.end_secs, s.text) for s in segs] == [(0.0, 2.5, "first words"), (2.5, 29.0, "and more"), (30.1, 34.0, "next window")]
+    assert render_transcript(segs, OutputFormat.SRT).startswith("1\n00:00:00,000 --> 00:00:02,500\nfirst words\n2\n00:00:02,500 --> 00:00:29,000\n")
+    assert render_transcript(segs, OutputFormat.VTT).startswith("WEBVTT\n\n00:00:00.000 --> 00:00:02.500\nfirst words\n")
+    assert render_transcript(segs, OutputFormat.TEXT) == "first words\nand more\nnext window\n"
+    assert render_transcript(segs, OutputFormat.TIMESTAMPED).splitlines()[2] == "[00:00:30] next window"
