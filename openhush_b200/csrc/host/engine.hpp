@@ -90,9 +90,14 @@ struct WhisperError {
         }
     }
 };
+struct TimedSegment {  // additive: the model's own segment times, 10 ms units, relative to the clip
+    int64_t t0 = 0, t1 = 0;
+    std::string text;
+};
 struct TranscriptionResult {
     std::string text, language;
     uint64_t duration_ms = 0;
+    std::vector<TimedSegment> segments;  // additive
 };
 struct BenchmarkResult {
     float overhead_secs, recommended_chunk_interval, test_audio_secs;
@@ -164,12 +169,14 @@ class WhisperEngine {
             return WhisperError{WhisperError::TranscriptionFailed, name ? std::string(name) : "GenericError(" + std::to_string(rc) + ")"};
         }
         std::string text;
+        TranscriptionResult r;
         const int n = oh_full_n_segments(state_);
         for (int i = 0; i < n; ++i) {
             const char* s = oh_full_get_segment_text(state_, i);
-            if (s && valid_utf8(s)) text += s;  // whisper.rs:276-280: invalid UTF-8 segments are skipped
+            if (!s || !valid_utf8(s)) continue;  // whisper.rs:276-280: invalid UTF-8 segments are skipped
+            text += s;
+            r.segments.push_back(TimedSegment{oh_full_get_segment_t0(state_, i), oh_full_get_segment_t1(state_, i), s});
         }
-        TranscriptionResult r;
         r.text = trim(text);
         r.language = language_ == "auto" ? "en" : language_;
         r.duration_ms = (uint64_t)std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count();
@@ -304,12 +311,14 @@ class WhisperEngine {
                 continue;
             }
             std::string text;
+            TranscriptionResult r;
             const int n = oh_full_n_segments_item(state_, (int)k);
             for (int i = 0; i < n; ++i) {
                 const char* sgm = oh_full_get_segment_text_item(state_, (int)k, i);
-                if (sgm && valid_utf8(sgm)) text += sgm;
+                if (!sgm || !valid_utf8(sgm)) continue;
+                text += sgm;
+                r.segments.push_back(TimedSegment{oh_full_get_segment_t0_item(state_, (int)k, i), oh_full_get_segment_t1_item(state_, (int)k, i), sgm});
             }
-            TranscriptionResult r;
             r.text = trim(text);
             r.language = language_ == "auto" ? "en" : language_;
             r.duration_ms = ms;
@@ -336,6 +345,7 @@ struct JobResult {
     uint32_t chunk_id;
     bool is_final;
     float duration_secs;
+    std::vector<TimedSegment> segments;  // additive: (t0, t1, text) of the chunk, 10 ms units, chunk-relative
 };
 inline JobResult process_job(const WhisperEngine* engine, const TranscriptionJob& job, const AudioConfig* audio_config = nullptr) {
     JobResult r{"", job.sequence_id, job.chunk_id, job.is_final, job.buffer.duration_secs()};
@@ -346,7 +356,10 @@ inline JobResult process_job(const WhisperEngine* engine, const TranscriptionJob
     AudioBuffer buffer = job.buffer;  // worker.rs:150-154: the job's buffer goes through preprocess_audio first
     if (audio_config && !engine->preprocess_audio({&buffer}, *audio_config)) return r;
     auto res = engine->transcribe(buffer);
-    if (auto* ok = std::get_if<TranscriptionResult>(&res)) r.text = ok->text;  // worker.rs:159-165: error -> logged + empty text
+    if (auto* ok = std::get_if<TranscriptionResult>(&res)) {  // worker.rs:159-165: error -> logged + empty text
+        r.text = ok->text;
+        r.segments = ok->segments;
+    }
     return r;
 }
 
@@ -410,7 +423,10 @@ class WorkerPool {
             for (auto& j : batch) res.push_back(JobResult{"", j.sequence_id, j.chunk_id, j.is_final, eng ? j.buffer.duration_secs() : 0.0f});
             if (out)
                 for (size_t k = 0; k < out->size() && k < res.size(); ++k)
-                    if (auto* ok = std::get_if<TranscriptionResult>(&(*out)[k])) res[k].text = ok->text;  // error -> empty text (worker.rs:159-165)
+                    if (auto* ok = std::get_if<TranscriptionResult>(&(*out)[k])) {  // error -> empty text (worker.rs:159-165)
+                        res[k].text = ok->text;
+                        res[k].segments = ok->segments;
+                    }
             {
                 std::lock_guard<std::mutex> lk(mu_);
                 for (auto& r : res) results_.push_back(std::move(r));

@@ -79,6 +79,29 @@ int main(int argc, char** argv) {
         for (uint32_t c = 0; c < 4; ++c) CHECK(b3.add_pending_with_config(0, c, 3, 2, BackpressureStrategy::Warn));
         CHECK(b3.pending_count() == 4 && b3.stats().waiting_count == 0 && !b3.is_empty());
     }
+    {  // timed output: the reference's formatter tests (recording.rs:528-590) and the model-timestamp route (N1)
+        CHECK(format_timestamp(0.0f) == "00:00:00" && format_timestamp(61.0f) == "00:01:01" && format_timestamp(3661.0f) == "01:01:01");
+        CHECK(format_srt_timestamp(0.0f) == "00:00:00,000" && format_srt_timestamp(1.5f) == "00:00:01,500" && format_srt_timestamp(3661.123f) == "01:01:01,123");
+        CHECK(format_vtt_timestamp(0.0f) == "00:00:00.000" && format_vtt_timestamp(1.5f) == "00:00:01.500");
+        CHECK(output_format_from_str("text") == OutputFormat::Text && output_format_from_str("srt") == OutputFormat::Srt);
+        CHECK(output_format_from_str("VTT") == OutputFormat::Vtt && !output_format_from_str("invalid"));
+        TranscribedSegment seg;
+        seg.end_secs = 5.0f;
+        seg.text = "Hello world";
+        CHECK(seg.format_timestamped().find("[00:00:00]") != std::string::npos);
+        CHECK(seg.format_srt(1).find("00:00:00,000 --> 00:00:05,000") != std::string::npos);
+        CHECK(seg.format_vtt().find("00:00:00.000 --> 00:00:05.000") != std::string::npos);
+        JobResult a{"", 0, 0, false, 30.0f, {{0, 250, " first words"}, {250, 2900, " and more"}}};
+        JobResult b{"", 0, 1, true, 30.0f, {{10, 400, " next window"}, {400, 400, "  "}}};
+        auto segs = transcribed_segments(merge_timed_segments({b, a}));
+        CHECK(segs.size() == 3 && segs[0].text == "first words" && segs[1].start_secs == 2.5f && segs[1].end_secs == 29.0f);
+        CHECK(segs[2].text == "next window" && std::fabs(segs[2].start_secs - 30.1f) < 1e-4f && segs[2].end_secs == 34.0f);
+        CHECK(render_transcript(segs, OutputFormat::Srt).rfind("1\n00:00:00,000 --> 00:00:02,500\nfirst words\n2\n00:00:02,500 --> 00:00:29,000\n", 0) == 0);
+        CHECK(render_transcript(segs, OutputFormat::Vtt).rfind("WEBVTT\n\n00:00:00.000 --> 00:00:02.500\nfirst words\n", 0) == 0);
+        CHECK(render_transcript(segs, OutputFormat::Text) == "first words\nand more\nnext window\n");
+        std::map<uint32_t, int64_t> off{{0, 0}, {1, 2950}};
+        CHECK(merge_timed_segments({a, b}, &off)[2].t0 == 2960);
+    }
     if (argc >= 2) {
         auto r = WhisperEngine::create(argv[1], "en", false, argc >= 4 ? atoi(argv[3]) != 0 : true);
         if (auto* err = std::get_if<WhisperError>(&r)) {
@@ -93,7 +116,9 @@ int main(int argc, char** argv) {
         auto tr = eng->transcribe(a);
         auto* ok = std::get_if<TranscriptionResult>(&tr);
         CHECK(ok != nullptr);
-        printf("TEXT_LEN %zu LANG %s MS %llu\n", ok->text.size(), ok->language.c_str(), (unsigned long long)ok->duration_ms);
+        printf("TEXT_LEN %zu LANG %s MS %llu SEGMENTS %zu\n", ok->text.size(), ok->language.c_str(), (unsigned long long)ok->duration_ms, ok->segments.size());
+        CHECK((ok->text.empty() && ok->segments.empty()) || !ok->segments.empty());  // the text is the segments' texts, trimmed
+        for (size_t i = 0; i < ok->segments.size(); ++i) CHECK(ok->segments[i].t0 >= 0);  // the model's own times, 10 ms units
         BenchmarkResult b = eng->benchmark(0.2f);
         CHECK(b.test_audio_secs == 2.0f && b.recommended_chunk_interval >= b.overhead_secs);
         {   // the worker's level-processing hook (worker.rs:196-240) through the mirror: off by default, on -> the engine

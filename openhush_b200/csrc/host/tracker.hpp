@@ -4,7 +4,10 @@
 // ordered hand-out by sequence id.  Same names, arguments and results as the reference.
 #pragma once
 #include <algorithm>
+#include <cmath>
+#include <cstdio>
 #include <map>
+#include <optional>
 #include <set>
 #include <sstream>
 #include <string>
@@ -106,5 +109,96 @@ class TranscriptionTracker {
     bool streaming_;
     std::string last_text_suffix_;
 };
+
+// ---- timed output ---------------------------------------------------------------------------
+// Timed segments of one recording on a common clock: `results` are the JobResults of ONE sequence; chunk k starts where
+// chunk k-1 ended unless chunk_offsets_cs has an entry for it (overlapping capture, recording.rs:32).  10 ms units.
+inline std::vector<TimedSegment> merge_timed_segments(std::vector<JobResult> results, const std::map<uint32_t, int64_t>* chunk_offsets_cs = nullptr) {
+    std::sort(results.begin(), results.end(), [](const JobResult& a, const JobResult& b) { return a.chunk_id < b.chunk_id; });
+    std::vector<TimedSegment> out;
+    int64_t clock = 0;
+    for (const JobResult& r : results) {
+        int64_t base = clock;
+        if (chunk_offsets_cs) {
+            auto it = chunk_offsets_cs->find(r.chunk_id);
+            if (it != chunk_offsets_cs->end()) base = it->second;
+        }
+        for (const TimedSegment& s : r.segments) out.push_back(TimedSegment{base + s.t0, base + s.t1, s.text});
+        clock = base + (int64_t)std::llround((double)r.duration_secs * 100.0);
+    }
+    std::stable_sort(out.begin(), out.end(), [](const TimedSegment& a, const TimedSegment& b) { return a.t0 != b.t0 ? a.t0 < b.t0 : a.t1 < b.t1; });
+    return out;
+}
+
+// recording.rs:167-194: `secs as u32` / `(secs * 1000.0) as u32` on f32 (truncating, saturating at 0)
+inline std::string format_timestamp(float secs) {
+    const uint32_t total = secs > 0.0f ? (uint32_t)secs : 0u;
+    char buf[32];
+    snprintf(buf, sizeof buf, "%02u:%02u:%02u", total / 3600, (total % 3600) / 60, total % 60);
+    return buf;
+}
+inline std::string format_ms_timestamp(float secs, char sep) {
+    const float v = secs * 1000.0f;
+    const uint32_t ms = v > 0.0f ? (uint32_t)v : 0u;
+    char buf[40];
+    snprintf(buf, sizeof buf, "%02u:%02u:%02u%c%03u", ms / 3600000, (ms % 3600000) / 60000, (ms % 60000) / 1000, sep, ms % 1000);
+    return buf;
+}
+inline std::string format_srt_timestamp(float secs) { return format_ms_timestamp(secs, ','); }
+inline std::string format_vtt_timestamp(float secs) { return format_ms_timestamp(secs, '.'); }
+
+// recording.rs:117-165.  The reference fills start / end from the capture loop's wall clock (recording.rs:385-392); here
+// they come from the model's timestamps through merge_timed_segments.
+struct TranscribedSegment {
+    float start_secs = 0.0f, end_secs = 0.0f;
+    std::string text;
+    std::optional<uint32_t> speaker_id;
+    std::string spoken() const { return speaker_id ? "<v Speaker " + std::to_string(*speaker_id) + ">" + text : text; }
+    std::string format_timestamped() const {
+        const std::string start = format_timestamp(start_secs);
+        return speaker_id ? "[" + start + "] Speaker " + std::to_string(*speaker_id) + ": " + text : "[" + start + "] " + text;
+    }
+    std::string format_srt(size_t index) const {
+        return std::to_string(index) + "\n" + format_srt_timestamp(start_secs) + " --> " + format_srt_timestamp(end_secs) + "\n" + spoken() + "\n";
+    }
+    std::string format_vtt() const { return format_vtt_timestamp(start_secs) + " --> " + format_vtt_timestamp(end_secs) + "\n" + spoken() + "\n"; }
+};
+
+inline std::vector<TranscribedSegment> transcribed_segments(const std::vector<TimedSegment>& merged) {
+    std::vector<TranscribedSegment> out;
+    for (const TimedSegment& s : merged) {
+        const size_t a = s.text.find_first_not_of(" \t\r\n"), b = s.text.find_last_not_of(" \t\r\n");
+        if (a == std::string::npos) continue;  // the capture loop stores no empty segment (recording.rs:386)
+        TranscribedSegment t;
+        t.start_secs = (float)s.t0 / 100.0f;
+        t.end_secs = (float)s.t1 / 100.0f;
+        t.text = s.text.substr(a, b - a + 1);
+        out.push_back(std::move(t));
+    }
+    return out;
+}
+
+enum class OutputFormat { Text, Timestamped, Srt, Vtt };  // recording.rs:72-101
+inline std::optional<OutputFormat> output_format_from_str(std::string s) {
+    std::transform(s.begin(), s.end(), s.begin(), [](unsigned char c) { return (char)std::tolower(c); });
+    if (s == "text" || s == "txt") return OutputFormat::Text;
+    if (s == "timestamped" || s == "ts") return OutputFormat::Timestamped;
+    if (s == "srt" || s == "subrip") return OutputFormat::Srt;
+    if (s == "vtt" || s == "webvtt") return OutputFormat::Vtt;
+    return std::nullopt;
+}
+// what RecordingSession::save_to_file writes (recording.rs:505-524)
+inline std::string render_transcript(const std::vector<TranscribedSegment>& segments, OutputFormat format) {
+    std::string out = format == OutputFormat::Vtt ? "WEBVTT\n\n" : "";
+    for (size_t i = 0; i < segments.size(); ++i) {
+        switch (format) {
+            case OutputFormat::Text: out += segments[i].text + "\n"; break;
+            case OutputFormat::Timestamped: out += segments[i].format_timestamped() + "\n"; break;
+            case OutputFormat::Srt: out += segments[i].format_srt(i + 1); break;
+            case OutputFormat::Vtt: out += segments[i].format_vtt(); break;
+        }
+    }
+    return out;
+}
 
 }  // namespace openhush
