@@ -6,6 +6,7 @@
 
 #include "engine.hpp"
 #include "tracker.hpp"
+#include "vad.hpp"
 
 using namespace openhush;
 #define CHECK(c)                                                          \
@@ -101,6 +102,41 @@ int main(int argc, char** argv) {
         CHECK(render_transcript(segs, OutputFormat::Text) == "first words\nand more\nnext window\n");
         std::map<uint32_t, int64_t> off{{0, 0}, {1, 2950}};
         CHECK(merge_timed_segments({a, b}, &off)[2].t0 == 2960);
+    }
+    {  // VAD state machine: the reference's unit tests (vad/mod.rs:250-315), defaults, the daemon's job cut
+        VadConfig c1;
+        c1.min_silence_ms = 100;
+        c1.min_speech_ms = 50;
+        VadState s1(c1, 16000);
+        const VadResult speech{0.8f, true}, silence{0.1f, false};
+        CHECK(!s1.update(speech, 512) && s1.is_speech());
+        CHECK(!s1.update(speech, 512));
+        CHECK(!s1.update(silence, 512) && s1.is_speech());  // brief silence: not enough to end
+        auto seg = s1.update(silence, 1600);                // more silence: the segment is returned
+        CHECK(seg && !s1.is_speech() && seg->start == 0 && seg->end == 1536 && std::fabs(seg->avg_probability - 0.45f) < 1e-6f);
+        VadConfig c2;
+        c2.min_silence_ms = 100;
+        c2.min_speech_ms = 500;
+        VadState s2(c2, 16000);
+        s2.update(speech, 512);
+        CHECK(!s2.update(silence, 3200));                   // too short: dropped
+        VadConfig d;
+        CHECK(!d.enabled && d.threshold == 0.5f && d.min_silence_ms == 700 && d.min_speech_ms == 250 && d.speech_pad_ms == 30);
+        VadState s3(d);
+        s3.update(VadResult{0.9f, true}, 512);
+        s3.reset();
+        CHECK(!s3.is_speech() && s3.total_samples() == 0);
+        // two bursts of speech separated by silence -> two jobs, each up to where the closing 700 ms of silence was noticed
+        const size_t sr = 16000, ch = 512;
+        std::vector<float> x(sr * 8, 0.0f), probs(x.size() / ch, 0.05f);
+        auto burst = [&](double t0, double t1) {
+            for (size_t k = (size_t)(t0 * sr) / ch; k < (size_t)(t1 * sr) / ch; ++k) probs[k] = 0.9f;
+        };
+        burst(0.5, 2.0);
+        burst(3.5, 5.5);
+        auto jobs = speech_jobs(x, probs, VadConfig());
+        CHECK(jobs.size() == 2 && jobs[0].chunk_id == 0 && jobs[1].chunk_id == 1 && !jobs[0].is_final && !jobs[1].is_final);
+        CHECK(std::fabs(jobs[0].buffer.duration_secs() - 2.2f) < 0.07f && std::fabs(jobs[1].buffer.duration_secs() - 2.7f) < 0.07f);
     }
     if (argc >= 2) {
         auto r = WhisperEngine::create(argv[1], "en", false, argc >= 4 ? atoi(argv[3]) != 0 : true);
